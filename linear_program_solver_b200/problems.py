@@ -1,0 +1,100 @@
+"""Seeded synthetic LP families used by the parity tests and by bench.py.
+
+The dense family is the one SURVEY.md section 8(d) defines (and BASELINE.md timed the
+reference on): m structural + m slack columns (n = 2m), strictly positive integer
+constraint matrix, so x = 0 is feasible, the LP is bounded and the tableau is
+already canonical with the slack basis (phase 1 is a no-op).
+
+Everything here is plain Python / numpy: it only *describes* inputs.  Nothing in
+this module computes a pivot.
+"""
+from __future__ import annotations
+
+import random
+from fractions import Fraction
+from typing import List, Sequence, Tuple
+
+Grid = Tuple[List[int], List[List[int]], List[int]]
+
+
+def dense_lp(m: int, seed: int = 0, lo: int = 1, hi: int = 9) -> Grid:
+    """Return (c, A, b) of the seeded dense feasible family.
+
+    Draw order (fixed, part of the fixture contract): all of c, then A row by
+    row, then b.  c has m negative structural costs followed by m zeros; A is
+    [random m x m | I_m]; b[i] in [hi*m//4, hi*m//2].
+    """
+    rng = random.Random(seed)
+    c = [-rng.randint(lo, hi) for _ in range(m)] + [0] * m
+    A = []
+    for i in range(m):
+        row = [rng.randint(lo, hi) for _ in range(m)] + [0] * m
+        row[m + i] = 1
+        A.append(row)
+    b = [rng.randint(hi * m // 4, hi * m // 2) for _ in range(m)]
+    return c, A, b
+
+
+def dense_lp_grid(m: int, seed: int = 0, lo: int = 1, hi: int = 9) -> List[List[int]]:
+    """Same family as one (m+1) x (n+1) grid in device layout.
+
+    Rows 0..m-1 are the constraints, row m is the objective row; columns
+    0..n-1 are the variables, column n is the right-hand side.  Cell (m, n) is
+    the reference's `_z` cell (= minus the objective value, 0 here).
+    """
+    c, A, b = dense_lp(m, seed, lo, hi)
+    grid = [A[i] + [b[i]] for i in range(m)]
+    grid.append(c + [0])
+    return grid
+
+
+def equality_lp(m: int, n: int, seed: int = 0, lo: int = -5, hi: int = 9) -> Grid:
+    """Non-canonical family (equality rows, no slack columns) for phase 1.
+
+    A feasible point x0 >= 0 is drawn first and b = A x0, so the LP is feasible;
+    costs are positive so it is bounded.  Rows are independent with
+    probability ~1 for n > m; b may come out negative, which exercises the
+    reference's sign normalisation (simplex.py:43-45).
+    """
+    rng = random.Random(seed)
+    A = [[rng.randint(lo, hi) for _ in range(n)] for _ in range(m)]
+    x0 = [rng.randint(0, 4) for _ in range(n)]
+    b = [sum(A[i][j] * x0[j] for j in range(n)) for i in range(m)]
+    c = [rng.randint(1, 9) for _ in range(n)]
+    return c, A, b
+
+
+#: Beale's cycling example: exercises the stale
+#: objective "stuck" counter and the switch from Dantzig to Bland pricing.
+BEALE = (
+    [Fraction(0), Fraction(0), Fraction(0), Fraction(-3, 4), Fraction(20), Fraction(-1, 2), Fraction(6)],
+    [
+        [Fraction(1), Fraction(0), Fraction(0), Fraction(1, 4), Fraction(-8), Fraction(-1), Fraction(9)],
+        [Fraction(0), Fraction(1), Fraction(0), Fraction(1, 2), Fraction(-12), Fraction(-1, 2), Fraction(3)],
+        [Fraction(0), Fraction(0), Fraction(1), Fraction(0), Fraction(0), Fraction(1), Fraction(0)],
+    ],
+    [Fraction(0), Fraction(0), Fraction(1)],
+)
+
+#: The textbook LP of the reference's own test fixture (test_tableau.py:9-29).
+TEXTBOOK = (
+    [-40, -30, 0, 0],
+    [[1, 1, 1, 0], [2, 1, 0, 1]],
+    [12, 16],
+)
+
+
+def var_names(m: int) -> List[str]:
+    """x0..x{m-1}, s0..s{m-1} for the dense family."""
+    return [f"x{j}" for j in range(m)] + [f"s{i}" for i in range(m)]
+
+
+def to_grid(c: Sequence, A: Sequence[Sequence], b: Sequence, z=0):
+    """(c, A, b[, z]) -> device-layout grid (objective last row, RHS last column).
+
+    `z` is the objective value as the user sets it (`setZ`); the grid's corner
+    cell stores -z like the reference's `_z` field (tableau.py:128-130).
+    """
+    grid = [list(A[i]) + [b[i]] for i in range(len(A))]
+    grid.append(list(c) + [-z])
+    return grid
