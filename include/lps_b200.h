@@ -1,0 +1,147 @@
+/*
+ * lps_b200.h -- C-ABI of the B200-native simplex pivot engine.
+ *
+ * The reference (tkoz0/linear-program-solver, `lpsol`) is pure Python and has no
+ * FFI: the drop-in boundary is the class surface between `Simplex` (caller) and
+ * `Tableau` (callee).  Each entry point below names the reference interface it
+ * replaces (file:line under /root/reference/lpsol).  The host package
+ * `linear_program_solver_b200` binds these with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - opaque handle, int status return, no exceptions across the boundary;
+ *   - the caller owns host buffers; device buffers are either owned by the
+ *     library or lent by the caller (a torch tensor's data_ptr) and must then
+ *     outlive the handle;
+ *   - one handle = one device + one CUDA stream; calls on a handle are not
+ *     thread-safe; every call is asynchronous on the stream unless it returns
+ *     data to the host;
+ *   - device layout of a tableau ("grid"): row-major (m+1) x ld, rows 0..m-1
+ *     the constraints, row m the objective row (reduced costs), columns 0..n-1
+ *     the variables, column n the right-hand side; cell (m,n) is the
+ *     reference's `_z` field, i.e. MINUS the objective value
+ *     (tableau.py:46,82-84,128-130).  ld = lps_grid_ld(n).
+ */
+#ifndef LPS_B200_H
+#define LPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes -------------------------------------------------------- */
+#define LPS_OK            0   /* call succeeded / solver still running                     */
+#define LPS_OPTIMAL       1   /* simplex.py:269 'optimal'                                   */
+#define LPS_UNBOUNDED     2   /* simplex.py:281 'unbounded' (solve(): AssertionError :125)  */
+#define LPS_ZERO_PIVOT    3   /* tableau.py:300-301 ZeroDivisionError('zero pivot r,c')     */
+#define LPS_MAX_PIVOTS    4   /* stopped after the requested pivot prefix (not in reference) */
+#define LPS_BAD_PRIME     5   /* exact mode: next pivot is 0 modulo a prime; re-encode      */
+#define LPS_E_INVALID    -1   /* bad argument                                              */
+#define LPS_E_CUDA       -2   /* CUDA runtime error, see lps_last_error()                  */
+#define LPS_E_NOMEM      -3
+#define LPS_E_STATE      -4   /* call not valid in the handle's current state              */
+
+/* pricing rules */
+#define LPS_RULE_DANTZIG  0   /* Simplex.findPivotStandard  simplex.py:251-284 */
+#define LPS_RULE_BLAND    1   /* Simplex.findPivotMinIndex  simplex.py:218-249 */
+
+typedef struct lps_handle lps_handle;
+
+/* ---- library ------------------------------------------------------------- */
+int         lps_version(void);
+const char *lps_last_error(void);              /* thread-local, valid until the next failing call */
+int         lps_device_count(int *count);
+size_t      lps_grid_ld(int n);                /* leading dimension (elements) of a grid with n variables */
+
+/* ---- fp64 tableau: storage (replaces Tableau.__init__ tableau.py:36-52) --- */
+/*
+ * m, n        local constraint rows and variables of this handle's grid.
+ * dev_grid    NULL: the library allocates (m+1)*ld doubles; else a device
+ *             pointer to that many doubles lent by the caller.
+ * stream      a cudaStream_t (as void*) to enqueue on, or NULL for a private one.
+ */
+int lps_create_f64(int m, int n, int device, void *dev_grid, void *stream, lps_handle **out);
+int lps_destroy(lps_handle *h);
+int lps_sync(lps_handle *h);
+
+/* Row-sharding: this handle holds constraint rows
+ * [row0, row0+m) of an m_total-row tableau on rank `rank` of `nranks`, plus its
+ * own replica of the objective row.  cand_send / cand_all are device buffers of
+ * lps_cand_bytes(n) and nranks*lps_cand_bytes(n) bytes lent by the caller (the
+ * all-gather send and receive buffers).  For nranks == 1 this call is optional. */
+size_t lps_cand_bytes(int n);
+int lps_set_shard(lps_handle *h, long long row0, long long m_total, int rank, int nranks,
+                  void *cand_send, void *cand_all);
+
+/* Host <-> device transfer of the whole grid (setA/setB/setC/setZ and the
+ * getters, tableau.py:70-180).  `host` is row-major (m+1) x ld_host doubles in
+ * the device layout described above. */
+int lps_upload_f64(lps_handle *h, const double *host, size_t ld_host);
+int lps_download_f64(lps_handle *h, double *host, size_t ld_host);
+/* getCj/getBi/getAij/getZ (tableau.py:82-108): one row / one column / one cell. */
+int lps_read_row_f64(lps_handle *h, int i, double *host);   /* n+1 doubles */
+int lps_read_col_f64(lps_handle *h, int j, double *host);   /* m+1 doubles */
+void *lps_grid_ptr(lps_handle *h);                          /* device pointer of the grid */
+
+/* ---- the hot path --------------------------------------------------------- */
+/* Tableau.pivot(r,c) tableau.py:295-308 (with rowDiv :262, rowAddToObj :282,
+ * rowSub :278 fused in one rank-1 update).  LPS_ZERO_PIVOT if a_rc == 0. */
+int lps_pivot(lps_handle *h, int r, int c);
+
+/* Row operations outside a pivot: rowMult tableau.py:254, rowAdd :269 (rd == m
+ * addresses the objective row, i.e. rowAddToObj :282). */
+int lps_row_scale_f64(lps_handle *h, int r, double mult);
+int lps_row_axpy_f64(lps_handle *h, int rd, int rs, double mult);
+
+/* Simplex.findPivotStandard / findPivotMinIndex with do_pivot=False
+ * (simplex.py:251-284, :218-249).  Returns LPS_OK with (*r,*c) set, or
+ * LPS_OPTIMAL / LPS_UNBOUNDED. */
+int lps_find_pivot(lps_handle *h, int rule, int *r, int *c);
+
+/* Tableau.isCanonical(bcols) tableau.py:466-496.  bcols (m ints, may be NULL)
+ * receives the lowest basic column per row or -1; *canonical is 0/1. */
+int lps_is_canonical(lps_handle *h, int *bcols, int *canonical);
+/* Tableau.isOptimal tableau.py:500-502 */
+int lps_is_optimal(lps_handle *h, int *optimal);
+
+/* Simplex.solve() simplex.py:110-148, the whole loop on the device: Dantzig
+ * pricing while the stuck counter is below m+n (the counter compares with the
+ * objective at entry, simplex.py:118/:134), then Bland.
+ *   max_pivots  < 0: run to the end; else stop after that many pivots
+ *   basis       in/out, m ints (Simplex._bfs): basis[r] = c after each pivot
+ *   marks       in/out, n ints 0/1 or NULL (Tableau._cm): Simplex._pivot's
+ *               bookkeeping simplex.py:195-197 (unmark leaving, mark entering)
+ *   trace       NULL or 3*trace_cap ints: (row, column, rule) per pivot
+ *   npiv        number of pivots done by this call
+ * Returns LPS_OPTIMAL, LPS_UNBOUNDED or LPS_MAX_PIVOTS. */
+int lps_solve(lps_handle *h, long long max_pivots, int *basis, int *marks, int *trace,
+              long long trace_cap, long long *npiv);
+
+/* Sharded stepping (one pivot = select, all-gather of candidates by the
+ * caller, update).  lps_solve_begin arms the loop state (stuck counter,
+ * objective at entry); lps_step_select prices on the replicated objective
+ * row, ratio-tests the local rows and fills cand_send; lps_step_update picks
+ * the global leaving row out of cand_all (lowest ratio, then lowest global row,
+ * simplex.py:277), applies the rank-1 update to the local rows and commits the
+ * pivot.  lps_solve_poll copies the state back: status, pivots so far. */
+int lps_solve_begin(lps_handle *h, long long max_pivots, const int *basis, const int *marks,
+                    long long trace_cap);
+int lps_step_select(lps_handle *h);
+int lps_step_update(lps_handle *h);
+int lps_solve_poll(lps_handle *h, int *status, long long *npiv);
+int lps_solve_end(lps_handle *h, int *basis, int *marks, int *trace, long long trace_cap,
+                  long long *npiv);
+
+/* Timing aid for bench.py: CUDA-event time (ms) and launch count of the
+ * rank-1 update kernels enqueued since the last reset, measured on the
+ * handle's own stream. */
+int lps_prof_reset(lps_handle *h);
+int lps_prof_read(lps_handle *h, double *update_ms, long long *update_launches, long long *all_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPS_B200_H */

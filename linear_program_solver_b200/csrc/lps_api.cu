@@ -1,0 +1,521 @@
+// C-ABI of the B200 simplex pivot engine (see include/lps_b200.h for the contract and the
+// reference interfaces each entry point replaces).  Host-side orchestration only: every
+// arithmetic step of the path runs in the kernels of lps_f64.cuh / lps_exact.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/lps_b200.h"
+#include "lps_f64.cuh"
+
+using namespace lps;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(LPS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+constexpr int kWideChunk = 1024;     // doubles per column chunk for large grids
+constexpr int kNarrowChunk = 512;    // ... for small ones (more CTAs)
+constexpr size_t kL2Bytes = 120ull << 20;
+
+struct lps_handle {
+    int mode = 0;                    // 0 = fp64
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int m = 0, n = 0;
+    size_t ld = 0;
+    long long row0 = 0, m_total = 0;
+    int rank = 0, nranks = 1;
+
+    double* T = nullptr;
+    bool own_T = false;
+    double* ucol = nullptr;
+    unsigned char* cand_send = nullptr;
+    unsigned char* cand_all = nullptr;
+    bool own_cand = false;
+    size_t cand_stride = 0;
+
+    int chunk = kWideChunk, nchunks = 0, rows_per_cta = 64, sel_blocks = 1;
+    bool stream_hint = false;
+    double* pd_val = nullptr;
+    int* pd_idx = nullptr;
+    int* pb_idx = nullptr;
+    ArgMinF64* sel_blk = nullptr;
+    SolveState* st = nullptr;
+    SolveState* st_host = nullptr;   // pinned mirror
+    int* basis = nullptr;            // m_total ints
+    int* marks = nullptr;            // n ints
+    bool use_marks = false;
+    int* trace = nullptr;
+    long long trace_cap = 0;
+    int* scratch_i = nullptr;        // n + 8 ints (isCanonical)
+    bool solving = false;
+
+    // profiling of the update kernel
+    bool prof = false;
+    std::vector<cudaEvent_t> ev;
+    size_t ev_used = 0;
+    long long launches_update = 0, launches_all = 0;
+};
+
+static F64Grid grid_of(const lps_handle* h) {
+    F64Grid g;
+    g.T = h->T; g.ld = h->ld; g.m = h->m; g.n = h->n; g.row0 = h->row0; g.m_total = h->m_total;
+    return g;
+}
+static PricePartials partials_of(const lps_handle* h) { return PricePartials{h->pd_val, h->pd_idx, h->pb_idx}; }
+
+static int use(const lps_handle* h) {
+    if (!h) return fail(LPS_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    return LPS_OK;
+}
+#define USE(h)                         \
+    do {                               \
+        int rc_ = use(h);              \
+        if (rc_ != LPS_OK) return rc_; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// library
+// ------------------------------------------------------------------------------------------------
+extern "C" int lps_version(void) { return 100; }
+extern "C" const char* lps_last_error(void) { return g_err; }
+extern "C" int lps_device_count(int* count) {
+    if (!count) return fail(LPS_E_INVALID, "null count");
+    CU(cudaGetDeviceCount(count));
+    return LPS_OK;
+}
+extern "C" size_t lps_grid_ld(int n) { return ((size_t)n + 1 + 15) / 16 * 16; }
+extern "C" size_t lps_cand_bytes(int n) { return sizeof(CandHeader) + lps_grid_ld(n) * sizeof(double); }
+
+static void plan(lps_handle* h) {
+    const size_t bytes = (size_t)(h->m + 1) * h->ld * sizeof(double);
+    h->stream_hint = bytes > kL2Bytes;
+    // wide chunks + tall row blocks once there is enough work for several waves of CTAs
+    const size_t tiles_wide = ((h->ld + kWideChunk - 1) / kWideChunk) * (((size_t)h->m + 1 + 63) / 64);
+    if (tiles_wide >= 148 * 8) { h->chunk = kWideChunk; h->rows_per_cta = 64; }
+    else { h->chunk = kNarrowChunk; h->rows_per_cta = ((size_t)(h->m + 1) * h->ld >= (1u << 20)) ? 16 : 8; }
+    h->nchunks = (int)((h->ld + h->chunk - 1) / h->chunk);
+    h->sel_blocks = std::max(1, std::min((h->m + kThreads - 1) / kThreads, 148 * 4));
+}
+
+extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* stream, lps_handle** out) {
+    if (!out) return fail(LPS_E_INVALID, "null out");
+    *out = nullptr;
+    if (m <= 0) return fail(LPS_E_INVALID, "need m > 0, provided m = %d", m);
+    if (n <= 0) return fail(LPS_E_INVALID, "need n > 0, provided n = %d", n);
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(LPS_E_INVALID, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    lps_handle* h = new (std::nothrow) lps_handle();
+    if (!h) return fail(LPS_E_NOMEM, "out of host memory");
+    h->device = device;
+    h->m = m; h->n = n; h->ld = lps_grid_ld(n);
+    h->row0 = 0; h->m_total = m;
+    if (stream) h->stream = (cudaStream_t)stream;
+    else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    const size_t grid_bytes = (size_t)(m + 1) * h->ld * sizeof(double);
+    if (dev_grid) h->T = (double*)dev_grid;
+    else {
+        cudaError_t e = cudaMalloc(&h->T, grid_bytes);
+        if (e != cudaSuccess) { delete h; return fail(LPS_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", grid_bytes, cudaGetErrorString(e)); }
+        h->own_T = true;
+        CU(cudaMemsetAsync(h->T, 0, grid_bytes, h->stream));
+    }
+    plan(h);
+    const size_t ucol_n = ((size_t)m + 1 + kMaxRowBlock - 1) / kMaxRowBlock * kMaxRowBlock + kMaxRowBlock;
+    CU(cudaMalloc(&h->ucol, ucol_n * sizeof(double)));
+    CU(cudaMemsetAsync(h->ucol, 0, ucol_n * sizeof(double), h->stream));
+    h->cand_stride = lps_cand_bytes(n);
+    CU(cudaMalloc(&h->cand_send, h->cand_stride));
+    CU(cudaMemsetAsync(h->cand_send, 0, h->cand_stride, h->stream));
+    h->cand_all = h->cand_send;
+    h->own_cand = true;
+    const int maxchunks = (int)((h->ld + kNarrowChunk - 1) / kNarrowChunk);
+    CU(cudaMalloc(&h->pd_val, maxchunks * sizeof(double)));
+    CU(cudaMalloc(&h->pd_idx, maxchunks * sizeof(int)));
+    CU(cudaMalloc(&h->pb_idx, maxchunks * sizeof(int)));
+    CU(cudaMalloc(&h->sel_blk, 148 * 4 * sizeof(ArgMinF64)));
+    CU(cudaMalloc(&h->st, sizeof(SolveState)));
+    CU(cudaMemsetAsync(h->st, 0, sizeof(SolveState), h->stream));
+    CU(cudaMallocHost(&h->st_host, sizeof(SolveState)));
+    CU(cudaMalloc(&h->basis, (size_t)m * sizeof(int)));
+    CU(cudaMemsetAsync(h->basis, 0xff, (size_t)m * sizeof(int), h->stream));
+    CU(cudaMalloc(&h->scratch_i, ((size_t)n + 8) * sizeof(int)));
+    CU(cudaMalloc(&h->marks, (size_t)n * sizeof(int)));
+    CU(cudaMemsetAsync(h->marks, 0, (size_t)n * sizeof(int), h->stream));
+    *out = h;
+    return LPS_OK;
+}
+
+extern "C" int lps_set_shard(lps_handle* h, long long row0, long long m_total, int rank, int nranks, void* cand_send,
+                             void* cand_all) {
+    USE(h);
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(LPS_E_INVALID, "bad rank %d of %d", rank, nranks);
+    if (row0 < 0 || row0 + h->m > m_total) return fail(LPS_E_INVALID, "rows [%lld,%lld) outside 0..%lld", row0, row0 + h->m, m_total);
+    if (nranks > 1 && (!cand_send || !cand_all)) return fail(LPS_E_INVALID, "sharded handles need candidate buffers");
+    h->row0 = row0; h->m_total = m_total; h->rank = rank; h->nranks = nranks;
+    if (cand_send && cand_all) {
+        if (h->own_cand) { CU(cudaFree(h->cand_send)); h->own_cand = false; }
+        h->cand_send = (unsigned char*)cand_send;
+        h->cand_all = (unsigned char*)cand_all;
+    }
+    CU(cudaFree(h->basis));
+    CU(cudaMalloc(&h->basis, (size_t)m_total * sizeof(int)));
+    CU(cudaMemsetAsync(h->basis, 0xff, (size_t)m_total * sizeof(int), h->stream));
+    return LPS_OK;
+}
+
+extern "C" int lps_destroy(lps_handle* h) {
+    if (!h) return LPS_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    if (h->own_T) cudaFree(h->T);
+    cudaFree(h->ucol);
+    if (h->own_cand) cudaFree(h->cand_send);
+    cudaFree(h->pd_val); cudaFree(h->pd_idx); cudaFree(h->pb_idx);
+    cudaFree(h->sel_blk); cudaFree(h->st); cudaFreeHost(h->st_host);
+    cudaFree(h->basis); cudaFree(h->marks); cudaFree(h->trace); cudaFree(h->scratch_i);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return LPS_OK;
+}
+
+extern "C" int lps_sync(lps_handle* h) {
+    USE(h);
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+extern "C" void* lps_grid_ptr(lps_handle* h) { return h ? (void*)h->T : nullptr; }
+
+// ------------------------------------------------------------------------------------------------
+// transfers
+// ------------------------------------------------------------------------------------------------
+extern "C" int lps_upload_f64(lps_handle* h, const double* host, size_t ld_host) {
+    USE(h);
+    if (!host || ld_host < (size_t)h->n + 1) return fail(LPS_E_INVALID, "bad host grid");
+    CU(cudaMemcpy2DAsync(h->T, h->ld * sizeof(double), host, ld_host * sizeof(double), ((size_t)h->n + 1) * sizeof(double),
+                         (size_t)h->m + 1, cudaMemcpyHostToDevice, h->stream));
+    if (h->ld > (size_t)h->n + 1)   // keep the padding columns at zero
+        CU(cudaMemset2DAsync(h->T + h->n + 1, h->ld * sizeof(double), 0, (h->ld - h->n - 1) * sizeof(double), (size_t)h->m + 1, h->stream));
+    return LPS_OK;
+}
+extern "C" int lps_download_f64(lps_handle* h, double* host, size_t ld_host) {
+    USE(h);
+    if (!host || ld_host < (size_t)h->n + 1) return fail(LPS_E_INVALID, "bad host grid");
+    CU(cudaMemcpy2DAsync(host, ld_host * sizeof(double), h->T, h->ld * sizeof(double), ((size_t)h->n + 1) * sizeof(double),
+                         (size_t)h->m + 1, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+extern "C" int lps_read_row_f64(lps_handle* h, int i, double* host) {
+    USE(h);
+    if (!host || i < 0 || i > h->m) return fail(LPS_E_INVALID, "row %d out of range", i);
+    CU(cudaMemcpyAsync(host, h->T + (size_t)i * h->ld, ((size_t)h->n + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+extern "C" int lps_read_col_f64(lps_handle* h, int j, double* host) {
+    USE(h);
+    if (!host || j < 0 || j > h->n) return fail(LPS_E_INVALID, "column %d out of range", j);
+    CU(cudaMemcpy2DAsync(host, sizeof(double), h->T + j, h->ld * sizeof(double), sizeof(double), (size_t)h->m + 1,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+static int launch_price(lps_handle* h) {
+    if (h->chunk == kWideChunk) k_price_f64<kWideChunk><<<h->nchunks, kThreads, 0, h->stream>>>(grid_of(h), partials_of(h));
+    else k_price_f64<kNarrowChunk><<<h->nchunks, kThreads, 0, h->stream>>>(grid_of(h), partials_of(h));
+    h->launches_all++;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+static int launch_select(lps_handle* h) {
+    SelectArgs a;
+    a.g = grid_of(h); a.pp = partials_of(h); a.nchunks = h->nchunks; a.st = h->st; a.ucol = h->ucol;
+    a.blk = h->sel_blk; a.cand = (CandHeader*)h->cand_send;
+    k_select_f64<<<h->sel_blocks, kThreads, 0, h->stream>>>(a);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+static int launch_update(lps_handle* h, int commit) {
+    UpdateArgs a;
+    a.g = grid_of(h); a.pp = partials_of(h); a.st = h->st; a.ucol = h->ucol;
+    a.cand_all = h->cand_all; a.cand_stride = h->cand_stride; a.nranks = h->nranks;
+    a.rows_per_cta = h->rows_per_cta; a.basis = h->basis; a.marks = h->use_marks ? h->marks : nullptr; a.trace = h->trace; a.trace_cap = h->trace_cap;
+    a.commit = commit;
+    dim3 grid(h->nchunks, (h->m + 1 + h->rows_per_cta - 1) / h->rows_per_cta);
+    const bool timed = h->prof && h->ev_used + 2 <= h->ev.size();
+    if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
+    if (h->chunk == kWideChunk) {
+        if (h->stream_hint) k_update_f64<kWideChunk, true><<<grid, kThreads, 0, h->stream>>>(a);
+        else k_update_f64<kWideChunk, false><<<grid, kThreads, 0, h->stream>>>(a);
+    } else {
+        if (h->stream_hint) k_update_f64<kNarrowChunk, true><<<grid, kThreads, 0, h->stream>>>(a);
+        else k_update_f64<kNarrowChunk, false><<<grid, kThreads, 0, h->stream>>>(a);
+    }
+    if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
+    h->launches_update++;
+    h->launches_all++;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+static int read_state(lps_handle* h) {
+    CU(cudaMemcpyAsync(h->st_host, h->st, sizeof(SolveState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+static int write_state(lps_handle* h, const SolveState& s) {
+    *h->st_host = s;
+    CU(cudaMemcpyAsync(h->st, h->st_host, sizeof(SolveState), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));   // st_host is reused
+    return LPS_OK;
+}
+#define TRY(x)                       \
+    do {                             \
+        int rc_ = (x);               \
+        if (rc_ < 0) return rc_;     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// hot path entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int lps_pivot(lps_handle* h, int r, int c) {
+    USE(h);
+    if (h->nranks != 1) return fail(LPS_E_STATE, "explicit pivots are not supported on a sharded handle");
+    if (r < 0 || r >= h->m || c < 0 || c >= h->n) return fail(LPS_E_INVALID, "pivot (%d,%d) out of range", r, c);
+    SolveState s{};
+    s.status = LPS_OK; s.max_pivots = -1;
+    TRY(write_state(h, s));
+    const int blocks = std::max(1, std::min((int)((std::max((size_t)h->m + 1, h->ld) + kThreads - 1) / kThreads), 148 * 2));
+    k_forced_f64<<<blocks, kThreads, 0, h->stream>>>(grid_of(h), h->st, h->ucol, (CandHeader*)h->cand_send, r, c);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    TRY(launch_update(h, 0));
+    TRY(read_state(h));
+    const int st = h->st_host->status;
+    return st == LPS_ZERO_PIVOT ? LPS_ZERO_PIVOT : LPS_OK;
+}
+
+extern "C" int lps_row_scale_f64(lps_handle* h, int r, double mult) {
+    USE(h);
+    if (r < 0 || r >= h->m) return fail(LPS_E_INVALID, "row %d out of range", r);
+    if (mult == 1.0) return LPS_OK;   // tableau.py:257
+    k_row_scale_f64<<<std::min((h->n + 256) / 256, 592), 256, 0, h->stream>>>(grid_of(h), r, mult);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+extern "C" int lps_row_axpy_f64(lps_handle* h, int rd, int rs, double mult) {
+    USE(h);
+    if (rd < 0 || rd > h->m || rs < 0 || rs >= h->m) return fail(LPS_E_INVALID, "rows (%d,%d) out of range", rd, rs);
+    if (mult == 0.0) return LPS_OK;   // tableau.py:272, :285
+    k_row_axpy_f64<<<std::min((h->n + 256) / 256, 592), 256, 0, h->stream>>>(grid_of(h), rd, rs, mult);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+
+extern "C" int lps_find_pivot(lps_handle* h, int rule, int* r, int* c) {
+    USE(h);
+    if (!r || !c || (rule != LPS_RULE_DANTZIG && rule != LPS_RULE_BLAND)) return fail(LPS_E_INVALID, "bad arguments");
+    if (h->nranks != 1) return fail(LPS_E_STATE, "find_pivot on a sharded handle: use the stepping calls");
+    SolveState s{};
+    s.status = LPS_OK; s.rule = rule; s.max_pivots = -1; s.dry_run = 1;
+    s.stuck = 0; s.last_r = -1; s.last_c = -1;
+    TRY(write_state(h, s));
+    TRY(launch_price(h));
+    TRY(launch_select(h));
+    TRY(read_state(h));
+    const SolveState& o = *h->st_host;
+    *r = o.last_r; *c = o.last_c;
+    if (o.status == LPS_OPTIMAL) return LPS_OPTIMAL;
+    if (o.last_r < 0) return LPS_UNBOUNDED;
+    return LPS_OK;
+}
+
+extern "C" int lps_is_optimal(lps_handle* h, int* optimal) {
+    int r, c;
+    if (!optimal) return fail(LPS_E_INVALID, "null result");
+    int rc = lps_find_pivot(h, LPS_RULE_BLAND, &r, &c);
+    if (rc < 0) return rc;
+    *optimal = (rc == LPS_OPTIMAL);
+    return LPS_OK;
+}
+
+extern "C" int lps_is_canonical(lps_handle* h, int* bcols, int* canonical) {
+    USE(h);
+    if (!canonical) return fail(LPS_E_INVALID, "null result");
+    if (h->nranks != 1) return fail(LPS_E_STATE, "is_canonical on a sharded handle");
+    int* flag = h->scratch_i + h->n;
+    CU(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+    k_any_neg_rhs_f64<<<std::max(1, std::min((h->m + 255) / 256, 592)), 256, 0, h->stream>>>(grid_of(h), flag);
+    int neg = 0;
+    CU(cudaMemcpyAsync(&neg, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->launches_all++;
+    if (neg) { *canonical = 0; return LPS_OK; }   // bcols untouched, like tableau.py:476-477
+    k_canon_cols_f64<<<(h->n + 127) / 128, 128, 0, h->stream>>>(grid_of(h), h->scratch_i);
+    int* d_bcols = nullptr;
+    CU(cudaMalloc(&d_bcols, (size_t)h->m * sizeof(int)));
+    CU(cudaMemsetAsync(d_bcols, 0x7f, (size_t)h->m * sizeof(int), h->stream));
+    k_canon_rows<<<std::max(1, std::min((h->n + 255) / 256, 592)), 256, 0, h->stream>>>(h->scratch_i, h->n, d_bcols);
+    h->launches_all += 2;
+    std::vector<int> tmp(h->m);
+    CU(cudaMemcpyAsync(tmp.data(), d_bcols, (size_t)h->m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaFree(d_bcols));
+    int all = 1;
+    for (int i = 0; i < h->m; ++i) {
+        const int j = (tmp[i] == 0x7f7f7f7f) ? -1 : tmp[i];
+        if (j < 0) all = 0;
+        if (bcols) bcols[i] = j;
+    }
+    *canonical = all;
+    return LPS_OK;
+}
+
+// ---- the solve loop ------------------------------------------------------------------------------
+extern "C" int lps_solve_begin(lps_handle* h, long long max_pivots, const int* basis, const int* marks, long long trace_cap) {
+    USE(h);
+    if (h->solving) return fail(LPS_E_STATE, "solve already in progress");
+    if (basis) CU(cudaMemcpyAsync(h->basis, basis, (size_t)h->m_total * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->use_marks = marks != nullptr;
+    if (marks) CU(cudaMemcpyAsync(h->marks, marks, (size_t)h->n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (trace_cap > h->trace_cap) {
+        if (h->trace) CU(cudaFree(h->trace));
+        h->trace = nullptr;
+        h->trace_cap = 0;
+        CU(cudaMalloc(&h->trace, (size_t)trace_cap * 3 * sizeof(int)));
+        h->trace_cap = trace_cap;
+    }
+    double zcell = 0.0;
+    CU(cudaMemcpyAsync(&zcell, h->T + (size_t)h->m * h->ld + h->n, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    SolveState s{};
+    s.status = LPS_OK; s.rule = LPS_RULE_DANTZIG; s.stuck = 0; s.z_entry_cell = zcell; s.npiv = 0;
+    s.max_pivots = max_pivots; s.pending_zcheck = 0; s.ticket = 0; s.dry_run = 0; s.last_r = -1; s.last_c = -1;
+    TRY(write_state(h, s));
+    TRY(launch_price(h));
+    h->solving = true;
+    return LPS_OK;
+}
+extern "C" int lps_step_select(lps_handle* h) {
+    USE(h);
+    if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
+    return launch_select(h);
+}
+extern "C" int lps_step_update(lps_handle* h) {
+    USE(h);
+    if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
+    return launch_update(h, 1);
+}
+extern "C" int lps_solve_poll(lps_handle* h, int* status, long long* npiv) {
+    USE(h);
+    TRY(read_state(h));
+    if (status) *status = h->st_host->status;
+    if (npiv) *npiv = h->st_host->npiv;
+    return LPS_OK;
+}
+extern "C" int lps_solve_end(lps_handle* h, int* basis, int* marks, int* trace, long long trace_cap, long long* npiv) {
+    USE(h);
+    if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
+    TRY(read_state(h));
+    h->solving = false;
+    const long long k = h->st_host->npiv;
+    if (npiv) *npiv = k;
+    if (basis) CU(cudaMemcpyAsync(basis, h->basis, (size_t)h->m_total * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (marks && h->use_marks) CU(cudaMemcpyAsync(marks, h->marks, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (trace && trace_cap > 0) {
+        const long long cnt = std::min(std::min(k, trace_cap), h->trace_cap);
+        if (cnt > 0) CU(cudaMemcpyAsync(trace, h->trace, (size_t)cnt * 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return h->st_host->status;
+}
+
+extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int* trace, long long trace_cap, long long* npiv) {
+    USE(h);
+    if (h->nranks != 1) return fail(LPS_E_STATE, "lps_solve on a sharded handle: drive it with the stepping calls");
+    if (!basis) return fail(LPS_E_INVALID, "null basis");
+    TRY(lps_solve_begin(h, max_pivots, basis, marks, trace ? trace_cap : 0));
+    // pivots enqueued per host check: about 2 ms of device work, between 4 and 256; a pivot
+    // prefix never enqueues more (select, update) pairs than it may commit
+    const double est_us = std::max(4.0, (double)(h->m + 1) * (double)h->ld * 16.0 / 5.0e6);
+    const long long burst = (long long)std::max(4.0, std::min(256.0, 2000.0 / est_us));
+    long long enqueued = 0;
+    for (;;) {
+        const long long room = max_pivots >= 0 ? max_pivots - enqueued : burst;
+        const long long now = std::min(burst, room);
+        for (long long k = 0; k < now; ++k) {
+            TRY(launch_select(h));
+            TRY(launch_update(h, 1));
+        }
+        enqueued += now;
+        if (now == 0) TRY(launch_select(h));   // lets the device report LPS_MAX_PIVOTS (or optimality)
+        TRY(read_state(h));
+        if (h->st_host->status != LPS_OK) break;
+    }
+    return lps_solve_end(h, basis, marks, trace, trace_cap, npiv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// profiling
+// ------------------------------------------------------------------------------------------------
+extern "C" int lps_prof_reset(lps_handle* h) {
+    USE(h);
+    if (h->ev.empty()) {
+        h->ev.resize(2 * 4096);
+        for (auto& e : h->ev) CU(cudaEventCreate(&e));
+    }
+    h->ev_used = 0;
+    h->launches_update = 0;
+    h->launches_all = 0;
+    h->prof = true;
+    return LPS_OK;
+}
+extern "C" int lps_prof_read(lps_handle* h, double* update_ms, long long* update_launches, long long* all_launches) {
+    USE(h);
+    CU(cudaStreamSynchronize(h->stream));
+    double total = 0.0;
+    for (size_t k = 0; k + 1 < h->ev_used; k += 2) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]));
+        total += ms;
+    }
+    if (update_ms) *update_ms = total;
+    if (update_launches) *update_launches = (long long)(h->ev_used / 2);
+    if (all_launches) *all_launches = h->launches_all;
+    return LPS_OK;
+}

@@ -1,0 +1,433 @@
+// fp64 simplex pivot kernels for sm_100a.
+//
+// One pivot = k_select_f64 (pricing on the objective row + ratio test on the local rows, produces
+// this rank's candidate: key + normalised pivot row) followed -- after the caller's all-gather of
+// candidates when the tableau is row-sharded -- by k_update_f64 (picks the global leaving row,
+// applies T <- T - u (x) v to the local rows, prices the new objective row for the next pivot and
+// commits the pivot).  No host round-trip inside the loop.
+//
+// Reference semantics reproduced (file:line under /root/reference/lpsol):
+//   tableau.py:295-308  pivot = row r times 1/p, objective += (-c_c) row r, row i += (-a_ic) row r
+//                       (product then sum, two roundings -- never an FMA; rows with a zero
+//                       multiplier are skipped, tableau.py:272/:285)
+//   simplex.py:262-267  Dantzig: most negative cost, lowest index among equals
+//   simplex.py:228-232  Bland: first negative cost
+//   simplex.py:272-279  ratio test: a_ic > 0 only, b_i / a_ic, lowest row among equals
+//   simplex.py:118-137  stuck counter against the objective at entry, then the rule switch
+#pragma once
+#include "lps_common.cuh"
+#include "../../include/lps_b200.h"
+
+namespace lps {
+
+constexpr int kThreads = 256;
+constexpr int kMaxRowBlock = 128;     // rows of u staged per CTA
+constexpr int kMaxRanks = 64;
+
+// Candidate slot exchanged between ranks: 64-byte header followed by ld doubles (the normalised row).
+struct alignas(16) CandHeader {
+    double ratio;        // b_i / a_ic of this rank's best row
+    long long row;       // GLOBAL row index of that row, -1: no row with a_ic > 0
+    int c;               // entering column (identical on every rank: the objective row is replicated)
+    int rule;            // rule that priced it
+    long long stuck;     // stuck counter after the objective check of this step
+    int pad[8];
+};
+static_assert(sizeof(CandHeader) == 64, "candidate header must stay 64 bytes");
+
+struct SolveState {
+    int status;              // LPS_OK while running
+    int rule;                // committed rule (Dantzig until the stuck counter trips)
+    long long stuck;
+    double z_entry_cell;     // corner cell when solve() was entered (simplex.py:118)
+    long long npiv;
+    long long max_pivots;    // < 0: unlimited
+    int pending_zcheck;      // last committed pivot was Dantzig-priced: compare the objective next
+    unsigned int ticket;     // last-block election of k_select
+    int dry_run;             // find_pivot: select only, nothing is committed
+    int last_r, last_c;      // last selected / committed pivot (global row)
+    int pad;
+};
+
+struct F64Grid {
+    double* T;               // (m+1) x ld, row m = objective row
+    size_t ld;
+    int m, n;                // local constraint rows, variables
+    long long row0, m_total; // global placement of the local rows
+};
+
+struct PricePartials {       // one entry per column chunk of the objective row
+    double* d_val;           // Dantzig: most negative value in the chunk (0 if none)
+    int* d_idx;              //          its lowest index, INT_MAX if none
+    int* b_idx;              // Bland:   lowest index with a negative value, INT_MAX if none
+};
+
+// ------------------------------------------------------------------------------------------------
+// pricing of one chunk of the objective row (used standalone and fused in the update)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void price_consider(double v, int j, int n, ArgMinF64& best, int& first_neg) {
+    if (j < n && v < 0.0) {
+        if (best.idx == INT_MAX || v < best.key || (v == best.key && j < best.idx)) {
+            best.key = v;
+            best.idx = j;
+        }
+        first_neg = min(first_neg, j);
+    }
+}
+
+template <int CW>
+__global__ void __launch_bounds__(kThreads) k_price_f64(F64Grid g, PricePartials pp) {
+    __shared__ ArgMinF64 s_arg[32];
+    __shared__ int s_int[32];
+    const double* obj = g.T + (size_t)g.m * g.ld;
+    const int col0 = blockIdx.x * CW;
+    ArgMinF64 best{0.0, INT_MAX};
+    int first_neg = INT_MAX;
+    for (int j = col0 + threadIdx.x; j < min(col0 + CW, g.n); j += kThreads) price_consider(obj[j], j, g.n, best, first_neg);
+    best = block_argmin(best, s_arg);
+    first_neg = block_min_int(first_neg, s_int);
+    if (threadIdx.x == 0) {
+        pp.d_val[blockIdx.x] = best.key;
+        pp.d_idx[blockIdx.x] = best.idx;
+        pp.b_idx[blockIdx.x] = first_neg;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// select: entering column from the partials, ratio test over the local rows, candidate slot
+// ------------------------------------------------------------------------------------------------
+struct SelectArgs {
+    F64Grid g;
+    PricePartials pp;
+    int nchunks;
+    SolveState* st;
+    double* ucol;            // m+1 (+pad): column c of the local grid, gathered here for the update
+    ArgMinF64* blk;          // gridDim.x per-block ratio partials
+    CandHeader* cand;        // this rank's candidate slot (header + ld doubles)
+};
+
+__global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
+    __shared__ ArgMinF64 s_arg[32];
+    __shared__ int s_int[32];
+    __shared__ int s_last;
+    SolveState* st = a.st;
+    const F64Grid& g = a.g;
+    if (st->status != LPS_OK) return;
+    if (st->max_pivots >= 0 && st->npiv >= st->max_pivots) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && !st->dry_run) st->status = LPS_MAX_PIVOTS;
+        return;
+    }
+    // stuck counter and rule (simplex.py:123,132-137), recomputed identically by every block
+    int rule = st->rule;
+    long long stuck = st->stuck;
+    if (st->pending_zcheck) stuck = (g.T[(size_t)g.m * g.ld + g.n] == st->z_entry_cell) ? stuck + 1 : 0;
+    if (rule == LPS_RULE_DANTZIG && !(stuck < g.m_total + (long long)g.n)) rule = LPS_RULE_BLAND;
+
+    // entering column
+    int c;
+    if (rule == LPS_RULE_DANTZIG) {
+        ArgMinF64 best{0.0, INT_MAX};
+        for (int k = threadIdx.x; k < a.nchunks; k += kThreads) best = argmin_pick(best, ArgMinF64{a.pp.d_val[k], a.pp.d_idx[k]});
+        best = block_argmin(best, s_arg);
+        c = best.idx;
+    } else {
+        int first = INT_MAX;
+        for (int k = threadIdx.x; k < a.nchunks; k += kThreads) first = min(first, a.pp.b_idx[k]);
+        c = block_min_int(first, s_int);
+    }
+    if (c == INT_MAX) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (st->dry_run) { st->last_r = -1; st->last_c = -1; }
+            st->status = LPS_OPTIMAL;
+        }
+        return;
+    }
+
+    // ratio test over this block's rows; column c is gathered into ucol on the way
+    ArgMinF64 best{0.0, INT_MAX};
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < g.m; i += gridDim.x * kThreads) {
+        const double aic = g.T[(size_t)i * g.ld + c];
+        a.ucol[i] = aic;
+        if (aic > 0.0) {
+            const double ratio = g.T[(size_t)i * g.ld + g.n] / aic;
+            if (best.idx == INT_MAX || ratio < best.key) { best.key = ratio; best.idx = i; }
+        }
+    }
+    best = block_argmin(best, s_arg);
+    if (threadIdx.x == 0) {
+        a.blk[blockIdx.x] = best;
+        __threadfence();
+        const unsigned int t = atomicAdd(&st->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+
+    // ---- last block: reduce the per-block partials, publish the candidate ----
+    __threadfence();
+    best = ArgMinF64{0.0, INT_MAX};
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += kThreads) {
+        ArgMinF64 o;
+        o.key = __ldcg(&a.blk[k].key);
+        o.idx = __ldcg(&a.blk[k].idx);
+        best = argmin_pick(best, o);
+    }
+    best = block_argmin(best, s_arg);
+    const int r = best.idx;
+    double* vrow = reinterpret_cast<double*>(a.cand + 1);
+    if (threadIdx.x == 0) {
+        st->ticket = 0;
+        a.ucol[g.m] = g.T[(size_t)g.m * g.ld + c];
+        a.cand->ratio = best.key;
+        a.cand->row = (r == INT_MAX) ? -1 : g.row0 + r;
+        a.cand->c = c;
+        a.cand->rule = rule;
+        a.cand->stuck = stuck;
+        if (st->dry_run) { st->last_r = (r == INT_MAX) ? -1 : (int)(g.row0 + r); st->last_c = c; }
+    }
+    if (r == INT_MAX || st->dry_run) return;
+    // normalised pivot row: row r times the reciprocal of the pivot (tableau.py:262-267, :254-260)
+    const double* src = g.T + (size_t)r * g.ld;
+    const double inv = 1.0 / src[c];
+    for (int j = threadIdx.x; j < (int)g.ld; j += kThreads) vrow[j] = (inv == 1.0) ? src[j] : src[j] * inv;
+}
+
+// Explicit pivot (Tableau.pivot(r,c)): gather column c and build the candidate for a caller-chosen (r,c).
+__global__ void __launch_bounds__(kThreads) k_forced_f64(F64Grid g, SolveState* st, double* ucol, CandHeader* cand, int r, int c) {
+    const double p = g.T[(size_t)r * g.ld + c];
+    if (p == 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->status = LPS_ZERO_PIVOT;
+        return;
+    }
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i <= g.m; i += gridDim.x * kThreads) ucol[i] = g.T[(size_t)i * g.ld + c];
+    double* vrow = reinterpret_cast<double*>(cand + 1);
+    const double* src = g.T + (size_t)r * g.ld;
+    const double inv = 1.0 / p;
+    for (int j = blockIdx.x * kThreads + threadIdx.x; j < (int)g.ld; j += gridDim.x * kThreads)
+        vrow[j] = (inv == 1.0) ? src[j] : src[j] * inv;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cand->ratio = 0.0;
+        cand->row = g.row0 + r;
+        cand->c = c;
+        cand->rule = 2;
+        cand->stuck = st->stuck;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// update: T <- T - u (x) v on the local rows, row r <- v, fused pricing of the new objective row
+// ------------------------------------------------------------------------------------------------
+struct UpdateArgs {
+    F64Grid g;
+    PricePartials pp;
+    SolveState* st;
+    const double* ucol;
+    const unsigned char* cand_all;   // nranks slots of cand_stride bytes
+    size_t cand_stride;
+    int nranks;
+    int rows_per_cta;                // <= kMaxRowBlock, multiple of RU
+    int* basis;                      // m_total entries, replicated
+    int* marks;                      // n entries (Tableau._cm as 0/1), replicated; may be NULL
+    int* trace;                      // 3 * trace_cap ints or NULL
+    long long trace_cap;
+    int commit;                      // 0 for an explicit Tableau.pivot (no basis / trace / counter)
+};
+
+template <int CW, bool STREAM>
+__global__ void __launch_bounds__(kThreads) k_update_f64(UpdateArgs a) {
+    constexpr int VPT = CW / (2 * kThreads);   // double2 vectors per thread per row
+    constexpr int RU = 4;                      // rows in flight per thread
+    static_assert(VPT >= 1, "chunk too narrow");
+    __shared__ alignas(128) double s_v[CW];
+    __shared__ alignas(128) double s_u[kMaxRowBlock];
+    __shared__ alignas(8) uint64_t s_bar;
+    __shared__ ArgMinF64 s_arg[32];
+    __shared__ int s_int[32];
+
+    SolveState* st = a.st;
+    const F64Grid& g = a.g;
+    if (st->status != LPS_OK) return;
+
+    // global leaving row: lowest ratio, then lowest global row (simplex.py:277), over all ranks' candidates
+    int w = -1;
+    double w_ratio = 0.0;
+    long long w_row = -1;
+    for (int k = 0; k < a.nranks; ++k) {
+        const CandHeader* h = reinterpret_cast<const CandHeader*>(a.cand_all + (size_t)k * a.cand_stride);
+        const long long row = h->row;
+        if (row < 0) continue;
+        const double ratio = h->ratio;
+        if (w < 0 || ratio < w_ratio || (ratio == w_ratio && row < w_row)) { w = k; w_ratio = ratio; w_row = row; }
+    }
+    const bool lead = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
+    if (w < 0) {
+        if (lead) st->status = LPS_UNBOUNDED;
+        return;
+    }
+    const CandHeader* hw = reinterpret_cast<const CandHeader*>(a.cand_all + (size_t)w * a.cand_stride);
+    const double* vrow = reinterpret_cast<const double*>(hw + 1);
+    const int c = hw->c;
+    const long long r_local_ll = w_row - g.row0;
+    const int r_local = (r_local_ll >= 0 && r_local_ll < g.m) ? (int)r_local_ll : -1;
+
+    const int col0 = blockIdx.x * CW;
+    const int row0 = blockIdx.y * a.rows_per_cta;
+    const int mrows = g.m + 1;
+    const int ncols = min(CW, (int)g.ld - col0);
+    const int nrows = min(a.rows_per_cta, mrows - row0);
+
+    // stage v (pivot row chunk) and u (pivot column block) in shared memory with TMA bulk copies
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        const uint32_t vb = (uint32_t)ncols * 8u, ub = (uint32_t)a.rows_per_cta * 8u;
+        mbar_expect_tx(&s_bar, vb + ub);
+        tma_load_1d(s_v, vrow + col0, vb, &s_bar);
+        tma_load_1d(s_u, a.ucol + row0, ub, &s_bar);
+    }
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+
+    double2 v[VPT];
+    bool vok[VPT];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        const int jl = 2 * threadIdx.x + k * 2 * kThreads;
+        vok[k] = jl < ncols;
+        v[k] = vok[k] ? *reinterpret_cast<const double2*>(&s_v[jl]) : make_double2(0.0, 0.0);
+    }
+    double* base = g.T + (size_t)row0 * g.ld + col0 + 2 * threadIdx.x;
+    const bool has_obj = (row0 + nrows == mrows);
+    double2 objv[VPT];
+
+    for (int rg = 0; rg < nrows; rg += RU) {
+        double2 t[RU][VPT];
+        double nu[RU];
+        bool act[RU];
+#pragma unroll
+        for (int q = 0; q < RU; ++q) {
+            const int il = rg + q, i = row0 + il;
+            const double u = (il < nrows) ? s_u[il] : 0.0;
+            nu[q] = -u;
+            // a zero multiplier leaves the row untouched (tableau.py:272); the objective row is
+            // always loaded because its new values feed the pricing partials
+            act[q] = (il < nrows) && (i != r_local) && (u != 0.0 || i == g.m);
+            if (act[q]) {
+#pragma unroll
+                for (int k = 0; k < VPT; ++k)
+                    if (vok[k]) t[q][k] = ld_f64x2<STREAM>(base + (size_t)il * g.ld + k * 2 * kThreads);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RU; ++q) {
+            const int il = rg + q, i = row0 + il;
+            if (act[q]) {
+                const bool write = (nu[q] != 0.0);
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    if (!vok[k]) continue;
+                    if (write) {
+                        t[q][k].x = __dadd_rn(t[q][k].x, __dmul_rn(nu[q], v[k].x));
+                        t[q][k].y = __dadd_rn(t[q][k].y, __dmul_rn(nu[q], v[k].y));
+                        st_f64x2<STREAM>(base + (size_t)il * g.ld + k * 2 * kThreads, t[q][k]);
+                    }
+                    if (i == g.m) objv[k] = t[q][k];
+                }
+            } else if (il < nrows && i == r_local) {
+#pragma unroll
+                for (int k = 0; k < VPT; ++k)
+                    if (vok[k]) st_f64x2<STREAM>(base + (size_t)il * g.ld + k * 2 * kThreads, v[k]);
+            }
+        }
+    }
+
+    if (has_obj) {   // price the new objective row chunk for the next select
+        ArgMinF64 best{0.0, INT_MAX};
+        int first_neg = INT_MAX;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            if (!vok[k]) continue;
+            const int j = col0 + 2 * threadIdx.x + k * 2 * kThreads;
+            price_consider(objv[k].x, j, g.n, best, first_neg);
+            price_consider(objv[k].y, j + 1, g.n, best, first_neg);
+        }
+        best = block_argmin(best, s_arg);
+        first_neg = block_min_int(first_neg, s_int);
+        if (threadIdx.x == 0) {
+            a.pp.d_val[blockIdx.x] = best.key;
+            a.pp.d_idx[blockIdx.x] = best.idx;
+            a.pp.b_idx[blockIdx.x] = first_neg;
+        }
+    }
+
+    if (lead) {   // commit (Simplex._pivot simplex.py:192-197: basis bookkeeping; marks live on the host)
+        st->last_r = (int)w_row;
+        st->last_c = c;
+        if (a.commit) {
+            const long long k = st->npiv;
+            if (a.trace && k < a.trace_cap) {
+                a.trace[3 * k] = (int)w_row;
+                a.trace[3 * k + 1] = c;
+                a.trace[3 * k + 2] = hw->rule;
+            }
+            if (a.marks) {   // simplex.py:195-197: unmark the leaving variable, mark the entering one
+                const int old = a.basis[w_row];
+                if (old >= 0 && old < g.n) a.marks[old] = 0;
+                a.marks[c] = 1;
+            }
+            a.basis[w_row] = c;
+            st->npiv = k + 1;
+            st->rule = hw->rule;
+            st->stuck = hw->stuck;
+            st->pending_zcheck = (hw->rule == LPS_RULE_DANTZIG);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels outside the loop
+// ------------------------------------------------------------------------------------------------
+__global__ void k_row_scale_f64(F64Grid g, int r, double mult) {   // tableau.py:254-260
+    double* row = g.T + (size_t)r * g.ld;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= g.n; j += gridDim.x * blockDim.x) row[j] = row[j] * mult;
+}
+__global__ void k_row_axpy_f64(F64Grid g, int rd, int rs, double mult) {   // tableau.py:269-289
+    double* dst = g.T + (size_t)rd * g.ld;
+    const double* src = g.T + (size_t)rs * g.ld;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= g.n; j += gridDim.x * blockDim.x)
+        dst[j] = __dadd_rn(dst[j], __dmul_rn(mult, src[j]));
+}
+__global__ void k_gather_col_f64(F64Grid g, int j, double* out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= g.m; i += gridDim.x * blockDim.x) out[i] = g.T[(size_t)i * g.ld + j];
+}
+
+// Tableau.isCanonical (tableau.py:466-496), column scan.  One thread per column walks the rows
+// (coalesced across the warp).  colrow[j] = row of the single exact 1 if column j is basic, else -1.
+__global__ void k_canon_cols_f64(F64Grid g, int* colrow) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.n) return;
+    int hit = -1;
+    bool clean = (g.T[(size_t)g.m * g.ld + j] == 0.0);
+    for (int i = 0; clean && i < g.m; ++i) {
+        const double v = g.T[(size_t)i * g.ld + j];
+        if (v == 0.0) continue;
+        if (v == 1.0 && hit == -1) hit = i; else clean = false;
+    }
+    colrow[j] = (clean && hit != -1) ? hit : -1;
+}
+// any b_i < 0 ?  (tableau.py:476-477)
+__global__ void k_any_neg_rhs_f64(F64Grid g, int* flag) {
+    int neg = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.m; i += gridDim.x * blockDim.x)
+        neg |= (g.T[(size_t)i * g.ld + g.n] < 0.0);
+    if (__any_sync(0xffffffffu, neg) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+// bcols[i] = lowest basic column of row i (tableau.py:490-495)
+__global__ void k_canon_rows(const int* colrow, int n, int* bcols) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int i = colrow[j];
+        if (i >= 0) atomicMin(&bcols[i], j);
+    }
+}
+
+}  // namespace lps

@@ -1,0 +1,170 @@
+"""Device engines: thin Python objects around one C-ABI handle each.
+
+`F64Engine` owns the fp64 device grid of one tableau (or of one row shard of
+it).  PyTorch is used only to allocate device / pinned buffers and to name the
+stream; every arithmetic step of the path happens inside the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_int, c_longlong, c_void_p, c_double
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+STATUS_NAME = {N.OPTIMAL: "optimal", N.UNBOUNDED: "unbounded", N.MAX_PIVOTS: "max_pivots", N.OK: "running",
+               N.ZERO_PIVOT: "zero_pivot", N.BAD_PRIME: "bad_prime"}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class F64Engine:
+    """fp64 tableau on one GPU.  Grid layout: see include/lps_b200.h."""
+
+    mode = "fp64"
+
+    def __init__(self, m: int, n: int, device: Optional[int] = None):
+        torch = _torch()
+        self.L = N.lib()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = int(device)
+        self.m, self.n = int(m), int(n)
+        self.ld = int(self.L.lps_grid_ld(self.n))
+        with torch.cuda.device(self.device):
+            self.grid = torch.zeros((self.m + 1, self.ld), dtype=torch.float64, device=f"cuda:{self.device}")
+            self.stream = torch.cuda.current_stream(self.device)
+        h = c_void_p()
+        N.check(self.L.lps_create_f64(self.m, self.n, self.device, self.grid.data_ptr(), self.stream.cuda_stream, byref(h)))
+        self.h = h
+        self.row0, self.m_total, self.rank, self.nranks = 0, self.m, 0, 1
+        self.cand_send = self.cand_all = None
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lps_destroy(self.h)
+            self.h = None
+            self.grid = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        N.check(self.L.lps_sync(self.h))
+
+    # -- sharding ------------------------------------------------------------------------------
+    def set_shard(self, row0: int, m_total: int, rank: int, nranks: int):
+        torch = _torch()
+        nb = int(self.L.lps_cand_bytes(self.n))
+        dev = f"cuda:{self.device}"
+        self.cand_send = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        self.cand_all = torch.zeros(nb * nranks, dtype=torch.uint8, device=dev) if nranks > 1 else self.cand_send
+        N.check(self.L.lps_set_shard(self.h, row0, m_total, rank, nranks, self.cand_send.data_ptr(), self.cand_all.data_ptr()))
+        self.row0, self.m_total, self.rank, self.nranks = row0, m_total, rank, nranks
+
+    # -- transfers -----------------------------------------------------------------------------
+    def upload(self, host: np.ndarray):
+        """host: float64 (m+1, >= n+1) array in grid layout (C-contiguous rows)."""
+        assert host.dtype == np.float64 and host.shape[0] == self.m + 1 and host.shape[1] >= self.n + 1
+        assert host.strides[1] == 8
+        N.check(self.L.lps_upload_f64(self.h, host.ctypes.data, host.strides[0] // 8))
+        self.sync()
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.m + 1, self.n + 1), dtype=np.float64)
+        N.check(self.L.lps_download_f64(self.h, out.ctypes.data, self.n + 1))
+        return out
+
+    def read_row(self, i: int) -> np.ndarray:
+        out = np.empty(self.n + 1, dtype=np.float64)
+        N.check(self.L.lps_read_row_f64(self.h, i, out.ctypes.data))
+        return out
+
+    def read_col(self, j: int) -> np.ndarray:
+        out = np.empty(self.m + 1, dtype=np.float64)
+        N.check(self.L.lps_read_col_f64(self.h, j, out.ctypes.data))
+        return out
+
+    # -- hot path ------------------------------------------------------------------------------
+    def pivot(self, r: int, c: int) -> int:
+        return N.check(self.L.lps_pivot(self.h, r, c))
+
+    def row_scale(self, r: int, mult: float):
+        N.check(self.L.lps_row_scale_f64(self.h, r, float(mult)))
+
+    def row_axpy(self, rd: int, rs: int, mult: float):
+        N.check(self.L.lps_row_axpy_f64(self.h, rd, rs, float(mult)))
+
+    def find_pivot(self, rule: int):
+        r, c = c_int(-1), c_int(-1)
+        rc = N.check(self.L.lps_find_pivot(self.h, rule, byref(r), byref(c)))
+        if rc == N.OPTIMAL:
+            return "optimal"
+        if rc == N.UNBOUNDED:
+            return "unbounded"
+        return r.value, c.value
+
+    def is_canonical(self, want_cols: bool = True):
+        cols = np.full(self.m, -1, dtype=np.int32)
+        flag = c_int(0)
+        N.check(self.L.lps_is_canonical(self.h, cols.ctypes.data if want_cols else None, byref(flag)))
+        return bool(flag.value), cols
+
+    def is_optimal(self) -> bool:
+        flag = c_int(0)
+        N.check(self.L.lps_is_optimal(self.h, byref(flag)))
+        return bool(flag.value)
+
+    def solve(self, basis: np.ndarray, marks: Optional[np.ndarray] = None, max_pivots: int = -1,
+              trace_cap: int = 0) -> Tuple[int, int, Optional[np.ndarray]]:
+        """Run `Simplex.solve` on the device.  basis / marks are int32 arrays updated in place."""
+        assert basis.dtype == np.int32 and basis.size == self.m_total
+        trace = np.zeros((trace_cap, 3), dtype=np.int32) if trace_cap > 0 else None
+        npiv = c_longlong(0)
+        rc = N.check(self.L.lps_solve(self.h, max_pivots, basis.ctypes.data,
+                                      marks.ctypes.data if marks is not None else None,
+                                      trace.ctypes.data if trace is not None else None, trace_cap, byref(npiv)))
+        k = npiv.value
+        return rc, k, (trace[: min(k, trace_cap)] if trace is not None else None)
+
+    # -- stepping (sharded driver) -----------------------------------------------------------------
+    def solve_begin(self, basis: Optional[np.ndarray], marks: Optional[np.ndarray], max_pivots: int, trace_cap: int):
+        N.check(self.L.lps_solve_begin(self.h, max_pivots, basis.ctypes.data if basis is not None else None,
+                                       marks.ctypes.data if marks is not None else None, trace_cap))
+
+    def step_select(self):
+        N.check(self.L.lps_step_select(self.h))
+
+    def step_update(self):
+        N.check(self.L.lps_step_update(self.h))
+
+    def poll(self) -> Tuple[int, int]:
+        st, k = c_int(0), c_longlong(0)
+        N.check(self.L.lps_solve_poll(self.h, byref(st), byref(k)))
+        return st.value, k.value
+
+    def solve_end(self, basis: np.ndarray, marks: Optional[np.ndarray], trace_cap: int = 0):
+        trace = np.zeros((trace_cap, 3), dtype=np.int32) if trace_cap > 0 else None
+        npiv = c_longlong(0)
+        rc = N.check(self.L.lps_solve_end(self.h, basis.ctypes.data, marks.ctypes.data if marks is not None else None,
+                                          trace.ctypes.data if trace is not None else None, trace_cap, byref(npiv)))
+        k = npiv.value
+        return rc, k, (trace[: min(k, trace_cap)] if trace is not None else None)
+
+    # -- profiling -----------------------------------------------------------------------------
+    def prof_reset(self):
+        N.check(self.L.lps_prof_reset(self.h))
+
+    def prof_read(self):
+        ms, nu, na = c_double(0), c_longlong(0), c_longlong(0)
+        N.check(self.L.lps_prof_read(self.h, byref(ms), byref(nu), byref(na)))
+        return ms.value, nu.value, na.value
