@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""Benchmark of the simplex pivot path (BASELINE.json metric: pivots/s and rank-1-update GB/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): C4 of BASELINE.json -- the fp64 32768 x 65536 tableau of the seeded dense
+family (17.2 GB, far larger than L2, so no flush is needed between iterations), generated on the
+device, row-sharded over the N GPUs (strong scaling: the tableau is fixed, each rank holds m/N rows).
+A step is `--pivots-per-step` consecutive simplex pivots (Dantzig pricing + ratio test + rank-1
+update, the reference's Simplex.solve loop); value = pivots/s over all ranks, device-timed with CUDA
+events on the launching stream, max over ranks.
+
+Extra objects on the JSON line:
+  roofline      the rank-1 update kernel: algorithmic bytes per launch (16(m_loc+1)(n+1) + 8(m_loc+1)
+                + 8(n+1)) / its mean CUDA-event duration in the timed region,
+                against MEASURED_PEAKS.json's hbm_gbs
+  e2e           the same metric through the public API with HOST buffers: every step uploads the
+                tableau from pinned host memory, runs the pivots, reads back basis, objective and
+                basic solution
+  cpu_baseline  the CPU oracle (C restatement of the reference's float path, all host cores) on the
+                same tableau, a few pivots (rank 0, N = 1 only)
+--impl reference times that CPU oracle alone (the reference itself is single-threaded pure Python
+and cannot hold this tableau: SURVEY.md section 8d); one pivot of the full tableau per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "pivots_per_sec", "pivots/s"
+
+
+def algorithmic_bytes(m_rows: int, n: int) -> int:
+    """fp64 bytes one pivot must move over (m_rows+1) x (n+1) cells."""
+    return 16 * (m_rows + 1) * (n + 1) + 8 * (m_rows + 1) + 8 * (n + 1)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the update kernel from the committed `ncu --set full` capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "update_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks and throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                      text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_mem_available() -> int:
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 1 << 62
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C restatement of the reference's float path) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_rows_that_fit(m: int, n: int) -> int:
+    need = (m + 1) * (n + 1) * 8
+    avail = host_mem_available()
+    rows = m
+    while rows > 64 and (rows + 1) * (n + 1) * 8 > 0.6 * avail:
+        rows //= 2
+    return rows
+
+
+def time_cpu_pivots(T: np.ndarray, m_rows: int, pivots: int):
+    """Seconds per pivot of the oracle's solve loop (pricing + ratio test + rank-1 update) on T."""
+    from oracle import c_oracle as C
+    basis = np.arange(T.shape[1] - 1 - m_rows, T.shape[1] - 1, dtype=np.int32)
+    t0 = time.perf_counter()
+    st, k, _ = C.solve(T, basis, max_pivots=pivots, want_trace=False)
+    dt = time.perf_counter() - t0
+    return dt / max(k, 1), k
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle as C
+    m, n = a.m, 2 * a.m
+    rows = cpu_rows_that_fit(m, n)
+    T = np.empty((rows + 1, n + 1), dtype=np.float64)
+    # a row slab of the same tableau when the host cannot hold all of it: per-pivot work is
+    # proportional to the rows, so the full-size rate is the slab's rate times rows/m
+    C.fill_dense(T, m, 0, a.seed, 1, 9)
+    scale = (rows + 1) / (m + 1)
+    basis = np.arange(m, m + rows, dtype=np.int32)
+    times = []
+    for s in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        C.solve(T, basis, max_pivots=1, want_trace=False)
+        dt = time.perf_counter() - t0
+        if s >= a.warmup:
+            times.append(dt)
+    sec = float(np.mean(times)) / scale
+    sample = f"1 pivot per step (pricing + ratio test + rank-1 update) of the {rows} x {n} " \
+             + ("full tableau" if rows == m else f"row slab of the {m} x {n} tableau, time scaled by rows") \
+             + f", {a.steps} steps"
+    val = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C4 fp64 {m}x{n} dense tableau, seed {a.seed}", "m": m, "n": n, "pivots_per_step": 1},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": C.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is single-threaded pure Python (fractions.Fraction) and cannot hold this tableau; "
+                "this arm is oracle/pivot_oracle.c, the C restatement of its float path, on all host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from linear_program_solver_b200 import _native as N
+    from linear_program_solver_b200.sharded import ShardedF64Solver, shard_rows
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {a.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    m, n, B = a.m, 2 * a.m, a.pivots_per_step
+    row0, m_loc = shard_rows(m, rank, world)
+    solver = ShardedF64Solver(m, n, rank, world, device=local)
+    eng = solver.eng
+    eng.fill_dense(a.seed, 1, 9)
+    basis = np.arange(m, 2 * m, dtype=np.int32)
+    solver.begin(basis, None, -1, 0)
+
+    def step():
+        solver.enqueue(B)
+        return solver.poll()
+
+    for _ in range(a.warmup):
+        step()
+    _, piv0 = solver.poll()
+    sampler = ClockSampler(local) if rank == 0 else None
+    eng.prof_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        status, piv1 = step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    upd_ms, upd_launches, all_launches = eng.prof_read()
+    pivots = piv1 - piv0
+    value = pivots / (ms * 1e-3)
+    bytes_launch = algorithmic_bytes(m_loc, n)
+    upd_avg_ms = max_over_ranks(upd_ms / max(upd_launches, 1))
+    peak, peak_src = measured_peak()
+    achieved = bytes_launch / (upd_avg_ms * 1e-3) / 1e9 if upd_launches else None
+    solver.end(basis, None, 0)
+
+    # ---- e2e: host buffers through the public API, upload + pivots + read-back every step ----------
+    host = torch.empty((m_loc + 1, n + 1), dtype=torch.float64, pin_memory=True)
+    eng.fill_dense(a.seed, 1, 9)
+    N.check(eng.L.lps_download_f64(eng.h, host.data_ptr(), n + 1))
+    host_np = host.numpy()
+    e2e_steps = max(1, min(a.steps, a.e2e_steps))
+    h2d = (m_loc + 1) * (n + 1) * 8
+    d2h_box = [0]
+
+    if world == 1:
+        from linear_program_solver_b200 import Simplex, Tableau
+        solver.close()
+
+        def e2e_step():
+            t = Tableau.from_grid(host_np, mode="fp64", device=local)
+            s = Simplex(t)                      # reads b, uploads, checks canonical form on the device
+            s.solve(max_pivots=B)
+            z = s.getObjValue()
+            x = s.getBFS()
+            d2h_box[0] = 8 * (n + 1) + 8 * (m + 1) + 4 * m + 4 * n + 12 * B
+            t._drop_engine()
+            return z, len(x)
+    else:
+        def e2e_step():
+            N.check(eng.L.lps_upload_f64(eng.h, host.data_ptr(), n + 1))
+            bs = np.arange(m, 2 * m, dtype=np.int32)
+            st_, k_, _ = solver.solve(bs, None, max_pivots=B)
+            z = -eng.read_row(m_loc)[n]
+            x = eng.read_col(n)
+            d2h_box[0] = 8 * (n + 1) + 8 * (m_loc + 1) + 4 * m
+            return z, len(x)
+
+    e2e_step()                                   # warm-up (engine creation, pinned mappings)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_val = e2e_steps * B / e2e_s
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on the same host tableau ----------
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        from oracle import c_oracle as C
+        sec1, _ = time_cpu_pivots(host_np, m, 1)
+        extra = int(max(1, min(16, 12.0 / max(sec1, 1e-3))))
+        sec, k = time_cpu_pivots(host_np, m, extra)
+        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": C.num_threads(), "kind": "port",
+               "sample": f"{k} consecutive pivots of the full {m} x {n} tableau after 1 warm-up pivot "
+                         "(oracle/pivot_oracle.c, pthread row-parallel)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4 fp64 {m}x{n} dense tableau, seed {a.seed}", "m": m, "n": n,
+                       "pivots_per_step": B, "sharding": f"rows/{world}", "rows_per_gpu": m_loc,
+                       "l2": "tableau (17.2 GB total) is larger than L2; no flush needed",
+                       "status_after": int(status), "pivots_timed": int(pivots)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": recorded_traffic(),
+                         "kernel": "k_update_f64", "bytes_per_launch": bytes_launch, "ms_per_launch": upd_avg_ms,
+                         "launches_timed": int(upd_launches), "peak_source": peak_src,
+                         "loop_frac": bytes_launch * pivots / (ms * 1e-3) / 1e9 / peak},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
+                    "d2h_bytes_per_step": d2h_box[0], "steps": e2e_steps, "pivots_per_step": B,
+                    "api": "Tableau.from_grid + Simplex + solve(max_pivots)" if world == 1 else
+                           "ShardedF64Solver: lps_upload_f64 + solve + read-back per rank"},
+            "gpu_launches": int(all_launches),
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--m", type=int, default=32768, help="constraint rows (n = 2m); default is config C4")
+    ap.add_argument("--pivots-per-step", type=int, default=32)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,7 @@ extern "C" {
 #define LPS_ZERO_PIVOT    3   /* tableau.py:300-301 ZeroDivisionError('zero pivot r,c')     */
 #define LPS_MAX_PIVOTS    4   /* stopped after the requested pivot prefix (not in reference) */
 #define LPS_BAD_PRIME     5   /* exact mode: next pivot is 0 modulo a prime; re-encode      */
+#define LPS_OBJ_INCREASED  6   /* simplex.py:133 'objective value increased (internal error)' */
 #define LPS_E_INVALID    -1   /* bad argument                                              */
 #define LPS_E_CUDA       -2   /* CUDA runtime error, see lps_last_error()                  */
 #define LPS_E_NOMEM      -3
@@ -85,6 +86,12 @@ int lps_download_f64(lps_handle *h, double *host, size_t ld_host);
 int lps_read_row_f64(lps_handle *h, int i, double *host);   /* n+1 doubles */
 int lps_read_col_f64(lps_handle *h, int j, double *host);   /* m+1 doubles */
 void *lps_grid_ptr(lps_handle *h);                          /* device pointer of the grid */
+/* Synthetic input (bench.py, tests): fill this handle's rows of the seeded dense
+ * family of SURVEY.md section 8(d) (n = 2 m_total, A in [lo,hi], slack identity,
+ * b in [hi*m/4, hi*m/2], costs -[lo,hi]) in place with a counter-based hash, so
+ * every shard can be generated on its own GPU.  Same values as
+ * problems.hashed_dense_grid() and the oracle's orc_fill_dense_f64(). */
+int lps_fill_dense_f64(lps_handle *h, unsigned long long seed, int lo, int hi);
 
 /* ---- the hot path --------------------------------------------------------- */
 /* Tableau.pivot(r,c) tableau.py:295-308 (with rowDiv :262, rowAddToObj :282,

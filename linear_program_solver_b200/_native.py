@@ -9,12 +9,12 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_longlong, c_size_t, c_uint32, c_void_p
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_longlong, c_size_t, c_uint32, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblps_b200.so")
 
-OK, OPTIMAL, UNBOUNDED, ZERO_PIVOT, MAX_PIVOTS, BAD_PRIME = 0, 1, 2, 3, 4, 5
+OK, OPTIMAL, UNBOUNDED, ZERO_PIVOT, MAX_PIVOTS, BAD_PRIME, STALLED = 0, 1, 2, 3, 4, 5, 6
 E_INVALID, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4
 RULE_DANTZIG, RULE_BLAND = 0, 1
 
@@ -45,6 +45,7 @@ SIGNATURES = {
     "lps_read_row_f64": (c_int, [c_void_p, c_int, c_void_p]),
     "lps_read_col_f64": (c_int, [c_void_p, c_int, c_void_p]),
     "lps_grid_ptr": (c_void_p, [c_void_p]),
+    "lps_fill_dense_f64": (c_int, [c_void_p, c_ulonglong, c_int, c_int]),
     "lps_pivot": (c_int, [c_void_p, c_int, c_int]),
     "lps_row_scale_f64": (c_int, [c_void_p, c_int, c_double]),
     "lps_row_axpy_f64": (c_int, [c_void_p, c_int, c_int, c_double]),

@@ -250,6 +250,18 @@ extern "C" int lps_read_col_f64(lps_handle* h, int j, double* host) {
     return LPS_OK;
 }
 
+
+extern "C" int lps_fill_dense_f64(lps_handle* h, unsigned long long seed, int lo, int hi) {
+    USE(h);
+    if (lo > hi) return fail(LPS_E_INVALID, "need lo <= hi");
+    if ((long long)h->n != 2 * h->m_total) return fail(LPS_E_INVALID, "the dense family has n = 2 m (n = %d, m = %lld)", h->n, h->m_total);
+    dim3 grid((unsigned)std::min<size_t>((h->ld + 255) / 256, 64), (unsigned)std::min(h->m + 1, 148 * 16));
+    k_fill_dense_f64<<<grid, 256, 0, h->stream>>>(grid_of(h), (uint64_t)seed, lo, hi);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------

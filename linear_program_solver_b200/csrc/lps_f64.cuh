@@ -430,4 +430,44 @@ __global__ void k_canon_rows(const int* colrow, int n, int* bcols) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// synthetic input: the seeded dense family of SURVEY.md section 8(d) generated in place with a
+// counter-based hash (same function in oracle/pivot_oracle.c and problems.hashed_dense_grid), so any
+// shard of the tableau can be produced independently on its own GPU
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t fill_mix(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t fill_draw(uint64_t seed, uint64_t i, uint64_t j, uint64_t span) {
+    return (fill_mix(fill_mix(seed) + i * 0x100000001B3ull + j) >> 33) % span;
+}
+constexpr uint64_t kFillSpecial = 0xFFFFFFFFull;   // pseudo row / column index of the cost row / rhs column
+
+__global__ void k_fill_dense_f64(F64Grid g, uint64_t seed, int lo, int hi) {
+    const long long mt = g.m_total;
+    const uint64_t span = (uint64_t)(hi - lo + 1);
+    const long long blo = (long long)hi * mt / 4, bhi = (long long)hi * mt / 2;
+    for (int il = blockIdx.y; il <= g.m; il += gridDim.y) {
+        double* row = g.T + (size_t)il * g.ld;
+        const bool obj = (il == g.m);
+        const uint64_t i = obj ? kFillSpecial : (uint64_t)(g.row0 + il);
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < (int)g.ld; j += gridDim.x * blockDim.x) {
+            double v = 0.0;
+            if (j < mt) {
+                const double a = (double)(lo + (long long)fill_draw(seed, i, (uint64_t)j, span));
+                v = obj ? -a : a;
+            } else if (j < g.n) {
+                v = (!obj && (long long)j - mt == (long long)i) ? 1.0 : 0.0;
+            } else if (j == g.n && !obj) {
+                v = (double)(blo + (long long)fill_draw(seed, i, kFillSpecial, (uint64_t)(bhi - blo + 1)));
+            }
+            row[j] = v;
+        }
+    }
+}
+
 }  // namespace lps

@@ -94,6 +94,10 @@ class F64Engine:
         N.check(self.L.lps_read_col_f64(self.h, j, out.ctypes.data))
         return out
 
+    def fill_dense(self, seed: int = 0, lo: int = 1, hi: int = 9):
+        """Generate this handle's rows of the hashed dense family (problems.hashed_dense_grid) in place."""
+        N.check(self.L.lps_fill_dense_f64(self.h, seed, lo, hi))
+
     # -- hot path ------------------------------------------------------------------------------
     def pivot(self, r: int, c: int) -> int:
         return N.check(self.L.lps_pivot(self.h, r, c))

@@ -64,6 +64,40 @@ def equality_lp(m: int, n: int, seed: int = 0, lo: int = -5, hi: int = 9) -> Gri
     return c, A, b
 
 
+def _mix(x):
+    import numpy as np
+    x = x + np.uint64(0x9E3779B97F4A7C15)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def hashed_dense_grid(m: int, seed: int = 0, lo: int = 1, hi: int = 9, row0: int = 0, m_local: int = None):
+    """The dense family from a counter-based hash instead of a sequential generator, as an
+    int64 (m_local+1, 2m+1) grid in device layout: rows [row0, row0+m_local) plus the cost row.
+
+    This is the function the CUDA library's `lps_fill_dense_f64` evaluates on the device (any
+    shard can be generated independently); same shape and ranges as `dense_lp`.
+    """
+    import numpy as np
+    if m_local is None:
+        m_local = m - row0
+    special = np.uint64(0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        s2 = _mix(np.uint64(seed))
+        rows = np.concatenate([np.arange(row0, row0 + m_local, dtype=np.uint64), [special]])
+        key = s2 + rows[:, None] * np.uint64(0x100000001B3)
+        draw = (_mix(key + np.arange(m, dtype=np.uint64)[None, :]) >> np.uint64(33)) % np.uint64(hi - lo + 1)
+        rhs = (_mix(key[:, 0] + special) >> np.uint64(33)) % np.uint64(hi * m // 2 - hi * m // 4 + 1)
+    grid = np.zeros((m_local + 1, 2 * m + 1), dtype=np.int64)
+    grid[:, :m] = lo + draw.astype(np.int64)
+    grid[m_local, :m] *= -1
+    idx = np.arange(m_local)
+    grid[idx, m + row0 + idx] = 1
+    grid[:m_local, 2 * m] = hi * m // 4 + rhs[:m_local].astype(np.int64)
+    return grid
+
+
 #: Beale's cycling example (SURVEY.md section 8c item 2): exercises the stale
 #: objective "stuck" counter and the switch from Dantzig to Bland pricing.
 BEALE = (

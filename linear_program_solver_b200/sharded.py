@@ -1,0 +1,91 @@
+"""Row-sharded fp64 tableau: one process per GPU, one exchange per pivot.
+
+Rank g holds constraint rows [g*m/G, (g+1)*m/G) plus its own replica of the objective row.  Per
+pivot: every rank prices the (identical) objective row and ratio-tests its own rows
+(`lps_step_select`), the candidates -- 64-byte header (ratio, global row, column, rule) followed
+by the normalised candidate row -- are all-gathered over NCCL/NVLink, and every rank picks the
+same winner (lowest ratio, then lowest global row: simplex.py:277) and applies the rank-1 update
+to its rows (`lps_step_update`).  The all-gather is the argmin-allreduce and the pivot-row
+broadcast of the north star in one collective.  No host round trip inside a burst of pivots.
+
+`engine_factory` exists so that the host-side protocol can be exercised on CPU (gloo) with a
+stand-in engine supplied by the tests; the product default is the CUDA `F64Engine`.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+
+def shard_rows(m_total: int, rank: int, nranks: int) -> Tuple[int, int]:
+    """(row0, m_local) of the contiguous row block owned by `rank`."""
+    lo = m_total * rank // nranks
+    hi = m_total * (rank + 1) // nranks
+    return lo, hi - lo
+
+
+class ShardedF64Solver:
+    def __init__(self, m_total: int, n: int, rank: int = 0, nranks: int = 1, device: Optional[int] = None,
+                 group=None, engine_factory: Optional[Callable] = None, burst: Optional[int] = None):
+        self.m_total, self.n, self.rank, self.nranks, self.group = int(m_total), int(n), rank, nranks, group
+        self.row0, self.m_local = shard_rows(m_total, rank, nranks)
+        if self.m_local <= 0:
+            raise ValueError(f"rank {rank} of {nranks} would own no rows of a {m_total}-row tableau")
+        if engine_factory is None:
+            from .engine import F64Engine
+            engine_factory = F64Engine
+        self.eng = engine_factory(self.m_local, self.n, device)
+        if nranks > 1:
+            self.eng.set_shard(self.row0, self.m_total, rank, nranks)
+        # pivots enqueued between two host checks: ~2 ms of device work, between 4 and 256
+        est_us = max(4.0, (self.m_local + 1) * (self.n + 1) * 16.0 / 5.0e6)
+        self.burst = burst or int(max(4, min(256, 2000.0 / est_us)))
+        self._active = False
+
+    def close(self):
+        self.eng.close()
+
+    # -- one pivot: select, exchange, update -------------------------------------------------------
+    def _exchange(self):
+        if self.nranks > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.eng.cand_all, self.eng.cand_send, group=self.group)
+
+    def enqueue(self, pivots: int):
+        """Enqueue `pivots` (select, exchange, update) triples without waiting for the device."""
+        eng = self.eng
+        for _ in range(pivots):
+            eng.step_select()
+            self._exchange()
+            eng.step_update()
+
+    # -- Simplex.solve (simplex.py:110-148) over all shards ----------------------------------------
+    def begin(self, basis: np.ndarray, marks: Optional[np.ndarray] = None, max_pivots: int = -1, trace_cap: int = 0):
+        assert basis.dtype == np.int32 and basis.size == self.m_total
+        self.eng.solve_begin(basis, marks, max_pivots, trace_cap)
+        self._active = True
+
+    def poll(self) -> Tuple[int, int]:
+        return self.eng.poll()
+
+    def end(self, basis: np.ndarray, marks: Optional[np.ndarray] = None, trace_cap: int = 0):
+        self._active = False
+        return self.eng.solve_end(basis, marks, trace_cap)
+
+    def solve(self, basis: np.ndarray, marks: Optional[np.ndarray] = None, max_pivots: int = -1, trace_cap: int = 0):
+        """Returns (status, pivots, trace) -- identical on every rank."""
+        self.begin(basis, marks, max_pivots, trace_cap)
+        done = 0
+        while True:
+            now = self.burst if max_pivots < 0 else min(self.burst, max_pivots - done)
+            self.enqueue(now)
+            done += now
+            if now == 0:
+                self.eng.step_select()      # lets the device report LPS_MAX_PIVOTS (or optimality)
+            status, _ = self.poll()
+            if status != N.OK:
+                break
+        return self.end(basis, marks, trace_cap)

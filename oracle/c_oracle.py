@@ -38,6 +38,9 @@ def lib():
         L.orc_pivot_modp.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32]
         L.orc_pivot_modp.restype = None
+        L.orc_fill_dense_f64.argtypes = [dp, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
+                                         ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int]
+        L.orc_fill_dense_f64.restype = None
         _lib = L
     return _lib
 
@@ -86,3 +89,9 @@ def solve(T: np.ndarray, basis: np.ndarray, max_pivots: int = -1, want_trace: bo
 def pivot_modp(N: np.ndarray, r: int, c: int, q: int, dinv: int) -> None:
     m, n = N.shape[0] - 1, N.shape[1] - 1
     lib().orc_pivot_modp(N.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), m, n, N.strides[0] // 4, r, c, q, dinv)
+
+
+def fill_dense(T: np.ndarray, m_total: int, row0: int = 0, seed: int = 0, lo: int = 1, hi: int = 9) -> None:
+    """Fill T ((m_local+1, ld) float64, ld >= 2*m_total+1) with rows [row0, row0+m_local) of the hashed dense family."""
+    m_local = T.shape[0] - 1
+    lib().orc_fill_dense_f64(_dp(T), m_total, row0, m_local, 2 * m_total, T.strides[0] // 8, seed, lo, hi)

@@ -59,11 +59,11 @@ static void *span_main(void *arg) {
 
 static void for_rows(row_fn fn, void *ctx, int nrows) {
     int k = orc_num_threads();
-    if (k > 64) k = 64;
+    if (k > 256) k = 256;
     if (k > nrows) k = nrows;
     if (k <= 1) { fn(ctx, 0, nrows); return; }
-    pthread_t tid[64];
-    span_t span[64];
+    pthread_t tid[256];
+    span_t span[256];
     for (int t = 0; t < k; ++t) {
         span[t].fn = fn; span[t].ctx = ctx;
         span[t].lo = (int)((long)nrows * t / k);
@@ -186,4 +186,52 @@ void orc_pivot_modp(uint32_t *N, int m, int n, size_t ld, int r, int c,
                     uint32_t q, uint32_t dinv) {
     modp_ctx ctx = { N, N + (size_t)r * ld, ld, n, r, c, q, dinv };
     for_rows(modp_rows, &ctx, m + 1);
+}
+
+/*
+ * Synthetic input: the seeded dense family of SURVEY.md section 8(d) from a
+ * counter-based hash (the same function as problems.hashed_dense_grid and the
+ * CUDA library's input generator), rows [row0, row0 + m_local) of an
+ * m_total-row tableau plus the objective row, written into T ((m_local+1) x ld).
+ */
+static uint64_t fill_mix(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static uint64_t fill_draw(uint64_t seed, uint64_t i, uint64_t j, uint64_t span) {
+    return (fill_mix(fill_mix(seed) + i * 0x100000001B3ull + j) >> 33) % span;
+}
+#define FILL_SPECIAL 0xFFFFFFFFull
+
+typedef struct { double *T; size_t ld; long mt, row0; int m_local, n; uint64_t seed; int lo, hi; } fill_ctx;
+
+static void fill_rows(void *vctx, int lo_row, int hi_row) {
+    fill_ctx *x = (fill_ctx *)vctx;
+    const uint64_t span = (uint64_t)(x->hi - x->lo + 1);
+    const long blo = (long)x->hi * x->mt / 4, bhi = (long)x->hi * x->mt / 2;
+    for (int il = lo_row; il < hi_row; ++il) {
+        double *row = x->T + (size_t)il * x->ld;
+        const int obj = (il == x->m_local);
+        const uint64_t i = obj ? FILL_SPECIAL : (uint64_t)(x->row0 + il);
+        for (long j = 0; j < (long)x->ld; ++j) {
+            double v = 0.0;
+            if (j < x->mt) {
+                double a = (double)(x->lo + (long)fill_draw(x->seed, i, (uint64_t)j, span));
+                v = obj ? -a : a;
+            } else if (j < x->n) {
+                v = (!obj && j - x->mt == (long)i) ? 1.0 : 0.0;
+            } else if (j == x->n && !obj) {
+                v = (double)(blo + (long)fill_draw(x->seed, i, FILL_SPECIAL, (uint64_t)(bhi - blo + 1)));
+            }
+            row[j] = v;
+        }
+    }
+}
+
+void orc_fill_dense_f64(double *T, long m_total, long row0, int m_local, int n, size_t ld,
+                        unsigned long long seed, int lo, int hi) {
+    fill_ctx ctx = { T, ld, m_total, row0, m_local, n, (uint64_t)seed, lo, hi };
+    for_rows(fill_rows, &ctx, m_local + 1);
 }
