@@ -142,6 +142,38 @@ int lps_solve_poll(lps_handle *h, int *status, long long *npiv);
 int lps_solve_end(lps_handle *h, int *basis, int *marks, int *trace, long long trace_cap,
                   long long *npiv);
 
+
+/* ---- exact mode: fraction-free integer tableau as residues modulo 31-bit primes ----
+ * The reference's arithmetic is fractions.Fraction (tableau.py:2,130-158).  The device holds an
+ * integer grid N and one common denominator D as residues modulo `nprimes` primes (one prime per
+ * grid slice), such that the reference's entry (i,j) is N_ij / (D * sigma_i); sigma_i is a positive
+ * per-row scale (1 for integer inputs) that a row keeps until it is first pivoted.  The caller
+ * sizes the prime set from a Hadamard bound on the minors of the uploaded integer matrix.
+ * lps_pivot / lps_find_pivot / lps_is_canonical / lps_is_optimal / lps_solve work on either mode.
+ * LPS_BAD_PRIME (a prime divides the next pivot element; nothing was changed) asks the caller to
+ * re-encode with a different prime set. */
+size_t lps_exact_ld(int n);
+int lps_create_exact(int m, int n, int nprimes, const uint32_t *primes, int device, void *stream,
+                     lps_handle **out);
+/* Upload: entry (i,j) of the (m+1) x ld_host host grid is a signed integer of `nlimbs`
+ * little-endian 32-bit limbs (magnitude) at limbs[(i*ld_host+j)*nlimbs] with sign neg[i*ld_host+j];
+ * sigma_limbs holds the m+1 row scales the same way.  Resets D to 1 (setA/setB/setC/setZ,
+ * tableau.py:128-166). */
+int lps_upload_exact(lps_handle *h, const uint32_t *limbs, int nlimbs, const unsigned char *neg,
+                     size_t ld_host, const uint32_t *sigma_limbs, int sigma_nlimbs);
+/* Read-out (getters, tableau.py:82-108) by mixed-radix reconstruction on the device.
+ * what 0: row `index` (n+1 numbers), 1: column `index` (m+1 numbers), 2: the denominator D.
+ * sign_out[e] in {-1,0,1}; digits_out[k*count+e] is digit k of |x_e| in the mixed radix
+ * (p_0, p_1, ...): |x| = d_0 + d_1 p_0 + d_2 p_0 p_1 + ...   */
+int lps_read_exact(lps_handle *h, int what, int index, signed char *sign_out, uint32_t *digits_out);
+int lps_read_alive(lps_handle *h, int *alive);   /* m+1 flags: row still carries its sigma_i */
+int lps_exact_info(lps_handle *h, int *nprimes, int *bad_prime, size_t *residue_bytes);
+/* Loop state of Simplex.solve (simplex.py:117-137: rule in force, stuck counter, whether the
+ * objective has moved since entry, pending objective check).  set == 0 reads it; set != 0 writes it
+ * and makes the next lps_solve continue from it (resuming after LPS_BAD_PRIME on a re-encoded
+ * tableau without disturbing the reference's rule-switch sequence). */
+int lps_exact_loop_state(lps_handle *h, int set, int *rule, long long *stuck, int *moved, int *pending);
+
 /* Timing aid for bench.py: CUDA-event time (ms) and launch count of the
  * rank-1 update kernels enqueued since the last reset, measured on the
  * handle's own stream. */

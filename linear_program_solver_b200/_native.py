@@ -58,6 +58,13 @@ SIGNATURES = {
     "lps_step_update": (c_int, [c_void_p]),
     "lps_solve_poll": (c_int, [c_void_p, POINTER(c_int), POINTER(c_longlong)]),
     "lps_solve_end": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, POINTER(c_longlong)]),
+    "lps_exact_ld": (c_size_t, [c_int]),
+    "lps_create_exact": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, POINTER(c_void_p)]),
+    "lps_upload_exact": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_int]),
+    "lps_read_exact": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "lps_read_alive": (c_int, [c_void_p, c_void_p]),
+    "lps_exact_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
+    "lps_exact_loop_state": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_longlong), POINTER(c_int), POINTER(c_int)]),
     "lps_prof_reset": (c_int, [c_void_p]),
     "lps_prof_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong), POINTER(c_longlong)]),
 }

@@ -10,76 +10,20 @@
 #include <new>
 #include <vector>
 
-#include "../../include/lps_b200.h"
-#include "lps_f64.cuh"
-
-using namespace lps;
+#include "lps_internal.h"
 
 // ------------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int lps_fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
 }
-#define CU(call)                                                                                      \
-    do {                                                                                              \
-        cudaError_t e_ = (call);                                                                      \
-        if (e_ != cudaSuccess) return fail(LPS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// handle
-// ------------------------------------------------------------------------------------------------
-constexpr int kWideChunk = 1024;     // doubles per column chunk for large grids
-constexpr int kNarrowChunk = 512;    // ... for small ones (more CTAs)
-constexpr size_t kL2Bytes = 120ull << 20;
-
-struct lps_handle {
-    int mode = 0;                    // 0 = fp64
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    int m = 0, n = 0;
-    size_t ld = 0;
-    long long row0 = 0, m_total = 0;
-    int rank = 0, nranks = 1;
-
-    double* T = nullptr;
-    bool own_T = false;
-    double* ucol = nullptr;
-    unsigned char* cand_send = nullptr;
-    unsigned char* cand_all = nullptr;
-    bool own_cand = false;
-    size_t cand_stride = 0;
-
-    int chunk = kWideChunk, nchunks = 0, rows_per_cta = 64, sel_blocks = 1;
-    bool stream_hint = false;
-    double* pd_val = nullptr;
-    int* pd_idx = nullptr;
-    int* pb_idx = nullptr;
-    ArgMinF64* sel_blk = nullptr;
-    SolveState* st = nullptr;
-    SolveState* st_host = nullptr;   // pinned mirror
-    int* basis = nullptr;            // m_total ints
-    int* marks = nullptr;            // n ints
-    bool use_marks = false;
-    int* trace = nullptr;
-    long long trace_cap = 0;
-    int* scratch_i = nullptr;        // n + 8 ints (isCanonical)
-    bool solving = false;
-
-    // profiling of the update kernel
-    bool prof = false;
-    std::vector<cudaEvent_t> ev;
-    size_t ev_used = 0;
-    long long launches_update = 0, launches_all = 0;
-};
 
 static F64Grid grid_of(const lps_handle* h) {
     F64Grid g;
@@ -88,16 +32,11 @@ static F64Grid grid_of(const lps_handle* h) {
 }
 static PricePartials partials_of(const lps_handle* h) { return PricePartials{h->pd_val, h->pd_idx, h->pb_idx}; }
 
-static int use(const lps_handle* h) {
+int lps_use(const lps_handle* h) {
     if (!h) return fail(LPS_E_INVALID, "null handle");
     CU(cudaSetDevice(h->device));
     return LPS_OK;
 }
-#define USE(h)                         \
-    do {                               \
-        int rc_ = use(h);              \
-        if (rc_ != LPS_OK) return rc_; \
-    } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // library
@@ -176,6 +115,7 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
 extern "C" int lps_set_shard(lps_handle* h, long long row0, long long m_total, int rank, int nranks, void* cand_send,
                              void* cand_all) {
     USE(h);
+    NEED_MODE(h, 0);
     if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(LPS_E_INVALID, "bad rank %d of %d", rank, nranks);
     if (row0 < 0 || row0 + h->m > m_total) return fail(LPS_E_INVALID, "rows [%lld,%lld) outside 0..%lld", row0, row0 + h->m, m_total);
     if (nranks > 1 && (!cand_send || !cand_all)) return fail(LPS_E_INVALID, "sharded handles need candidate buffers");
@@ -193,6 +133,7 @@ extern "C" int lps_set_shard(lps_handle* h, long long row0, long long m_total, i
 
 extern "C" int lps_destroy(lps_handle* h) {
     if (!h) return LPS_OK;
+    if (h->mode == 1) return lpsx_destroy(h);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -212,13 +153,14 @@ extern "C" int lps_sync(lps_handle* h) {
     CU(cudaStreamSynchronize(h->stream));
     return LPS_OK;
 }
-extern "C" void* lps_grid_ptr(lps_handle* h) { return h ? (void*)h->T : nullptr; }
+extern "C" void* lps_grid_ptr(lps_handle* h) { return (h && h->mode == 0) ? (void*)h->T : nullptr; }
 
 // ------------------------------------------------------------------------------------------------
 // transfers
 // ------------------------------------------------------------------------------------------------
 extern "C" int lps_upload_f64(lps_handle* h, const double* host, size_t ld_host) {
     USE(h);
+    NEED_MODE(h, 0);
     if (!host || ld_host < (size_t)h->n + 1) return fail(LPS_E_INVALID, "bad host grid");
     CU(cudaMemcpy2DAsync(h->T, h->ld * sizeof(double), host, ld_host * sizeof(double), ((size_t)h->n + 1) * sizeof(double),
                          (size_t)h->m + 1, cudaMemcpyHostToDevice, h->stream));
@@ -228,6 +170,7 @@ extern "C" int lps_upload_f64(lps_handle* h, const double* host, size_t ld_host)
 }
 extern "C" int lps_download_f64(lps_handle* h, double* host, size_t ld_host) {
     USE(h);
+    NEED_MODE(h, 0);
     if (!host || ld_host < (size_t)h->n + 1) return fail(LPS_E_INVALID, "bad host grid");
     CU(cudaMemcpy2DAsync(host, ld_host * sizeof(double), h->T, h->ld * sizeof(double), ((size_t)h->n + 1) * sizeof(double),
                          (size_t)h->m + 1, cudaMemcpyDeviceToHost, h->stream));
@@ -236,6 +179,7 @@ extern "C" int lps_download_f64(lps_handle* h, double* host, size_t ld_host) {
 }
 extern "C" int lps_read_row_f64(lps_handle* h, int i, double* host) {
     USE(h);
+    NEED_MODE(h, 0);
     if (!host || i < 0 || i > h->m) return fail(LPS_E_INVALID, "row %d out of range", i);
     CU(cudaMemcpyAsync(host, h->T + (size_t)i * h->ld, ((size_t)h->n + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -243,6 +187,7 @@ extern "C" int lps_read_row_f64(lps_handle* h, int i, double* host) {
 }
 extern "C" int lps_read_col_f64(lps_handle* h, int j, double* host) {
     USE(h);
+    NEED_MODE(h, 0);
     if (!host || j < 0 || j > h->n) return fail(LPS_E_INVALID, "column %d out of range", j);
     CU(cudaMemcpy2DAsync(host, sizeof(double), h->T + j, h->ld * sizeof(double), sizeof(double), (size_t)h->m + 1,
                          cudaMemcpyDeviceToHost, h->stream));
@@ -253,6 +198,7 @@ extern "C" int lps_read_col_f64(lps_handle* h, int j, double* host) {
 
 extern "C" int lps_fill_dense_f64(lps_handle* h, unsigned long long seed, int lo, int hi) {
     USE(h);
+    NEED_MODE(h, 0);
     if (lo > hi) return fail(LPS_E_INVALID, "need lo <= hi");
     if ((long long)h->n != 2 * h->m_total) return fail(LPS_E_INVALID, "the dense family has n = 2 m (n = %d, m = %lld)", h->n, h->m_total);
     dim3 grid((unsigned)std::min<size_t>((h->ld + 255) / 256, 64), (unsigned)std::min(h->m + 1, 148 * 16));
@@ -314,17 +260,12 @@ static int write_state(lps_handle* h, const SolveState& s) {
     CU(cudaStreamSynchronize(h->stream));   // st_host is reused
     return LPS_OK;
 }
-#define TRY(x)                       \
-    do {                             \
-        int rc_ = (x);               \
-        if (rc_ < 0) return rc_;     \
-    } while (0)
-
 // ------------------------------------------------------------------------------------------------
 // hot path entry points
 // ------------------------------------------------------------------------------------------------
 extern "C" int lps_pivot(lps_handle* h, int r, int c) {
     USE(h);
+    if (h->mode == 1) return lpsx_pivot(h, r, c);
     if (h->nranks != 1) return fail(LPS_E_STATE, "explicit pivots are not supported on a sharded handle");
     if (r < 0 || r >= h->m || c < 0 || c >= h->n) return fail(LPS_E_INVALID, "pivot (%d,%d) out of range", r, c);
     SolveState s{};
@@ -342,6 +283,7 @@ extern "C" int lps_pivot(lps_handle* h, int r, int c) {
 
 extern "C" int lps_row_scale_f64(lps_handle* h, int r, double mult) {
     USE(h);
+    NEED_MODE(h, 0);
     if (r < 0 || r >= h->m) return fail(LPS_E_INVALID, "row %d out of range", r);
     if (mult == 1.0) return LPS_OK;   // tableau.py:257
     k_row_scale_f64<<<std::min((h->n + 256) / 256, 592), 256, 0, h->stream>>>(grid_of(h), r, mult);
@@ -351,6 +293,7 @@ extern "C" int lps_row_scale_f64(lps_handle* h, int r, double mult) {
 }
 extern "C" int lps_row_axpy_f64(lps_handle* h, int rd, int rs, double mult) {
     USE(h);
+    NEED_MODE(h, 0);
     if (rd < 0 || rd > h->m || rs < 0 || rs >= h->m) return fail(LPS_E_INVALID, "rows (%d,%d) out of range", rd, rs);
     if (mult == 0.0) return LPS_OK;   // tableau.py:272, :285
     k_row_axpy_f64<<<std::min((h->n + 256) / 256, 592), 256, 0, h->stream>>>(grid_of(h), rd, rs, mult);
@@ -362,6 +305,7 @@ extern "C" int lps_row_axpy_f64(lps_handle* h, int rd, int rs, double mult) {
 extern "C" int lps_find_pivot(lps_handle* h, int rule, int* r, int* c) {
     USE(h);
     if (!r || !c || (rule != LPS_RULE_DANTZIG && rule != LPS_RULE_BLAND)) return fail(LPS_E_INVALID, "bad arguments");
+    if (h->mode == 1) return lpsx_find_pivot(h, rule, r, c);
     if (h->nranks != 1) return fail(LPS_E_STATE, "find_pivot on a sharded handle: use the stepping calls");
     SolveState s{};
     s.status = LPS_OK; s.rule = rule; s.max_pivots = -1; s.dry_run = 1;
@@ -389,6 +333,7 @@ extern "C" int lps_is_optimal(lps_handle* h, int* optimal) {
 extern "C" int lps_is_canonical(lps_handle* h, int* bcols, int* canonical) {
     USE(h);
     if (!canonical) return fail(LPS_E_INVALID, "null result");
+    if (h->mode == 1) return lpsx_is_canonical(h, bcols, canonical);
     if (h->nranks != 1) return fail(LPS_E_STATE, "is_canonical on a sharded handle");
     int* flag = h->scratch_i + h->n;
     CU(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
@@ -421,6 +366,7 @@ extern "C" int lps_is_canonical(lps_handle* h, int* bcols, int* canonical) {
 // ---- the solve loop ------------------------------------------------------------------------------
 extern "C" int lps_solve_begin(lps_handle* h, long long max_pivots, const int* basis, const int* marks, long long trace_cap) {
     USE(h);
+    NEED_MODE(h, 0);
     if (h->solving) return fail(LPS_E_STATE, "solve already in progress");
     if (basis) CU(cudaMemcpyAsync(h->basis, basis, (size_t)h->m_total * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     h->use_marks = marks != nullptr;
@@ -445,16 +391,19 @@ extern "C" int lps_solve_begin(lps_handle* h, long long max_pivots, const int* b
 }
 extern "C" int lps_step_select(lps_handle* h) {
     USE(h);
+    NEED_MODE(h, 0);
     if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
     return launch_select(h);
 }
 extern "C" int lps_step_update(lps_handle* h) {
     USE(h);
+    NEED_MODE(h, 0);
     if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
     return launch_update(h, 1);
 }
 extern "C" int lps_solve_poll(lps_handle* h, int* status, long long* npiv) {
     USE(h);
+    NEED_MODE(h, 0);
     TRY(read_state(h));
     if (status) *status = h->st_host->status;
     if (npiv) *npiv = h->st_host->npiv;
@@ -462,6 +411,7 @@ extern "C" int lps_solve_poll(lps_handle* h, int* status, long long* npiv) {
 }
 extern "C" int lps_solve_end(lps_handle* h, int* basis, int* marks, int* trace, long long trace_cap, long long* npiv) {
     USE(h);
+    NEED_MODE(h, 0);
     if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
     TRY(read_state(h));
     h->solving = false;
@@ -481,6 +431,7 @@ extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* m
     USE(h);
     if (h->nranks != 1) return fail(LPS_E_STATE, "lps_solve on a sharded handle: drive it with the stepping calls");
     if (!basis) return fail(LPS_E_INVALID, "null basis");
+    if (h->mode == 1) return lpsx_solve(h, max_pivots, basis, marks, trace, trace_cap, npiv);
     TRY(lps_solve_begin(h, max_pivots, basis, marks, trace ? trace_cap : 0));
     // pivots enqueued per host check: about 2 ms of device work, between 4 and 256; a pivot
     // prefix never enqueues more (select, update) pairs than it may commit

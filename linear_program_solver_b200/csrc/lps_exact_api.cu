@@ -1,0 +1,499 @@
+// Exact-mode half of the C-ABI (include/lps_b200.h): host-side orchestration of the kernels in
+// lps_exact.cuh.  No arithmetic of the path runs here: the host only sizes buffers, precomputes the
+// prime-dependent tables and enqueues launches.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "lps_internal.h"
+#include "lps_exact.cuh"
+
+struct ExactData {
+    int P = 0, spt = 1, lane_threads = 1024;
+    PrimeQ* pr = nullptr;
+    uint32_t* invtab = nullptr;
+    uint32_t* half = nullptr;
+    double* wmant = nullptr;
+    int* wexp = nullptr;
+    uint32_t* R = nullptr;
+    size_t ld = 0, plane = 0;
+    uint32_t *Dres = nullptr, *dinv_m = nullptr, *alpha_m = nullptr;
+    uint32_t* nbeta = nullptr;
+    size_t nbeta_ld = 0;
+    uint32_t *sigma = nullptr, *one = nullptr;
+    size_t sstride = 0;
+    int* alive = nullptr;
+    signed char *obj_sign = nullptr, *cr_sign = nullptr, *rd_sign = nullptr;
+    int *obj_top = nullptr, *cr_top = nullptr, *rd_top = nullptr;
+    double *obj_mant = nullptr, *cr_mant = nullptr, *rd_mant = nullptr;
+    uint32_t *obj_dig = nullptr, *rd_dig = nullptr;
+    size_t obj_dstride = 0, rd_stride = 0;
+    int* cand = nullptr;
+    XState* st = nullptr;
+    XState* st_host = nullptr;
+    int chunk = 2048, rows_per_cta = 64;
+    bool stream_hint = false;
+    bool resume = false;             // next lps_solve continues the loop state set by lps_exact_loop_state
+};
+
+static XGrid xgrid_of(const lps_handle* h) {
+    const ExactData* x = h->x;
+    XGrid g;
+    g.R = x->R; g.ld = x->ld; g.plane = x->plane; g.m = h->m; g.n = h->n; g.P = x->P;
+    g.pr = x->pr; g.invtab = x->invtab; g.half = x->half; g.wmant = x->wmant; g.wexp = x->wexp;
+    return g;
+}
+static XPivotConst pconst_of(const lps_handle* h) { return XPivotConst{h->x->Dres, h->x->dinv_m, h->x->alpha_m}; }
+
+extern "C" size_t lps_exact_ld(int n) { return ((size_t)n + 1 + 31) / 32 * 32; }
+
+static PrimeQ make_prime(uint32_t q) {
+    PrimeQ p;
+    p.q = q;
+    uint32_t inv = q;                                   // Newton: q * inv = 1 mod 2^32
+    for (int i = 0; i < 5; ++i) inv *= 2u - q * inv;
+    p.qinv = 0u - inv;
+    p.r1 = (uint32_t)((1ull << 32) % q);
+    p.r2 = (uint32_t)(((unsigned __int128)1 << 64) % q);
+    return p;
+}
+
+#define CUX(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            lpsx_destroy(h);                                                                        \
+            return fail(e_ == cudaErrorMemoryAllocation ? LPS_E_NOMEM : LPS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                           \
+    } while (0)
+
+extern "C" int lps_create_exact(int m, int n, int nprimes, const uint32_t* primes, int device, void* stream, lps_handle** out) {
+    if (!out) return fail(LPS_E_INVALID, "null out");
+    *out = nullptr;
+    if (m <= 0) return fail(LPS_E_INVALID, "need m > 0, provided m = %d", m);
+    if (n <= 0) return fail(LPS_E_INVALID, "need n > 0, provided n = %d", n);
+    if (nprimes <= 0 || nprimes > 1024 * kMaxSPT || !primes) return fail(LPS_E_INVALID, "need 1..%d primes", 1024 * kMaxSPT);
+    for (int k = 0; k < nprimes; ++k) {
+        if (!(primes[k] & 1u) || primes[k] < 3u || primes[k] >= (1u << 31)) return fail(LPS_E_INVALID, "prime %u is not an odd number below 2^31", primes[k]);
+        for (int j = 0; j < k; ++j)
+            if (primes[j] == primes[k]) return fail(LPS_E_INVALID, "prime %u listed twice", primes[k]);
+    }
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(LPS_E_INVALID, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    lps_handle* h = new (std::nothrow) lps_handle();
+    ExactData* x = new (std::nothrow) ExactData();
+    if (!h || !x) { delete h; delete x; return fail(LPS_E_NOMEM, "out of host memory"); }
+    h->mode = 1; h->x = x; h->device = device; h->m = m; h->n = n; h->m_total = m;
+    if (stream) h->stream = (cudaStream_t)stream;
+    else { CUX(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    const int P = nprimes;
+    x->P = P;
+    x->spt = P <= 1024 ? 1 : kMaxSPT;
+    x->lane_threads = P <= 1024 ? std::max(32, (P + 31) / 32 * 32) : 1024;
+    x->ld = lps_exact_ld(n);
+    h->ld = x->ld;
+    x->plane = (size_t)(m + 1) * x->ld;
+
+    // prime-dependent tables (host side, exact integer / long double arithmetic)
+    std::vector<PrimeQ> pr(P);
+    for (int k = 0; k < P; ++k) pr[k] = make_prime(primes[k]);
+    std::vector<uint32_t> half(P);
+    {   // (M-1)/2 in the mixed radix (p_0, p_1, ...): long division by 2 from the top digit of M-1
+        uint64_t carry = 0;
+        for (int k = P - 1; k >= 0; --k) {
+            const uint64_t cur = carry * primes[k] + (primes[k] - 1u);
+            half[k] = (uint32_t)(cur / 2);
+            carry = cur & 1u;
+        }
+    }
+    std::vector<double> wm(P + 1);
+    std::vector<int> we(P + 1);
+    {
+        long double mant = 0.5L;
+        int ex = 1;                                       // W_0 = 1 = 0.5 * 2^1
+        wm[0] = (double)mant; we[0] = ex;
+        for (int t = 1; t <= P; ++t) {
+            int e2;
+            mant = frexpl(mant * (long double)primes[t - 1], &e2);
+            ex += e2;
+            wm[t] = (double)mant; we[t] = ex;
+        }
+    }
+    CUX(cudaMalloc(&x->pr, P * sizeof(PrimeQ)));
+    CUX(cudaMemcpyAsync(x->pr, pr.data(), P * sizeof(PrimeQ), cudaMemcpyHostToDevice, h->stream));
+    CUX(cudaMalloc(&x->half, P * sizeof(uint32_t)));
+    CUX(cudaMemcpyAsync(x->half, half.data(), P * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CUX(cudaMalloc(&x->wmant, (P + 1) * sizeof(double)));
+    CUX(cudaMemcpyAsync(x->wmant, wm.data(), (P + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUX(cudaMalloc(&x->wexp, (P + 1) * sizeof(int)));
+    CUX(cudaMemcpyAsync(x->wexp, we.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUX(cudaStreamSynchronize(h->stream));                // the host vectors go out of scope below
+    CUX(cudaMalloc(&x->invtab, (size_t)P * P * sizeof(uint32_t)));
+    k_xinvtab<<<dim3((P + 127) / 128, P), 128, 0, h->stream>>>(x->pr, P, x->invtab);
+    CUX(cudaGetLastError());
+
+    const size_t bytes = (size_t)P * x->plane * sizeof(uint32_t);
+    {
+        cudaError_t e = cudaMalloc(&x->R, bytes);
+        if (e != cudaSuccess) { lpsx_destroy(h); return fail(LPS_E_NOMEM, "cudaMalloc of %zu bytes (%d primes) failed: %s", bytes, P, cudaGetErrorString(e)); }
+    }
+    CUX(cudaMemsetAsync(x->R, 0, bytes, h->stream));
+    x->stream_hint = bytes > kL2Bytes;
+    // column chunks of 2048 / 1024 residues, row blocks sized so that small tableaux still fill the SMs
+    const size_t cells = x->plane * P;
+    if (cells >= (size_t)148 * 8 * 2048 * 64) { x->chunk = 2048; x->rows_per_cta = 64; }
+    else if (cells >= (size_t)148 * 4 * 1024 * 16) { x->chunk = 1024; x->rows_per_cta = 16; }
+    else { x->chunk = 1024; x->rows_per_cta = 8; }
+    x->nbeta_ld = ((size_t)m + 1 + kXMaxRowBlock - 1) / kXMaxRowBlock * kXMaxRowBlock + kXMaxRowBlock;
+    CUX(cudaMalloc(&x->nbeta, (size_t)P * x->nbeta_ld * sizeof(uint32_t)));
+    CUX(cudaMemsetAsync(x->nbeta, 0, (size_t)P * x->nbeta_ld * sizeof(uint32_t), h->stream));
+    CUX(cudaMalloc(&x->Dres, P * sizeof(uint32_t)));
+    CUX(cudaMalloc(&x->dinv_m, P * sizeof(uint32_t)));
+    CUX(cudaMalloc(&x->alpha_m, P * sizeof(uint32_t)));
+    x->sstride = ((size_t)m + 1 + 3) / 4 * 4;
+    CUX(cudaMalloc(&x->sigma, (size_t)P * x->sstride * sizeof(uint32_t)));
+    CUX(cudaMalloc(&x->one, (size_t)P * x->sstride * sizeof(uint32_t)));
+    CUX(cudaMalloc(&x->alive, ((size_t)m + 1) * sizeof(int)));
+    const size_t nobj = (size_t)n + 1, ncr = 2 * ((size_t)m + 1), nrd = std::max(nobj, (size_t)m + 1);
+    CUX(cudaMalloc(&x->obj_sign, nobj)); CUX(cudaMalloc(&x->obj_top, nobj * sizeof(int))); CUX(cudaMalloc(&x->obj_mant, nobj * sizeof(double)));
+    CUX(cudaMalloc(&x->cr_sign, ncr)); CUX(cudaMalloc(&x->cr_top, ncr * sizeof(int))); CUX(cudaMalloc(&x->cr_mant, ncr * sizeof(double)));
+    CUX(cudaMalloc(&x->rd_sign, nrd)); CUX(cudaMalloc(&x->rd_top, nrd * sizeof(int))); CUX(cudaMalloc(&x->rd_mant, nrd * sizeof(double)));
+    x->obj_dstride = (nobj + 7) / 8 * 8;
+    x->rd_stride = (nrd + 7) / 8 * 8;
+    CUX(cudaMalloc(&x->obj_dig, (size_t)P * x->obj_dstride * sizeof(uint32_t)));
+    CUX(cudaMalloc(&x->rd_dig, (size_t)P * x->rd_stride * sizeof(uint32_t)));
+    CUX(cudaMalloc(&x->cand, (size_t)m * sizeof(int)));
+    CUX(cudaMalloc(&x->st, sizeof(XState)));
+    CUX(cudaMallocHost(&x->st_host, sizeof(XState)));
+    CUX(cudaMalloc(&h->basis, (size_t)m * sizeof(int)));
+    CUX(cudaMemsetAsync(h->basis, 0xff, (size_t)m * sizeof(int), h->stream));
+    CUX(cudaMalloc(&h->marks, (size_t)n * sizeof(int)));
+    CUX(cudaMemsetAsync(h->marks, 0, (size_t)n * sizeof(int), h->stream));
+    CUX(cudaMalloc(&h->scratch_i, ((size_t)n + 8) * sizeof(int)));
+    CUX(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return LPS_OK;
+}
+
+int lpsx_destroy(lps_handle* h) {
+    if (!h) return LPS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    ExactData* x = h->x;
+    if (x) {
+        cudaFree(x->pr); cudaFree(x->invtab); cudaFree(x->half); cudaFree(x->wmant); cudaFree(x->wexp);
+        cudaFree(x->R); cudaFree(x->Dres); cudaFree(x->dinv_m); cudaFree(x->alpha_m); cudaFree(x->nbeta);
+        cudaFree(x->sigma); cudaFree(x->one); cudaFree(x->alive);
+        cudaFree(x->obj_sign); cudaFree(x->obj_top); cudaFree(x->obj_mant); cudaFree(x->obj_dig);
+        cudaFree(x->cr_sign); cudaFree(x->cr_top); cudaFree(x->cr_mant);
+        cudaFree(x->rd_sign); cudaFree(x->rd_top); cudaFree(x->rd_mant); cudaFree(x->rd_dig);
+        cudaFree(x->cand); cudaFree(x->st);
+        if (x->st_host) cudaFreeHost(x->st_host);
+        delete x;
+    }
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    cudaFree(h->basis); cudaFree(h->marks); cudaFree(h->trace); cudaFree(h->scratch_i);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return LPS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state helpers
+// ------------------------------------------------------------------------------------------------
+static int xread_state(lps_handle* h) {
+    CU(cudaMemcpyAsync(h->x->st_host, h->x->st, sizeof(XState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+static int xwrite_state(lps_handle* h) {
+    CU(cudaMemcpyAsync(h->x->st, h->x->st_host, sizeof(XState), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload / read-out
+// ------------------------------------------------------------------------------------------------
+extern "C" int lps_upload_exact(lps_handle* h, const uint32_t* limbs, int nlimbs, const unsigned char* neg, size_t ld_host,
+                                const uint32_t* sigma_limbs, int sigma_nlimbs) {
+    USE(h);
+    NEED_MODE(h, 1);
+    ExactData* x = h->x;
+    if (!limbs || !neg || nlimbs <= 0 || ld_host < (size_t)h->n + 1) return fail(LPS_E_INVALID, "bad host grid");
+    if (!sigma_limbs || sigma_nlimbs <= 0) return fail(LPS_E_INVALID, "bad row scales");
+    const size_t entries = (size_t)(h->m + 1) * ld_host;
+    uint32_t* d_limbs = nullptr;
+    unsigned char* d_neg = nullptr;
+    uint32_t* d_sig = nullptr;
+    CU(cudaMalloc(&d_limbs, entries * nlimbs * sizeof(uint32_t)));
+    CU(cudaMalloc(&d_neg, entries));
+    CU(cudaMalloc(&d_sig, ((size_t)h->m + 1) * sigma_nlimbs * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(d_limbs, limbs, entries * nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_neg, neg, entries, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_sig, sigma_limbs, ((size_t)h->m + 1) * sigma_nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    const XGrid g = xgrid_of(h);
+    const unsigned bx = (unsigned)std::min<size_t>((x->plane + 255) / 256, 148 * 8);
+    k_xencode<<<dim3(bx, x->P), 256, 0, h->stream>>>(g, d_limbs, nlimbs, d_neg, ld_host);
+    k_xencode_vec<<<dim3((h->m + 256) / 256, x->P), 256, 0, h->stream>>>(g, d_sig, sigma_nlimbs, h->m + 1, x->sigma, x->sstride);
+    h->launches_all += 2;
+    CU(cudaGetLastError());
+    std::vector<uint32_t> ones(x->P, 1u);
+    CU(cudaMemcpyAsync(x->Dres, ones.data(), x->P * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    std::vector<int> alive(h->m + 1, 1);
+    CU(cudaMemcpyAsync(x->alive, alive.data(), alive.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    XState s{};
+    s.status = LPS_OK; s.max_pivots = -1; s.sgnD = 1; s.c = s.r = s.last_r = s.last_c = -1; s.bad_prime = -1;
+    *x->st_host = s;
+    CU(cudaMemcpyAsync(x->st, x->st_host, sizeof(XState), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaFree(d_limbs)); CU(cudaFree(d_neg)); CU(cudaFree(d_sig));
+    return LPS_OK;
+}
+
+template <int NB>
+static int launch_garner(lps_handle* h, const GarnerJob& job) {
+    const ExactData* x = h->x;
+    const int blocks = (job.count + NB - 1) / NB;
+    if (x->spt == 1) k_garner<NB, 1><<<blocks, x->lane_threads, 0, h->stream>>>(xgrid_of(h), x->st, job);
+    else k_garner<NB, kMaxSPT><<<blocks, x->lane_threads, 0, h->stream>>>(xgrid_of(h), x->st, job);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+
+// what: 0 = row `index` (n+1 numbers), 1 = column `index` (m+1 numbers), 2 = the denominator D (1 number).
+// sign_out: count bytes (-1/0/+1); digits_out: P x count uint32, digit k of |x_e| at [k*count + e].
+extern "C" int lps_read_exact(lps_handle* h, int what, int index, signed char* sign_out, uint32_t* digits_out) {
+    USE(h);
+    NEED_MODE(h, 1);
+    ExactData* x = h->x;
+    if (!sign_out || !digits_out) return fail(LPS_E_INVALID, "null output");
+    GarnerJob job{};
+    job.check_status = 0;
+    job.meta = XMeta{x->rd_sign, x->rd_top, x->rd_mant};
+    job.dig = x->rd_dig; job.dstride = x->rd_stride;
+    if (what == 0) {
+        if (index < 0 || index > h->m) return fail(LPS_E_INVALID, "row %d out of range", index);
+        job.src = XSRC_ROW; job.index = index; job.count = h->n + 1;
+    } else if (what == 1) {
+        if (index < 0 || index > h->n) return fail(LPS_E_INVALID, "column %d out of range", index);
+        job.src = XSRC_COL; job.index = index; job.count = h->m + 1;
+    } else if (what == 2) {
+        job.src = XSRC_CUSTOM; job.custom = x->Dres; job.cstride = 1; job.count = 1; job.index = 0;
+    } else return fail(LPS_E_INVALID, "bad selector %d", what);
+    TRY(launch_garner<8>(h, job));
+    CU(cudaMemcpyAsync(sign_out, x->rd_sign, job.count, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpy2DAsync(digits_out, (size_t)job.count * sizeof(uint32_t), x->rd_dig, x->rd_stride * sizeof(uint32_t),
+                         (size_t)job.count * sizeof(uint32_t), x->P, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+
+extern "C" int lps_read_alive(lps_handle* h, int* alive) {
+    USE(h);
+    NEED_MODE(h, 1);
+    if (!alive) return fail(LPS_E_INVALID, "null output");
+    CU(cudaMemcpyAsync(alive, h->x->alive, ((size_t)h->m + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+
+extern "C" int lps_exact_info(lps_handle* h, int* nprimes, int* bad_prime, size_t* residue_bytes) {
+    USE(h);
+    NEED_MODE(h, 1);
+    TRY(xread_state(h));
+    if (nprimes) *nprimes = h->x->P;
+    if (bad_prime) *bad_prime = h->x->st_host->bad_prime;
+    if (residue_bytes) *residue_bytes = (size_t)h->x->P * h->x->plane * sizeof(uint32_t);
+    return LPS_OK;
+}
+
+// Loop state of Simplex.solve (rule, stuck counter, "objective moved", pending objective check):
+// set == 0 reads it; set != 0 writes it and makes the next lps_solve continue from it instead of
+// starting over (used when a solve is resumed on a re-encoded tableau after LPS_BAD_PRIME).
+extern "C" int lps_exact_loop_state(lps_handle* h, int set, int* rule, long long* stuck, int* moved, int* pending) {
+    USE(h);
+    NEED_MODE(h, 1);
+    if (!rule || !stuck || !moved || !pending) return fail(LPS_E_INVALID, "null argument");
+    TRY(xread_state(h));
+    XState& s = *h->x->st_host;
+    if (!set) { *rule = s.rule; *stuck = s.stuck; *moved = s.moved; *pending = s.pending_zcheck; return LPS_OK; }
+    s.rule = *rule; s.stuck = *stuck; s.moved = *moved; s.pending_zcheck = *pending;
+    TRY(xwrite_state(h));
+    h->x->resume = true;
+    return LPS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches of one pivot
+// ------------------------------------------------------------------------------------------------
+static int xlaunch_select(lps_handle* h) {
+    ExactData* x = h->x;
+    GarnerJob job{};
+    job.src = XSRC_ROW; job.index = h->m; job.count = h->n + 1; job.check_status = 1;
+    job.meta = XMeta{x->obj_sign, x->obj_top, x->obj_mant};
+    job.dig = x->obj_dig; job.dstride = x->obj_dstride;
+    TRY(launch_garner<8>(h, job));
+    XPriceArgs pa{xgrid_of(h), x->st, job.meta, x->obj_dig, x->obj_dstride};
+    k_xprice<<<1, kLaneThreads, 0, h->stream>>>(pa);
+    GarnerJob cj{};
+    cj.src = XSRC_COLPAIR; cj.index = -1; cj.count = 2 * (h->m + 1); cj.check_status = 1;
+    cj.meta = XMeta{x->cr_sign, x->cr_top, x->cr_mant};
+    TRY(launch_garner<8>(h, cj));
+    XRatioArgs ra{xgrid_of(h), x->st, cj.meta, pconst_of(h), x->cand};
+    if (x->spt == 1) k_xratio<1><<<1, kLaneThreads, 0, h->stream>>>(ra);
+    else k_xratio<kMaxSPT><<<1, kLaneThreads, 0, h->stream>>>(ra);
+    h->launches_all += 2;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+
+static int xlaunch_apply(lps_handle* h, int commit) {
+    ExactData* x = h->x;
+    const XGrid g = xgrid_of(h);
+    k_xstage<<<dim3(std::max(1, std::min((h->m + 256) / 256, 64)), x->P), 256, 0, h->stream>>>(g, x->st, pconst_of(h), x->nbeta, x->nbeta_ld);
+    XUpdateArgs a;
+    a.g = g; a.st = x->st; a.alpha_m = x->alpha_m; a.nbeta = x->nbeta; a.nbeta_ld = x->nbeta_ld;
+    a.rows_per_cta = x->rows_per_cta; a.basis = h->basis; a.marks = h->use_marks ? h->marks : nullptr;
+    a.trace = h->trace; a.trace_cap = h->trace_cap; a.alive = x->alive; a.commit = commit;
+    dim3 grid((unsigned)((x->ld + x->chunk - 1) / x->chunk), (unsigned)((h->m + 1 + x->rows_per_cta - 1) / x->rows_per_cta), (unsigned)x->P);
+    const bool timed = h->prof && h->ev_used + 2 <= h->ev.size();
+    if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
+    if (x->chunk == 2048) {
+        if (x->stream_hint) k_xupdate<2048, true><<<grid, kXThreads, 0, h->stream>>>(a);
+        else k_xupdate<2048, false><<<grid, kXThreads, 0, h->stream>>>(a);
+    } else {
+        if (x->stream_hint) k_xupdate<1024, true><<<grid, kXThreads, 0, h->stream>>>(a);
+        else k_xupdate<1024, false><<<grid, kXThreads, 0, h->stream>>>(a);
+    }
+    if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
+    h->launches_update++;
+    h->launches_all += 2;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hooks behind the mode-independent entry points
+// ------------------------------------------------------------------------------------------------
+int lpsx_pivot(lps_handle* h, int r, int c) {
+    ExactData* x = h->x;
+    if (r < 0 || r >= h->m || c < 0 || c >= h->n) return fail(LPS_E_INVALID, "pivot (%d,%d) out of range", r, c);
+    TRY(xread_state(h));
+    x->st_host->status = LPS_OK; x->st_host->dry_run = 0; x->st_host->bad_prime = -1;
+    TRY(xwrite_state(h));
+    if (x->spt == 1) k_xforced<1><<<1, kLaneThreads, 0, h->stream>>>(xgrid_of(h), x->st, pconst_of(h), r, c);
+    else k_xforced<kMaxSPT><<<1, kLaneThreads, 0, h->stream>>>(xgrid_of(h), x->st, pconst_of(h), r, c);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    TRY(xlaunch_apply(h, 0));
+    TRY(xread_state(h));
+    const int st = x->st_host->status;
+    return (st == LPS_ZERO_PIVOT || st == LPS_BAD_PRIME) ? st : LPS_OK;
+}
+
+int lpsx_find_pivot(lps_handle* h, int rule, int* r, int* c) {
+    ExactData* x = h->x;
+    TRY(xread_state(h));
+    XState keep = *x->st_host;
+    x->st_host->status = LPS_OK; x->st_host->dry_run = 1; x->st_host->rule = rule;
+    x->st_host->last_r = x->st_host->last_c = -1;
+    TRY(xwrite_state(h));
+    TRY(xlaunch_select(h));
+    TRY(xread_state(h));
+    const XState o = *x->st_host;
+    keep.status = LPS_OK;
+    *x->st_host = keep;
+    TRY(xwrite_state(h));
+    *r = o.last_r; *c = o.last_c;
+    if (o.status == LPS_OPTIMAL) return LPS_OPTIMAL;
+    if (o.status == LPS_UNBOUNDED) return LPS_UNBOUNDED;
+    return LPS_OK;
+}
+
+int lpsx_is_canonical(lps_handle* h, int* bcols, int* canonical) {
+    ExactData* x = h->x;
+    const XGrid g = xgrid_of(h);
+    GarnerJob job{};
+    job.src = XSRC_COL; job.index = h->n; job.count = h->m + 1; job.check_status = 0;
+    job.meta = XMeta{x->rd_sign, x->rd_top, x->rd_mant};
+    TRY(launch_garner<8>(h, job));
+    int* flag = h->scratch_i + h->n;
+    CU(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+    k_xany_neg<<<std::max(1, std::min((h->m + 255) / 256, 592)), 256, 0, h->stream>>>(x->rd_sign, h->m, x->st, flag);
+    int neg = 0;
+    CU(cudaMemcpyAsync(&neg, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->launches_all++;
+    if (neg) { *canonical = 0; return LPS_OK; }                  // bcols untouched (tableau.py:476-477)
+    k_xone<<<dim3(std::max(1, std::min((h->m + 256) / 256, 64)), x->P), 256, 0, h->stream>>>(g, x->Dres, x->sigma, x->sstride, x->alive, x->one);
+    k_xcanon_a<<<(h->n + 127) / 128, 128, 0, h->stream>>>(g, x->one, h->scratch_i);
+    if (x->P > 1) k_xcanon_b<<<dim3((h->n + 127) / 128, x->P - 1), 128, 0, h->stream>>>(g, x->one, x->sstride, h->scratch_i);
+    int* d_bcols = nullptr;
+    CU(cudaMalloc(&d_bcols, (size_t)h->m * sizeof(int)));
+    CU(cudaMemsetAsync(d_bcols, 0x7f, (size_t)h->m * sizeof(int), h->stream));
+    k_canon_rows<<<std::max(1, std::min((h->n + 255) / 256, 592)), 256, 0, h->stream>>>(h->scratch_i, h->n, d_bcols);
+    h->launches_all += 4;
+    std::vector<int> tmp(h->m);
+    CU(cudaMemcpyAsync(tmp.data(), d_bcols, (size_t)h->m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaFree(d_bcols));
+    int all = 1;
+    for (int i = 0; i < h->m; ++i) {
+        const int j = (tmp[i] == 0x7f7f7f7f) ? -1 : tmp[i];
+        if (j < 0) all = 0;
+        if (bcols) bcols[i] = j;
+    }
+    *canonical = all;
+    return LPS_OK;
+}
+
+int lpsx_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int* trace, long long trace_cap, long long* npiv) {
+    ExactData* x = h->x;
+    CU(cudaMemcpyAsync(h->basis, basis, (size_t)h->m * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->use_marks = marks != nullptr;
+    if (marks) CU(cudaMemcpyAsync(h->marks, marks, (size_t)h->n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (!trace) trace_cap = 0;
+    if (trace_cap > h->trace_cap) {
+        if (h->trace) CU(cudaFree(h->trace));
+        h->trace = nullptr; h->trace_cap = 0;
+        CU(cudaMalloc(&h->trace, (size_t)trace_cap * 3 * sizeof(int)));
+        h->trace_cap = trace_cap;
+    }
+    TRY(xread_state(h));
+    XState& s = *x->st_host;
+    s.status = LPS_OK; s.npiv = 0; s.max_pivots = max_pivots; s.dry_run = 0; s.obj_increased = 0; s.bad_prime = -1;
+    if (!x->resume) { s.rule = LPS_RULE_DANTZIG; s.stuck = 0; s.moved = 0; s.pending_zcheck = 0; }
+    x->resume = false;
+    TRY(xwrite_state(h));
+    const double est_us = std::max(20.0, (double)x->plane * x->P * 8.0 / 5.0e6);
+    const long long burst = (long long)std::max(2.0, std::min(128.0, 2000.0 / est_us));
+    long long enqueued = 0;
+    for (;;) {
+        const long long room = max_pivots >= 0 ? max_pivots - enqueued : burst;
+        const long long now = std::min(burst, room);
+        for (long long k = 0; k < now; ++k) {
+            TRY(xlaunch_select(h));
+            TRY(xlaunch_apply(h, 1));
+        }
+        enqueued += now;
+        if (now == 0) TRY(xlaunch_select(h));
+        TRY(xread_state(h));
+        if (x->st_host->status != LPS_OK) break;
+    }
+    const long long k = x->st_host->npiv;
+    if (npiv) *npiv = k;
+    CU(cudaMemcpyAsync(basis, h->basis, (size_t)h->m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (marks) CU(cudaMemcpyAsync(marks, h->marks, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (trace && trace_cap > 0) {
+        const long long cnt = std::min(k, std::min(trace_cap, h->trace_cap));
+        if (cnt > 0) CU(cudaMemcpyAsync(trace, h->trace, (size_t)cnt * 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return x->st_host->status;
+}

@@ -1,0 +1,90 @@
+// Internal declarations shared by the translation units of liblps_b200.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/lps_b200.h"
+#include "lps_f64.cuh"
+
+int lps_fail(int code, const char* fmt, ...);
+#define fail lps_fail
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(LPS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(x)                       \
+    do {                             \
+        int rc_ = (x);               \
+        if (rc_ < 0) return rc_;     \
+    } while (0)
+
+struct ExactData;   // lps_exact_api.cu
+
+using namespace lps;
+
+constexpr int kWideChunk = 1024;     // doubles per column chunk for large grids
+constexpr int kNarrowChunk = 512;    // ... for small ones (more CTAs)
+constexpr size_t kL2Bytes = 120ull << 20;
+
+struct lps_handle {
+    int mode = 0;                    // 0 = fp64, 1 = exact (multi-modular integers)
+    ExactData* x = nullptr;          // exact-mode state
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int m = 0, n = 0;
+    size_t ld = 0;
+    long long row0 = 0, m_total = 0;
+    int rank = 0, nranks = 1;
+
+    double* T = nullptr;
+    bool own_T = false;
+    double* ucol = nullptr;
+    unsigned char* cand_send = nullptr;
+    unsigned char* cand_all = nullptr;
+    bool own_cand = false;
+    size_t cand_stride = 0;
+
+    int chunk = kWideChunk, nchunks = 0, rows_per_cta = 64, sel_blocks = 1;
+    bool stream_hint = false;
+    double* pd_val = nullptr;
+    int* pd_idx = nullptr;
+    int* pb_idx = nullptr;
+    ArgMinF64* sel_blk = nullptr;
+    SolveState* st = nullptr;
+    SolveState* st_host = nullptr;   // pinned mirror
+    int* basis = nullptr;            // m_total ints
+    int* marks = nullptr;            // n ints
+    bool use_marks = false;
+    int* trace = nullptr;
+    long long trace_cap = 0;
+    int* scratch_i = nullptr;        // n + 8 ints (isCanonical)
+    bool solving = false;
+
+    // profiling of the update kernel
+    bool prof = false;
+    std::vector<cudaEvent_t> ev;
+    size_t ev_used = 0;
+    long long launches_update = 0, launches_all = 0;
+};
+
+
+int lps_use(const lps_handle* h);
+#define USE(h)                         \
+    do {                               \
+        int rc_ = lps_use(h);          \
+        if (rc_ != LPS_OK) return rc_; \
+    } while (0)
+#define NEED_MODE(h, want)                                                                         \
+    do {                                                                                           \
+        if ((h)->mode != (want)) return fail(LPS_E_STATE, "%s: wrong arithmetic mode for this handle", __func__); \
+    } while (0)
+
+// exact-mode hooks used by the mode-independent entry points (lps_exact_api.cu)
+int lpsx_destroy(lps_handle* h);
+int lpsx_pivot(lps_handle* h, int r, int c);
+int lpsx_find_pivot(lps_handle* h, int rule, int* r, int* c);
+int lpsx_is_canonical(lps_handle* h, int* bcols, int* canonical);
+int lpsx_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int* trace, long long trace_cap, long long* npiv);

@@ -1,0 +1,363 @@
+"""Exact-mode device engine: a rational tableau as a fraction-free integer grid on the GPU.
+
+The reference computes in `fractions.Fraction` (tableau.py:2).  Here a tableau T of Fractions is
+held on the device as an integer matrix N and one common denominator D, as residues modulo a set of
+31-bit primes sized from a Hadamard bound (include/lps_b200.h, "exact mode"):
+
+    T[i][j] == Fraction(N[i][j], D * sigma[i])
+
+`sigma[i]` is the positive integer that cleared the denominators of row i at upload time; a row
+loses it the first time it is a pivot row (the pivot row of a simplex tableau is scale free).  The
+host side of this module only *encodes* (Fractions -> integer limbs, prime set) and *decodes*
+(mixed-radix digits -> Python ints -> Fractions); every arithmetic step of a pivot, pricing, ratio
+test and the solve loop runs in the CUDA library.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from ctypes import byref, c_int, c_longlong, c_size_t, c_void_p
+from fractions import Fraction
+from functools import lru_cache
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+# ------------------------------------------------------------------------------------------------
+# prime set
+# ------------------------------------------------------------------------------------------------
+_MR_BASES = (2, 3, 5, 7)            # deterministic Miller-Rabin below 3,215,031,751
+
+
+def _is_prime(q: int) -> bool:
+    if q < 2:
+        return False
+    for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        if q % p == 0:
+            return q == p
+    d, s = q - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        s += 1
+    for a in _MR_BASES:
+        x = pow(a, d, q)
+        if x in (1, q - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % q
+            if x == q - 1:
+                break
+        else:
+            return False
+    return True
+
+
+_PRIMES: List[int] = []
+
+
+def primes_below_2_31(count: int, skip: Sequence[int] = ()) -> List[int]:
+    """The `count` largest primes below 2^31 (descending), leaving out those in `skip`."""
+    q = (_PRIMES[-1] - 2) if _PRIMES else (1 << 31) - 1
+    while len(_PRIMES) < count + len(skip):
+        if _is_prime(q):
+            _PRIMES.append(q)
+        q -= 2
+    skip = set(skip)
+    out = [p for p in _PRIMES if p not in skip]
+    return out[:count]
+
+
+def hadamard_bits(rows: List[List[int]]) -> int:
+    """Bits of a bound on |minor| over all square submatrices of the integer matrix `rows`:
+    min(product of row norms, product of the min(#rows, #cols) largest column norms), each norm
+    clamped to >= 1 (so that sub-minors are covered too)."""
+    nr, nc = len(rows), len(rows[0])
+    row_sq = [max(1, sum(x * x for x in r)) for r in rows]
+    col_sq = [0] * nc
+    for r in rows:
+        for j, x in enumerate(r):
+            if x:
+                col_sq[j] += x * x
+    col_sq = [max(1, c) for c in col_sq]
+    order = min(nr, nc)
+    by_rows = sum(math.log2(v) for v in sorted(row_sq, reverse=True)[:order]) / 2
+    by_cols = sum(math.log2(v) for v in sorted(col_sq, reverse=True)[:order]) / 2
+    return int(math.ceil(min(by_rows, by_cols))) + 2
+
+
+def hadamard_bits_np(G: np.ndarray) -> int:
+    """Same bound for an int64 matrix with small entries (float64 norms are accurate enough; the +2
+    bits of `hadamard_bits` plus one more absorb their rounding)."""
+    A = G.astype(np.float64)
+    row_sq = np.maximum(1.0, (A * A).sum(axis=1))
+    col_sq = np.maximum(1.0, (A * A).sum(axis=0))
+    order = min(A.shape)
+    by_rows = np.log2(np.sort(row_sq)[::-1][:order]).sum() / 2
+    by_cols = np.log2(np.sort(col_sq)[::-1][:order]).sum() / 2
+    return int(math.ceil(min(by_rows, by_cols))) + 3
+
+
+def primes_for_bits(bits: int, skip: Sequence[int] = ()) -> List[int]:
+    """Enough primes that their product exceeds 2^(bits+2): symmetric range plus one guard bit."""
+    need = bits + 2
+    count = max(2, int(math.ceil(need / 30.999999)))
+    while True:
+        ps = primes_below_2_31(count, skip)
+        if sum(math.log2(p) for p in ps) > need:
+            return ps
+        count += 1
+
+
+# ------------------------------------------------------------------------------------------------
+# encode / decode
+# ------------------------------------------------------------------------------------------------
+def clear_denominators(grid) -> Tuple[List[List[int]], List[int]]:
+    """Fractions -> (integer rows, per-row scale sigma) with sigma_i = lcm of row i's denominators."""
+    ints, sigma = [], []
+    for row in grid:
+        s = 1
+        for x in row:
+            d = x.denominator
+            if d != 1:
+                s = s * d // math.gcd(s, d)
+        sigma.append(s)
+        ints.append([int(x * s) for x in row] if s != 1 else [int(x) for x in row])
+    return ints, sigma
+
+
+def to_limbs(values: Sequence[int], nlimbs: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray, int]:
+    """Signed Python ints -> (uint32 limbs [len, nlimbs] little endian, uint8 negative flags, nlimbs)."""
+    mags = [abs(int(v)) for v in values]
+    top = max(mags, default=0)
+    need = max(1, (top.bit_length() + 31) // 32)
+    nlimbs = max(need, nlimbs or 1)
+    neg = np.fromiter((1 if int(v) < 0 else 0 for v in values), dtype=np.uint8, count=len(mags))
+    if nlimbs <= 2:
+        arr = np.fromiter(mags, dtype=np.uint64, count=len(mags))
+        limbs = np.empty((len(mags), nlimbs), dtype=np.uint32)
+        limbs[:, 0] = (arr & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        if nlimbs == 2:
+            limbs[:, 1] = (arr >> np.uint64(32)).astype(np.uint32)
+        return limbs, neg, nlimbs
+    buf = b"".join(v.to_bytes(4 * nlimbs, "little") for v in mags)
+    return np.frombuffer(buf, dtype="<u4").reshape(len(mags), nlimbs).copy(), neg, nlimbs
+
+
+class MixedRadix:
+    """Digits (p_0, p_1, ...) -> Python ints, vectorised over numbers with numpy object arrays."""
+
+    def __init__(self, primes: Sequence[int]):
+        self.primes = [int(p) for p in primes]
+
+    def decode(self, sign: np.ndarray, digits: np.ndarray) -> List[int]:
+        """sign: int8 [count]; digits: uint32 [P, count] (digit k of |x|).  Horner from the highest
+        digit that is nonzero anywhere."""
+        count = sign.shape[0]
+        nz = np.nonzero(digits.any(axis=1))[0]
+        acc = np.zeros(count, dtype=object)
+        if nz.size:
+            for k in range(int(nz[-1]), -1, -1):
+                acc = acc * self.primes[k] + digits[k].astype(object)
+        out = [int(v) for v in acc]
+        return [-v if s < 0 else v for v, s in zip(out, sign.tolist())]
+
+
+# ------------------------------------------------------------------------------------------------
+# engine
+# ------------------------------------------------------------------------------------------------
+class ExactEngine:
+    """Exact rational tableau on one GPU (same method surface as `engine.F64Engine`)."""
+
+    mode = "exact"
+
+    def __init__(self, m: int, n: int, device: Optional[int] = None, primes: Optional[Sequence[int]] = None):
+        import torch
+        self.L = N.lib()
+        self.device = int(torch.cuda.current_device() if device is None else device)
+        self.m, self.n = int(m), int(n)
+        self.h = None
+        self.primes: List[int] = []
+        self.forced_primes = [int(p) for p in primes] if primes is not None else None
+        self.banned: List[int] = []
+        self.reencodes = 0
+        self.last_bits = 0
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def _create(self, primes: Sequence[int]):
+        self.close()
+        arr = np.asarray(primes, dtype=np.uint32)
+        h = c_void_p()
+        N.check(self.L.lps_create_exact(self.m, self.n, len(primes), arr.ctypes.data, self.device, None, byref(h)))
+        self.h = h
+        self.primes = [int(p) for p in primes]
+        self.codec = MixedRadix(self.primes)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lps_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        N.check(self.L.lps_sync(self.h))
+
+    # -- transfers -----------------------------------------------------------------------------
+    def upload(self, grid):
+        """grid: (m+1) x (n+1) Fractions / ints in device layout, or an int64 numpy array."""
+        if isinstance(grid, np.ndarray) and grid.dtype.kind in "iu":
+            G = np.ascontiguousarray(grid, dtype=np.int64)
+            bits = hadamard_bits_np(G)
+            sigma = [1] * (self.m + 1)
+            mags = np.abs(G).astype(np.uint64)
+            nl = 1 if int(mags.max(initial=0)) < (1 << 32) else 2
+            limbs = np.empty(G.shape + (nl,), dtype=np.uint32)
+            limbs[..., 0] = (mags & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+            if nl == 2:
+                limbs[..., 1] = (mags >> np.uint64(32)).astype(np.uint32)
+            neg = (G < 0).astype(np.uint8)
+        else:
+            rows = [[x if isinstance(x, Fraction) else Fraction(x) for x in row] for row in grid]
+            ints, sigma = clear_denominators(rows)
+            bits = hadamard_bits(ints)
+            flat = [v for row in ints for v in row]
+            limbs, neg, nl = to_limbs(flat)
+        bits += max(s.bit_length() for s in sigma)       # "== 1" tests compare with D * sigma_i
+        self.last_bits = bits
+        primes = self.forced_primes if self.forced_primes is not None else primes_for_bits(bits, self.banned)
+        if self.h is None or primes != self.primes:
+            self._create(primes)
+        sl, _, snl = to_limbs(sigma)
+        limbs = np.ascontiguousarray(limbs)
+        N.check(self.L.lps_upload_exact(self.h, limbs.ctypes.data, nl, np.ascontiguousarray(neg).ctypes.data, self.n + 1,
+                                        sl.ctypes.data, snl))
+        self.sigma = sigma
+
+    def _read(self, what: int, index: int, count: int) -> List[int]:
+        sign = np.empty(count, dtype=np.int8)
+        digits = np.empty((len(self.primes), count), dtype=np.uint32)
+        N.check(self.L.lps_read_exact(self.h, what, index, sign.ctypes.data, digits.ctypes.data))
+        return self.codec.decode(sign, digits)
+
+    def denominator(self) -> int:
+        return self._read(2, 0, 1)[0]
+
+    def _alive(self) -> np.ndarray:
+        out = np.empty(self.m + 1, dtype=np.int32)
+        N.check(self.L.lps_read_alive(self.h, out.ctypes.data))
+        return out
+
+    def _row_den(self, D: int, alive, i: int) -> int:
+        return D * self.sigma[i] if alive[i] else D
+
+    def read_row(self, i: int) -> List[Fraction]:
+        D, alive = self.denominator(), self._alive()
+        den = self._row_den(D, alive, i)
+        return [Fraction(v, den) for v in self._read(0, i, self.n + 1)]
+
+    def read_col(self, j: int) -> List[Fraction]:
+        D, alive = self.denominator(), self._alive()
+        vals = self._read(1, j, self.m + 1)
+        return [Fraction(v, self._row_den(D, alive, i)) for i, v in enumerate(vals)]
+
+    def download(self) -> List[List[Fraction]]:
+        D, alive = self.denominator(), self._alive()
+        out = []
+        for i in range(self.m + 1):
+            den = self._row_den(D, alive, i)
+            out.append([Fraction(v, den) for v in self._read(0, i, self.n + 1)])
+        return out
+
+    def integer_state(self) -> Tuple[List[List[int]], int]:
+        """(N, D) as Python ints -- what tests compare with the oracle's Bareiss restatement."""
+        return [self._read(0, i, self.n + 1) for i in range(self.m + 1)], self.denominator()
+
+    def info(self):
+        p, bad, nbytes = c_int(0), c_int(-1), c_size_t(0)
+        N.check(self.L.lps_exact_info(self.h, byref(p), byref(bad), byref(nbytes)))
+        return {"primes": p.value, "bad_prime": bad.value, "residue_bytes": nbytes.value, "bound_bits": self.last_bits}
+
+    # -- re-encoding when a prime divides a pivot element -----------------------------------------
+    def _reencode(self):
+        """Download the (still intact) tableau, drop the offending prime, upload again."""
+        bad = self.info()["bad_prime"]
+        if self.forced_primes is not None:
+            if len(self.forced_primes) <= 1:
+                raise N.NativeError("prime set exhausted while re-encoding")
+            self.forced_primes = [p for k, p in enumerate(self.forced_primes) if k != bad]
+        else:
+            self.banned.append(self.primes[bad])
+        grid = self.download()
+        self.reencodes += 1
+        self.upload(grid)
+
+    # -- hot path ------------------------------------------------------------------------------
+    def pivot(self, r: int, c: int) -> int:
+        while True:
+            rc = N.check(self.L.lps_pivot(self.h, r, c))
+            if rc != N.BAD_PRIME:
+                return rc
+            self._reencode()
+
+    def find_pivot(self, rule: int):
+        r, c = c_int(-1), c_int(-1)
+        rc = N.check(self.L.lps_find_pivot(self.h, rule, byref(r), byref(c)))
+        if rc == N.OPTIMAL:
+            return "optimal"
+        if rc == N.UNBOUNDED:
+            return "unbounded"
+        return r.value, c.value
+
+    def is_canonical(self, want_cols: bool = True):
+        cols = np.full(self.m, -1, dtype=np.int32)
+        flag = c_int(0)
+        N.check(self.L.lps_is_canonical(self.h, cols.ctypes.data if want_cols else None, byref(flag)))
+        return bool(flag.value), cols
+
+    def is_optimal(self) -> bool:
+        flag = c_int(0)
+        N.check(self.L.lps_is_optimal(self.h, byref(flag)))
+        return bool(flag.value)
+
+    def solve(self, basis: np.ndarray, marks: Optional[np.ndarray] = None, max_pivots: int = -1, trace_cap: int = 0):
+        """`Simplex.solve` on the device; basis / marks are int32 arrays updated in place."""
+        assert basis.dtype == np.int32 and basis.size == self.m
+        total, pieces = 0, []
+        left = max_pivots
+        while True:
+            trace = np.zeros((max(trace_cap - total, 0), 3), dtype=np.int32) if trace_cap > 0 else None
+            npiv = c_longlong(0)
+            rc = N.check(self.L.lps_solve(self.h, left, basis.ctypes.data, marks.ctypes.data if marks is not None else None,
+                                          trace.ctypes.data if trace is not None and trace.size else None,
+                                          trace.shape[0] if trace is not None else 0, byref(npiv)))
+            k = npiv.value
+            if trace is not None:
+                pieces.append(trace[: min(k, trace.shape[0])])
+            total += k
+            if rc != N.BAD_PRIME:
+                break
+            # a prime divides the next pivot element (probability ~2^-31 per prime and pivot):
+            # re-encode without that prime and continue the loop exactly where it stopped
+            rule, stuck, moved, pend = c_int(0), c_longlong(0), c_int(0), c_int(0)
+            N.check(self.L.lps_exact_loop_state(self.h, 0, byref(rule), byref(stuck), byref(moved), byref(pend)))
+            self._reencode()
+            N.check(self.L.lps_exact_loop_state(self.h, 1, byref(rule), byref(stuck), byref(moved), byref(pend)))
+            if left >= 0:
+                left -= k
+        tr = np.concatenate(pieces) if pieces else None
+        return rc, total, tr
+
+    # -- profiling -----------------------------------------------------------------------------
+    def prof_reset(self):
+        N.check(self.L.lps_prof_reset(self.h))
+
+    def prof_read(self):
+        from ctypes import c_double
+        ms, nu, na = c_double(0), c_longlong(0), c_longlong(0)
+        N.check(self.L.lps_prof_read(self.h, byref(ms), byref(nu), byref(na)))
+        return ms.value, nu.value, na.value

@@ -1,0 +1,218 @@
+"""GPU parity of the exact (multi-modular Bareiss) mode against the reference fixtures and the oracle.
+
+Exact mode must reproduce the reference's pivot sequence, basis and rational results bit-for-bit, so
+every comparison here is `==` on ints / Fractions / pivot lists."""
+import random
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from linear_program_solver_b200 import problems
+
+pytestmark = pytest.mark.gpu
+
+
+def _tab(c, A, b, mode="exact"):
+    from linear_program_solver_b200 import Tableau
+    t = Tableau(len(A), len(c), mode=mode)
+    t.setC(list(c))
+    t.setB(list(b))
+    t.setA([list(r) for r in A])
+    return t
+
+
+def _frac_grid(c, A, b):
+    from oracle import lpsol_oracle as O
+    return O.make_grid(c, A, b)
+
+
+@pytest.mark.parametrize("bits", [8, 31, 32, 63, 64, 200, 1000])
+def test_encode_decode_roundtrip(bits):
+    """Residue encoding + on-device Garner reconstruction give back the uploaded integers."""
+    from linear_program_solver_b200.exact import ExactEngine
+    rng = random.Random(bits)
+    m, n = 5, 9
+    grid = [[rng.choice([-1, 1]) * rng.getrandbits(bits) if rng.random() < 0.9 else 0 for _ in range(n + 1)] for _ in range(m + 1)]
+    grid[0][0], grid[1][1], grid[2][2] = (1 << bits) - 1, -((1 << bits) - 1), 0
+    e = ExactEngine(m, n)
+    e.upload(grid)
+    assert e.denominator() == 1
+    N, D = e.integer_state()
+    assert N == grid and D == 1
+    assert e.download() == [[Fraction(x) for x in row] for row in grid]
+    assert e.read_col(3) == [Fraction(grid[i][3]) for i in range(m + 1)]
+    e.close()
+
+
+def test_rational_rows_keep_their_scale_until_pivoted():
+    from linear_program_solver_b200.exact import ExactEngine
+    from oracle import lpsol_oracle as O
+    c, A, b = problems.BEALE
+    grid = O.make_grid(c, A, b)
+    e = ExactEngine(3, 7)
+    e.upload(grid)
+    assert e.download() == grid
+    O.pivot(grid, 0, 3)
+    assert e.pivot(0, 3) == 0
+    assert e.download() == grid
+    O.pivot(grid, 1, 4)
+    assert e.pivot(1, 4) == 0
+    assert e.download() == grid
+    e.close()
+
+
+def test_reference_known_answer_test_pivot():
+    """test_tableau.py:220-227 on the new Tableau in exact mode (whole-tableau equality, marks included)."""
+    g = load_golden("textbook")
+    t = _tab(g["c"], g["A"], g["b"])
+    for step in g["steps"]:
+        t.pivot(*step["pivot"])
+        assert [str(x) for x in t.getC()] == step["c"]
+        assert str(t._z) == step["z_cell"]
+        assert [str(x) for x in t.getB()] == step["b"]
+        assert [[str(x) for x in r] for r in t.getA()] == step["a"]
+    assert t.getZ() == -400
+    t2 = _tab(g["c"], g["A"], g["b"])
+    t2.pivot(0, 1)
+    t3 = _tab(g["c"], g["A"], g["b"])
+    t3.pivot(1, 0)
+    t3.pivot(0, 1)
+    t2.pivot(1, 0)
+    assert t3 == t and t2 == t
+    with pytest.raises(ZeroDivisionError, match="zero pivot 0,3"):
+        _tab(g["c"], g["A"], g["b"]).pivot(0, 3)
+
+
+@pytest.mark.parametrize("m,seed", [(6, 0), (20, 1), (50, 2)])
+def test_pivots_match_oracle_fractions_and_bareiss_integers(m, seed):
+    from linear_program_solver_b200.exact import ExactEngine
+    from oracle import lpsol_oracle as O
+    c, A, b = problems.dense_lp(m, seed)
+    grid = O.make_grid(c, A, b)
+    Nint = [[int(x) for x in row] for row in grid]
+    D = 1
+    e = ExactEngine(m, 2 * m)
+    e.upload(grid)
+    rng = random.Random(seed)
+    for _ in range(5):
+        r, cc = rng.randrange(m), rng.randrange(2 * m)
+        while grid[r][cc] == 0:
+            cc = rng.randrange(2 * m)
+        O.pivot(grid, r, cc)
+        D = O.bareiss_pivot(Nint, D, r, cc)
+        assert e.pivot(r, cc) == 0
+        gotN, gotD = e.integer_state()
+        assert gotD == D and gotN == Nint
+        assert e.download() == grid
+    e.close()
+
+
+@pytest.mark.parametrize("rec", load_golden("dense_exact"), ids=lambda r: f"m{r['m']}s{r['seed']}h{r['hi']}")
+def test_simplex_matches_reference_exactly(rec):
+    from linear_program_solver_b200 import Simplex
+    c, A, b = problems.dense_lp(rec["m"], rec["seed"], rec["lo"], rec["hi"])
+    t = _tab(c, A, b)
+    s = Simplex(t)
+    assert s.getBasicSequence() == rec["initial_basis"]
+    mp = rec.get("max_pivots")
+    s.solve(max_pivots=-1 if mp is None else mp)
+    assert [list(p) for p in s.pivot_log] == rec["pivots"]
+    assert s.getBasicSequence() == rec["basis"]
+    assert str(s.getObjValue()) == rec["objective"]
+    assert {str(j): str(v) for j, v in s.getBFS().items()} == rec["bfs"]
+    assert [bool(x) for x in t.getVarMarks()] == rec["marks"]
+
+
+@pytest.mark.parametrize("rec", load_golden("phase1"), ids=lambda r: f"m{r['m']}n{r['n']}s{r['seed']}")
+def test_phase1_matches_reference_exactly(rec):
+    from linear_program_solver_b200 import Simplex
+    c, A, b = problems.equality_lp(rec["m"], rec["n"], rec["seed"])
+    t = _tab(c, A, b)
+    if "ctor_error" in rec:
+        with pytest.raises({"ValueError": ValueError, "IndexError": IndexError}[rec["ctor_error"][0]]) as ei:
+            Simplex(t)
+        if rec["ctor_error"][0] == "ValueError":
+            assert str(ei.value) == rec["ctor_error"][1]
+        return
+    s = Simplex(t)
+    n1 = len(rec["phase1_pivots"])
+    assert [list(p) for p in s.pivot_log] == rec["phase1_pivots"]
+    assert s.getBasicSequence() == rec["initial_basis"]
+    s.solve()
+    assert [list(p) for p in s.pivot_log[n1:]] == rec["pivots"]
+    assert s.getBasicSequence() == rec["basis"]
+    assert str(s.getObjValue()) == rec["objective"]
+    assert {str(j): str(v) for j, v in s.getBFS().items()} == rec["bfs"]
+    assert [bool(x) for x in t.getVarMarks()] == rec["marks"]
+    assert list(t.getTableauSize()) == rec["m_n"]
+
+
+def test_special_cases():
+    from linear_program_solver_b200 import Simplex
+    sp = load_golden("special")
+    c, A, b = problems.BEALE
+    s = Simplex(_tab(c, A, b))
+    s.solve()
+    assert [list(p) for p in s.pivot_log] == sp["beale"]["pivots"]       # 10 Dantzig then 8 Bland pivots
+    assert str(s.getObjValue()) == sp["beale"]["objective"] == "-5/4"
+    assert {str(j): str(v) for j, v in s.getBFS().items()} == sp["beale"]["bfs"]
+    t = _tab([0, 0], [[1, 1], [1, 1]], [1, 2])
+    with pytest.raises(ValueError, match="infeasible problem, artificial opt = 1"):
+        Simplex(t)
+    assert t.getNumVars() == 4
+    s = Simplex(_tab([-1, 0], [[-1, 1]], [1]))
+    assert s.findPivotStandard() == "unbounded" and s.findPivotMinIndex() == "unbounded"
+    with pytest.raises(AssertionError, match="unbounded artificial problem"):
+        s.solve()
+    with pytest.raises(IndexError):
+        Simplex(_tab([1, 1, 1], [[1, 1, 0], [2, 2, 0], [0, 1, 1]], [2, 4, 3]))
+
+
+def test_find_pivot_is_canonical_is_optimal_match_oracle():
+    from linear_program_solver_b200.exact import ExactEngine
+    from oracle import lpsol_oracle as O
+    c, A, b = problems.dense_lp(16, 4)
+    grid = O.make_grid(c, A, b)
+    e = ExactEngine(16, 32)
+    e.upload(grid)
+    want = [-1] * 16
+    assert O.is_canonical(grid, want)
+    ok, cols = e.is_canonical()
+    assert ok and cols.tolist() == want
+    for _ in range(6):
+        for rule in (0, 1):
+            assert e.find_pivot(rule) == O.find_pivot(grid, rule)
+        found = O.find_pivot(grid, 0)
+        if isinstance(found, str):
+            break
+        r, cc = found
+        O.pivot(grid, r, cc)
+        assert e.pivot(r, cc) == 0
+        want = [-1] * 16
+        O.is_canonical(grid, want)
+        ok, cols = e.is_canonical()
+        assert cols.tolist() == want
+        assert e.is_optimal() == O.is_optimal(grid)
+    e.close()
+
+
+def test_prime_dividing_a_pivot_forces_a_reencode_and_keeps_the_answer():
+    """Small primes make 'p_k divides the pivot element' certain; results must not change."""
+    from linear_program_solver_b200.exact import ExactEngine, primes_for_bits
+    from oracle import lpsol_oracle as O
+    c, A, b = problems.dense_lp(8, 0)
+    want = O.simplex(c, A, b)
+    small = [3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97, 101, 103,
+             107, 109, 113, 127, 131, 137, 139, 149, 151, 157, 163, 167, 173, 179, 181, 191, 193, 197, 199, 211, 223,
+             227, 229, 233, 239, 241, 251, 257, 263, 269, 271, 277, 281, 283, 293]
+    e = ExactEngine(8, 16, primes=small + primes_for_bits(64))
+    e.upload(O.make_grid(c, A, b))
+    basis = np.arange(8, 16, dtype=np.int32)
+    st, k, trace = e.solve(basis, None, trace_cap=256)
+    assert st == 1 and e.reencodes > 0
+    assert [tuple(p) for p in trace.tolist()] == [tuple(p) for p in want["pivots"]]
+    assert basis.tolist() == want["basis"]
+    assert -e.read_row(8)[16] == want["objective"]
+    e.close()
