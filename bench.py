@@ -227,10 +227,10 @@ def run_ours(a):
     eng.prof_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
+    e0.record(eng.stream)                      # CUDA events on the stream the kernels are launched on
     for _ in range(a.steps):
         status, piv1 = step()
-    e1.record()
+    e1.record(eng.stream)
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None

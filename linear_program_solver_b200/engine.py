@@ -38,7 +38,11 @@ class F64Engine:
         self.ld = int(self.L.lps_grid_ld(self.n))
         with torch.cuda.device(self.device):
             self.grid = torch.zeros((self.m + 1, self.ld), dtype=torch.float64, device=f"cuda:{self.device}")
-            self.stream = torch.cuda.current_stream(self.device)
+            # A stream of our own, handed to the library by handle: torch's default stream has handle 0,
+            # which the C-ABI reads as "make a private stream" -- collectives and CUDA events issued from
+            # Python must be ordered on the very stream the kernels run on (use `with eng.on_stream():`).
+            self.stream = torch.cuda.Stream(self.device)
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
         h = c_void_p()
         N.check(self.L.lps_create_f64(self.m, self.n, self.device, self.grid.data_ptr(), self.stream.cuda_stream, byref(h)))
         self.h = h
@@ -61,13 +65,18 @@ class F64Engine:
     def sync(self):
         N.check(self.L.lps_sync(self.h))
 
+    def on_stream(self):
+        """Context manager: make the engine's stream torch's current stream (for collectives, events)."""
+        return _torch().cuda.stream(self.stream)
+
     # -- sharding ------------------------------------------------------------------------------
     def set_shard(self, row0: int, m_total: int, rank: int, nranks: int):
         torch = _torch()
         nb = int(self.L.lps_cand_bytes(self.n))
         dev = f"cuda:{self.device}"
-        self.cand_send = torch.zeros(nb, dtype=torch.uint8, device=dev)
-        self.cand_all = torch.zeros(nb * nranks, dtype=torch.uint8, device=dev) if nranks > 1 else self.cand_send
+        with self.on_stream():
+            self.cand_send = torch.zeros(nb, dtype=torch.uint8, device=dev)
+            self.cand_all = torch.zeros(nb * nranks, dtype=torch.uint8, device=dev) if nranks > 1 else self.cand_send
         N.check(self.L.lps_set_shard(self.h, row0, m_total, rank, nranks, self.cand_send.data_ptr(), self.cand_all.data_ptr()))
         self.row0, self.m_total, self.rank, self.nranks = row0, m_total, rank, nranks
 

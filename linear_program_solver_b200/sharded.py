@@ -52,7 +52,11 @@ class ShardedF64Solver:
     def _exchange(self):
         if self.nranks > 1:
             import torch.distributed as dist
-            dist.all_gather_into_tensor(self.eng.cand_all, self.eng.cand_send, group=self.group)
+            if hasattr(self.eng, "on_stream"):        # order the collective on the engine's own stream
+                with self.eng.on_stream():
+                    dist.all_gather_into_tensor(self.eng.cand_all, self.eng.cand_send, group=self.group)
+            else:
+                dist.all_gather_into_tensor(self.eng.cand_all, self.eng.cand_send, group=self.group)
 
     def enqueue(self, pivots: int):
         """Enqueue `pivots` (select, exchange, update) triples without waiting for the device."""

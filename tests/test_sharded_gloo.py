@@ -1,0 +1,157 @@
+"""Host-side protocol of the row-sharded solver on CPU: world_size 2 and 3 over gloo.
+
+The product engine is CUDA-only, so the ranks here plug a stand-in engine built on the CPU oracle
+(test infrastructure) into `ShardedF64Solver(engine_factory=...)`.  What is under test is the
+driver: row partition, candidate all-gather, global leaving-row choice (lowest ratio, then lowest
+global row), identical decisions on every rank, burst / poll / max_pivots logic.  The result must
+equal the single-process oracle solve of the whole tableau bit-for-bit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+HEADER = 64      # bytes of the candidate header (ratio f64, row i64, column i32, rule i32, stuck i64, pad)
+
+
+class OracleShardEngine:
+    """CPU stand-in with the stepping surface of F64Engine (candidate slot layout included)."""
+
+    def __init__(self, m, n, device=None):
+        self.m, self.n = m, n
+        self.T = np.zeros((m + 1, n + 1))
+        self.row0, self.m_total, self.rank, self.nranks = 0, m, 0, 1
+        self._alloc(1)
+
+    def _alloc(self, nranks):
+        self.slot = HEADER + 8 * (self.n + 1)
+        self.cand_send = torch.zeros(self.slot, dtype=torch.uint8)
+        self.cand_all = torch.zeros(self.slot * nranks, dtype=torch.uint8) if nranks > 1 else self.cand_send
+
+    def set_shard(self, row0, m_total, rank, nranks):
+        self.row0, self.m_total, self.rank, self.nranks = row0, m_total, rank, nranks
+        self._alloc(nranks)
+
+    def close(self):
+        pass
+
+    def solve_begin(self, basis, marks, max_pivots, trace_cap):
+        self.basis = basis.copy()
+        self.z_entry = self.T[self.m, self.n]
+        self.status, self.rule, self.stuck, self.npiv, self.max_pivots = 0, 0, 0, 0, max_pivots
+        self.pending = False
+        self.trace = []
+
+    def step_select(self):
+        from oracle import c_oracle as C
+        if self.status != 0:
+            return
+        if self.max_pivots >= 0 and self.npiv >= self.max_pivots:
+            self.status = 4
+            return
+        stuck, rule = self.stuck, self.rule
+        if self.pending:
+            stuck = stuck + 1 if self.T[self.m, self.n] == self.z_entry else 0
+        if rule == 0 and not stuck < self.m_total + self.n:
+            rule = 1
+        c = C.price(self.T, rule)
+        if c < 0:
+            self.status = 1
+            return
+        r = C.ratio(self.T, c)
+        hdr = np.zeros(8, dtype=np.int64)
+        buf = self.cand_send.numpy()
+        ratio = self.T[r, self.n] / self.T[r, c] if r >= 0 else 0.0
+        buf[0:8] = np.frombuffer(np.float64(ratio).tobytes(), dtype=np.uint8)
+        buf[8:16] = np.frombuffer(np.int64(self.row0 + r if r >= 0 else -1).tobytes(), dtype=np.uint8)
+        buf[16:24] = np.frombuffer(np.array([c, rule], dtype=np.int32).tobytes(), dtype=np.uint8)
+        buf[24:32] = np.frombuffer(np.int64(stuck).tobytes(), dtype=np.uint8)
+        if r >= 0:
+            p = self.T[r, c]
+            inv = 1.0 / p
+            row = self.T[r] if inv == 1.0 else self.T[r] * inv
+            buf[HEADER:] = np.frombuffer(row.tobytes(), dtype=np.uint8)
+
+    def step_update(self):
+        if self.status != 0:
+            return
+        buf = self.cand_all.numpy()
+        best = None
+        for k in range(self.nranks):
+            s = buf[k * self.slot:(k + 1) * self.slot]
+            ratio = float(np.frombuffer(s[0:8].tobytes(), dtype=np.float64)[0])
+            row = int(np.frombuffer(s[8:16].tobytes(), dtype=np.int64)[0])
+            if row < 0:
+                continue
+            if best is None or ratio < best[0] or (ratio == best[0] and row < best[1]):
+                best = (ratio, row, k)
+        if best is None:
+            self.status = 2
+            return
+        _, grow, k = best
+        s = buf[k * self.slot:(k + 1) * self.slot]
+        c, rule = np.frombuffer(s[16:24].tobytes(), dtype=np.int32)
+        stuck = int(np.frombuffer(s[24:32].tobytes(), dtype=np.int64)[0])
+        v = np.frombuffer(s[HEADER:].tobytes(), dtype=np.float64)
+        lr = grow - self.row0
+        for i in range(self.m + 1):
+            if i == lr:
+                continue
+            mult = -self.T[i, c]
+            if mult != 0.0:
+                self.T[i] = self.T[i] + mult * v       # product then sum, like the reference
+        if 0 <= lr < self.m:
+            self.T[lr] = v
+        self.basis[grow] = c
+        self.trace.append((grow, int(c), int(rule)))
+        self.npiv += 1
+        self.rule, self.stuck, self.pending = int(rule), stuck, rule == 0
+
+    def poll(self):
+        return self.status, self.npiv
+
+    def solve_end(self, basis, marks, trace_cap):
+        basis[:] = self.basis
+        return self.status, self.npiv, np.array(self.trace[:trace_cap], dtype=np.int32).reshape(-1, 3)
+
+
+def _worker(rank, world, port, m, seed, max_pivots, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from linear_program_solver_b200 import problems
+    from linear_program_solver_b200.sharded import ShardedF64Solver, shard_rows
+    sv = ShardedF64Solver(m, 2 * m, rank, world, engine_factory=OracleShardEngine, burst=3)
+    row0, ml = shard_rows(m, rank, world)
+    sv.eng.T[:] = problems.hashed_dense_grid(m, seed, 1, 9, row0, ml).astype(np.float64)
+    basis = np.arange(m, 2 * m, dtype=np.int32)
+    st, k, trace = sv.solve(basis, None, max_pivots=max_pivots, trace_cap=10 ** 6)
+    out[rank] = (st, k, trace.tolist(), basis.tolist(), row0, sv.eng.T.copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,m,seed,max_pivots", [(2, 24, 0, -1), (3, 31, 1, -1), (2, 40, 2, 7)])
+def test_sharded_protocol_equals_single_process_oracle(world, m, seed, max_pivots):
+    from linear_program_solver_b200 import problems
+    from oracle import c_oracle as C
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() + 7 * world + m) % 2000
+    mp.spawn(_worker, args=(world, port, m, seed, max_pivots, out), nprocs=world, join=True)
+    T = problems.hashed_dense_grid(m, seed).astype(np.float64)
+    basis = np.arange(m, 2 * m, dtype=np.int32)
+    st, k, trace = C.solve(T, basis, max_pivots=max_pivots)
+    assert len(out) == world
+    for rank in range(world):
+        rst, rk, rtrace, rbasis, row0, shard = out[rank]
+        assert (rst, rk) == (st, k) and rtrace == trace.tolist() and rbasis == basis.tolist()
+        ml = shard.shape[0] - 1
+        assert shard[:ml].tobytes() == T[row0:row0 + ml].tobytes()       # the rank's rows
+        assert shard[ml].tobytes() == T[m].tobytes()                      # its replica of the objective row

@@ -151,7 +151,7 @@ def main():
             dense.append(rec)
             print("dense exact", m, seed, len(rec["pivots"]), rec["objective"], flush=True)
     # 8-bit coefficients (config 3 family), small sizes + a pivot prefix at a larger one
-    for m, seeds, mp in [(24, range(3), None), (60, [0], None), (200, [0], 12)]:
+    for m, seeds, mp in [(24, range(3), None), (60, [0], None), (200, [0], 12), (1000, [0], 6)]:
         for seed in seeds:
             c, A, b = problems.dense_lp(m, seed, 1, 127)
             rec = run(ref, c, A, b, max_pivots=mp)
