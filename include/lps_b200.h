@@ -40,6 +40,9 @@ extern "C" {
 #define LPS_MAX_PIVOTS    4   /* stopped after the requested pivot prefix (not in reference) */
 #define LPS_BAD_PRIME     5   /* exact mode: next pivot is 0 modulo a prime; re-encode      */
 #define LPS_OBJ_INCREASED  6   /* simplex.py:133 'objective value increased (internal error)' */
+#define LPS_INFEASIBLE       7   /* simplex.py:64-67 ValueError('infeasible problem, artificial opt = z') */
+#define LPS_REDUNDANT_ROW    8   /* simplex.py:84-93 dependent row dropped: the reference then fails with IndexError */
+#define LPS_NEED_ARTIFICIALS 9   /* batched solve: more artificial columns needed than the batch reserved */
 #define LPS_E_INVALID    -1   /* bad argument                                              */
 #define LPS_E_CUDA       -2   /* CUDA runtime error, see lps_last_error()                  */
 #define LPS_E_NOMEM      -3
@@ -173,6 +176,41 @@ int lps_exact_info(lps_handle *h, int *nprimes, int *bad_prime, size_t *residue_
  * and makes the next lps_solve continue from it (resuming after LPS_BAD_PRIME on a re-encoded
  * tableau without disturbing the reference's rule-switch sequence). */
 int lps_exact_loop_state(lps_handle *h, int set, int *rule, long long *stuck, int *moved, int *pending);
+
+/* ---- batched node LPs (MILP branch and bound, BASELINE.json config 5) ---------------------------
+ * The reference's LinProg is an empty stub (linprog.py:383-393), so there is no branch-and-bound to
+ * replace; what a B&B driver calls per node is `Simplex(tab); tab... solve()` (simplex.py:24-148) on a
+ * small integer tableau.  A batch runs that WHOLE sequence -- phase 1 included (simplex.py:36-108) --
+ * for `count` independent LPs of one shape in one kernel launch: one LP per thread-block cluster, the
+ * exact-mode residue planes resident in (distributed) shared memory, `cluster` CTAs per LP
+ * (0 = automatic; 1 when the planes of all primes fit one CTA).
+ *   grids      count x (m+1) x (n+1) int32 in the device layout above (integer coefficients)
+ *   art_cap    artificial columns reserved per LP (rows without a basic column, simplex.py:54)
+ *   primes     <= 32 distinct odd primes below 2^31 whose product exceeds twice the Hadamard bound of
+ *              every LP's extended matrix (phase-1 objective included)
+ * Per-LP status: LPS_OPTIMAL, LPS_UNBOUNDED, LPS_INFEASIBLE, LPS_REDUNDANT_ROW, LPS_MAX_PIVOTS,
+ * LPS_BAD_PRIME (solve that LP alone with another prime set), LPS_NEED_ARTIFICIALS. */
+typedef struct lps_batch lps_batch;
+size_t lps_batch_smem_bytes(int m, int n, int art_cap, int nprimes, int cluster);
+int lps_batch_create(int count, int m, int n, int art_cap, int nprimes, const uint32_t *primes, int cluster,
+                     int trace_cap, int device, void *stream, lps_batch **out);
+int lps_batch_destroy(lps_batch *b);
+int lps_batch_upload(lps_batch *b, const int32_t *grids);          /* host -> device, asynchronous */
+void *lps_batch_grids_ptr(lps_batch *b);                           /* device copy of the grids */
+int lps_batch_run(lps_batch *b, long long max_pivots);             /* Simplex(tab); solve() per LP, asynchronous */
+int lps_batch_sync(lps_batch *b);
+/* Number of consecutive Dantzig pivots at the entry objective after which solve() switches to Bland's rule.
+ * Negative (default): the reference's m + n (simplex.py:123).  Parity tests lower it to reach loop B. */
+int lps_batch_set_stuck_limit(lps_batch *b, long long limit);
+/* Results (any pointer may be NULL): status[count]; npiv[count][4] = phase-1, drive-out, phase-2 pivots and
+ * the number of artificial columns; basis[count][m] (Simplex._bfs); sign[count][m+2] / digits[count][P][m+2]:
+ * b_0..b_{m-1}, the `_z` cell and the common denominator D as sign + mixed-radix digits (see
+ * lps_read_exact), so that b_i = N_i / D; trace[count][trace_cap][3] = (row, column, rule) per pivot,
+ * rule 2 = phase-1 drive-out pivot. */
+int lps_batch_download(lps_batch *b, int *status, int *npiv, int *basis, signed char *sign, uint32_t *digits,
+                       int *trace);
+int lps_batch_info(lps_batch *b, int *cluster, int *primes_per_cta, size_t *smem_bytes, int *resident_clusters,
+                   double *last_run_ms, long long *launches);
 
 /* Timing aid for bench.py: CUDA-event time (ms) and launch count of the
  * rank-1 update kernels enqueued since the last reset, measured on the

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblps_b200.so")
 
 OK, OPTIMAL, UNBOUNDED, ZERO_PIVOT, MAX_PIVOTS, BAD_PRIME, STALLED = 0, 1, 2, 3, 4, 5, 6
+INFEASIBLE, REDUNDANT_ROW, NEED_ARTIFICIALS = 7, 8, 9
 E_INVALID, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4
 RULE_DANTZIG, RULE_BLAND = 0, 1
 
@@ -65,6 +66,17 @@ SIGNATURES = {
     "lps_read_alive": (c_int, [c_void_p, c_void_p]),
     "lps_exact_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     "lps_exact_loop_state": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_longlong), POINTER(c_int), POINTER(c_int)]),
+    "lps_batch_smem_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "lps_batch_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "lps_batch_destroy": (c_int, [c_void_p]),
+    "lps_batch_upload": (c_int, [c_void_p, c_void_p]),
+    "lps_batch_grids_ptr": (c_void_p, [c_void_p]),
+    "lps_batch_run": (c_int, [c_void_p, c_longlong]),
+    "lps_batch_sync": (c_int, [c_void_p]),
+    "lps_batch_set_stuck_limit": (c_int, [c_void_p, c_longlong]),
+    "lps_batch_download": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lps_batch_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t), POINTER(c_int), POINTER(c_double),
+                               POINTER(c_longlong)]),
     "lps_prof_reset": (c_int, [c_void_p]),
     "lps_prof_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong), POINTER(c_longlong)]),
 }

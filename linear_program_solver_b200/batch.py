@@ -1,0 +1,234 @@
+"""Batched exact solves of small LPs: `Simplex(tab); solve()` for many tableaux in one kernel launch.
+
+This is the node-LP engine of the branch-and-bound driver in `linprog.py` (BASELINE.json config 5).
+The reference has no such thing -- its `LinProg` is an empty stub (linprog.py:383-393) -- but what a
+B&B driver does per node is exactly the reference's `Simplex(tab)` constructor (phase 1,
+simplex.py:36-108) followed by `solve()` (simplex.py:110-148); `lps_batch_*` (include/lps_b200.h) runs
+that whole sequence for every LP of a batch on the GPU, one LP per thread-block cluster with the
+multi-modular tableau in shared memory.
+
+The host side here only SIZES the batch (how many artificial columns to reserve, how many primes the
+Hadamard bound asks for) and DECODES results (mixed-radix digits -> Python ints -> Fractions).  No
+pivot, pricing, ratio test or phase-1 arithmetic runs on the host; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from ctypes import byref, c_double, c_int, c_longlong, c_size_t, c_void_p
+from fractions import Fraction
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .exact import MixedRadix, primes_for_bits
+
+MAX_PRIMES = 16
+
+STATUS_NAME = {N.OPTIMAL: "optimal", N.UNBOUNDED: "unbounded", N.MAX_PIVOTS: "max_pivots", N.BAD_PRIME: "bad_prime",
+               N.STALLED: "objective_increased", N.INFEASIBLE: "infeasible", N.REDUNDANT_ROW: "redundant_row",
+               N.NEED_ARTIFICIALS: "need_artificials"}
+
+
+# ------------------------------------------------------------------------------------------------
+# sizing (no arithmetic of the path: only counts and norms)
+# ------------------------------------------------------------------------------------------------
+def missing_basic_rows(G: np.ndarray) -> np.ndarray:
+    """[count, m] bool: rows that lack a basic column after the sign normalisation of simplex.py:43-45,
+    i.e. the rows that get an artificial column (tableau.py:466-496 decides what a basic column is)."""
+    m = G.shape[1] - 1
+    n = G.shape[2] - 1
+    sign = np.where(G[:, :m, n] < 0, -1, 1).astype(G.dtype)
+    A = G[:, :m, :n] * sign[:, :, None]
+    nonzero = A != 0
+    basic = (G[:, m, :n] == 0) & (nonzero.sum(axis=1) == 1) & ((A == 1).sum(axis=1) == 1)
+    hit = nonzero.argmax(axis=1)                                     # row of the single nonzero
+    has = np.zeros((G.shape[0], m), dtype=bool)
+    b_idx, j_idx = np.nonzero(basic)
+    has[b_idx, hit[b_idx, j_idx]] = True
+    return ~has
+
+
+def bound_bits(G: np.ndarray, missing: np.ndarray) -> int:
+    """Bits of a Hadamard bound on every minor of every LP's extended matrix, the phase-1 objective
+    (minus the sum of the rows that get an artificial, simplex.py:56-60) included."""
+    m = G.shape[1] - 1
+    A = G.astype(np.float64)
+    phase1_obj = -(np.abs(A[:, :m, :]) * missing[:, :, None]).sum(axis=1)      # |.| bounds both row signs
+    obj = np.maximum(np.abs(A[:, m, :]), np.abs(phase1_obj))
+    body = A[:, :m, :]
+    row_sq = np.concatenate([(body * body).sum(axis=2), (obj * obj).sum(axis=1)[:, None]], axis=1)
+    col_sq = (body * body).sum(axis=1) + obj * obj
+    row_sq = np.maximum(row_sq, 1.0)
+    col_sq = np.maximum(col_sq, 1.0)
+    order = min(row_sq.shape[1], col_sq.shape[1])
+    by_rows = np.log2(np.sort(row_sq, axis=1)[:, ::-1][:, :order]).sum(axis=1) / 2
+    by_cols = np.log2(np.sort(col_sq, axis=1)[:, ::-1][:, :order]).sum(axis=1) / 2
+    return int(math.ceil(float(np.minimum(by_rows, by_cols).max()))) + 3
+
+
+class BatchResult:
+    """Results of one batch; numbers are decoded lazily into Fractions."""
+
+    def __init__(self, m: int, n: int, status, npiv, basis, sign, digits, trace, codec: MixedRadix):
+        self.m, self.n = m, n
+        self.status = status                  # [count] lps status codes
+        self.npiv = npiv                      # [count, 4]: phase-1, drive-out, phase-2 pivots, artificial columns
+        self.basis = basis                    # [count, m]
+        self._sign, self._digits, self._codec = sign, digits, codec
+        self.trace = trace                    # [count, trace_cap, 3] or None
+        self._ints: Dict[int, List[int]] = {}
+
+    def __len__(self) -> int:
+        return len(self.status)
+
+    def status_name(self, k: int) -> str:
+        return STATUS_NAME.get(int(self.status[k]), str(int(self.status[k])))
+
+    def integers(self, k: int) -> List[int]:
+        """[N_0n, ..., N_(m-1)n, the z cell, D] of LP k as Python ints."""
+        if k not in self._ints:
+            self._ints[k] = self._codec.decode(self._sign[k], self._digits[k])
+        return self._ints[k]
+
+    def rhs(self, k: int) -> List[Fraction]:
+        v = self.integers(k)
+        D = v[self.m + 1]
+        return [Fraction(x, D) for x in v[: self.m]]
+
+    def objective(self, k: int) -> Fraction:
+        """`Simplex.getObjValue` (simplex.py:188-190): minus the corner cell."""
+        v = self.integers(k)
+        return Fraction(-v[self.m], v[self.m + 1])
+
+    def bfs(self, k: int) -> Dict[int, Fraction]:
+        """`Simplex.getBFS` (simplex.py:165-172)."""
+        b = self.rhs(k)
+        return {int(j): b[i] for i, j in enumerate(self.basis[k])}
+
+    def pivots(self, k: int) -> List[tuple]:
+        """(row, column, rule) of every pivot of LP k in order; rule 2 marks a phase-1 drive-out pivot."""
+        if self.trace is None:
+            raise ValueError("the batch was run without a pivot trace")
+        cnt = int(self.npiv[k, :3].sum())
+        return [tuple(int(v) for v in row) for row in self.trace[k, : min(cnt, self.trace.shape[1])]]
+
+    def raise_for_status(self, k: int):
+        """The exception the reference's `Simplex(tab); solve()` raises for this outcome."""
+        st = int(self.status[k])
+        if st == N.OPTIMAL:
+            return
+        if st == N.INFEASIBLE:
+            raise ValueError(f"infeasible problem, artificial opt = {self.objective(k)}")
+        if st == N.REDUNDANT_ROW:
+            raise IndexError("list index out of range")
+        if st == N.UNBOUNDED:
+            raise AssertionError("unbounded artificial problem (internal error)")
+        if st == N.STALLED:
+            raise AssertionError("objective value increased (internal error)")
+        raise N.NativeError(f"batched solve ended with status {self.status_name(k)}")
+
+
+class BatchExactSolver:
+    """`count` LPs of one shape on one GPU.  `solve(grids)` = `[Simplex(Tableau(grid)).solve() for grid in grids]`."""
+
+    def __init__(self, count: int, m: int, n: int, primes: Sequence[int], art_cap: int = 0, cluster: int = 0,
+                 trace_cap: int = 0, device: Optional[int] = None):
+        import torch
+        self.L = N.lib()
+        self.device = int(torch.cuda.current_device() if device is None else device)
+        self.count, self.m, self.n = int(count), int(m), int(n)
+        self.art_cap, self.trace_cap = int(art_cap), int(trace_cap)
+        self.primes = [int(p) for p in primes]
+        self.codec = MixedRadix(self.primes)
+        arr = np.asarray(self.primes, dtype=np.uint32)
+        h = c_void_p()
+        N.check(self.L.lps_batch_create(self.count, self.m, self.n, self.art_cap, len(self.primes), arr.ctypes.data,
+                                        int(cluster), self.trace_cap, self.device, None, byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lps_batch_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        c, pl, sm, rc, ms, nl = c_int(0), c_int(0), c_size_t(0), c_int(0), c_double(0), c_longlong(0)
+        N.check(self.L.lps_batch_info(self.h, byref(c), byref(pl), byref(sm), byref(rc), byref(ms), byref(nl)))
+        return {"cluster": c.value, "primes": len(self.primes), "primes_per_cta": pl.value, "smem_bytes": sm.value,
+                "resident_clusters": rc.value, "last_run_ms": ms.value, "launches": nl.value}
+
+    def upload(self, grids: np.ndarray):
+        assert grids.dtype == np.int32 and grids.shape == (self.count, self.m + 1, self.n + 1) and grids.flags.c_contiguous
+        N.check(self.L.lps_batch_upload(self.h, grids.ctypes.data))
+        self._keep = grids                    # the copy is asynchronous
+
+    def run(self, max_pivots: int = -1):
+        N.check(self.L.lps_batch_run(self.h, max_pivots))
+
+    def sync(self):
+        N.check(self.L.lps_batch_sync(self.h))
+
+    def set_stuck_limit(self, limit: int = -1):
+        """Degenerate Dantzig pivots before the switch to Bland; -1 = the reference's m + n (simplex.py:123)."""
+        N.check(self.L.lps_batch_set_stuck_limit(self.h, int(limit)))
+
+    def download(self, want_numbers: bool = True) -> BatchResult:
+        c, m, P = self.count, self.m, len(self.primes)
+        status = np.empty(c, dtype=np.int32)
+        npiv = np.empty((c, 4), dtype=np.int32)
+        basis = np.empty((c, m), dtype=np.int32)
+        sign = np.empty((c, m + 2), dtype=np.int8) if want_numbers else None
+        digits = np.empty((c, P, m + 2), dtype=np.uint32) if want_numbers else None
+        trace = np.zeros((c, self.trace_cap, 3), dtype=np.int32) if self.trace_cap > 0 else None
+        N.check(self.L.lps_batch_download(self.h, status.ctypes.data, npiv.ctypes.data, basis.ctypes.data,
+                                          sign.ctypes.data if want_numbers else None,
+                                          digits.ctypes.data if want_numbers else None,
+                                          trace.ctypes.data if trace is not None else None))
+        return BatchResult(m, self.n, status, npiv, basis, sign, digits, trace, self.codec)
+
+    def solve(self, grids: np.ndarray, max_pivots: int = -1) -> BatchResult:
+        self.upload(grids)
+        self.run(max_pivots)
+        return self.download()
+
+
+def plan_batch(grids: np.ndarray, banned: Sequence[int] = ()):
+    """(art_cap, primes) for a batch of integer tableaux, or raises ValueError when the Hadamard bound
+    needs more primes than the batched kernel holds (solve those LPs one at a time)."""
+    G = np.ascontiguousarray(grids)
+    missing = missing_basic_rows(G)
+    art_cap = int(missing.sum(axis=1).max(initial=0))
+    bits = bound_bits(G, missing)
+    primes = primes_for_bits(bits, banned)
+    if len(primes) > MAX_PRIMES:
+        raise ValueError(f"Hadamard bound of {bits} bits needs {len(primes)} primes; the batched kernel holds {MAX_PRIMES}")
+    return art_cap, primes, bits
+
+
+def solve_batch(grids, trace_cap: int = 0, cluster: int = 0, device: Optional[int] = None, max_pivots: int = -1,
+                stuck_limit: int = -1) -> BatchResult:
+    """`Simplex(tab); solve()` of the reference for every integer tableau of `grids`
+    ([count, m+1, n+1], device layout: row m = costs, column n = rhs, cell (m, n) = minus the objective)."""
+    G = np.ascontiguousarray(np.asarray(grids), dtype=np.int64)
+    if G.ndim != 3:
+        raise ValueError("grids must be [count, m+1, n+1]")
+    if np.abs(G).max(initial=0) >= 2 ** 31:
+        raise ValueError("batched tableaux take 32-bit integer coefficients")
+    G32 = np.ascontiguousarray(G, dtype=np.int32)
+    art_cap, primes, _ = plan_batch(G32)
+    solver = BatchExactSolver(G.shape[0], G.shape[1] - 1, G.shape[2] - 1, primes, art_cap=art_cap, cluster=cluster,
+                              trace_cap=trace_cap, device=device)
+    if max_pivots < 0:                       # Bland's rule terminates; the cap only bounds a run gone wrong
+        max_pivots = 64 * (G.shape[1] + G.shape[2]) + 256
+    try:
+        solver.set_stuck_limit(stuck_limit)
+        return solver.solve(G32, max_pivots)
+    finally:
+        solver.close()

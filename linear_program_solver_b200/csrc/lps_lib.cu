@@ -2,3 +2,4 @@
 // C-ABI, so the two API files are compiled together.
 #include "lps_api.cu"
 #include "lps_exact_api.cu"
+#include "lps_batch_api.cu"

@@ -209,7 +209,8 @@ class UnboundedError(AssertionError):
     """The reference asserts on an unbounded LP (simplex.py:125, :140)."""
 
 
-def solve(grid: Grid, basis: List[int], trace: Optional[list] = None, max_pivots: Optional[int] = None) -> int:
+def solve(grid: Grid, basis: List[int], trace: Optional[list] = None, max_pivots: Optional[int] = None,
+          stuck_limit: Optional[int] = None) -> int:
     """`Simplex.solve` (simplex.py:110-148).  Mutates grid and basis; returns the pivot count.
 
     Loop A prices with Dantzig while the stuck counter is below m+n; the counter
@@ -217,7 +218,8 @@ def solve(grid: Grid, basis: List[int], trace: Optional[list] = None, max_pivots
     refreshes `obj_val`, simplex.py:118/:134 -- SURVEY F5a) and resets
     otherwise.  Loop B prices with Bland until optimal and never goes back.
     `trace` receives (row, column, rule) per pivot.  `max_pivots` (not in the
-    reference) stops after a prefix, for timing large cases.
+    reference) stops after a prefix, for timing large cases.  `stuck_limit` (not in the reference, whose
+    limit is m+n) lets tests reach loop B on LPs that do not cycle.
     """
     m, n = shape(grid)
     z_entry = objective(grid)
@@ -227,7 +229,7 @@ def solve(grid: Grid, basis: List[int], trace: Optional[list] = None, max_pivots
         return 0
     rule = RULE_DANTZIG
     while True:
-        if rule == RULE_DANTZIG and not (stuck < m + n):
+        if rule == RULE_DANTZIG and not (stuck < (m + n if stuck_limit is None else stuck_limit)):
             rule = RULE_BLAND
         if max_pivots is not None and done >= max_pivots:
             return done
@@ -258,7 +260,7 @@ class InfeasibleError(ValueError):
     pass
 
 
-def find_bfs(grid: Grid, trace: Optional[list] = None) -> Tuple[Grid, List[int]]:
+def find_bfs(grid: Grid, trace: Optional[list] = None, stuck_limit: Optional[int] = None) -> Tuple[Grid, List[int]]:
     """`Simplex._find_bfs` (simplex.py:36-108).  Returns (grid, basis); the grid may be re-shaped.
 
     Rows with b_i < 0 are negated; if the tableau is then canonical the basis
@@ -299,7 +301,7 @@ def find_bfs(grid: Grid, trace: Optional[list] = None) -> Tuple[Grid, List[int]]
         grid[i][n + idx] = num(1)
         row_axpy(grid, m, i, -num(1))
         basis[i] = n + idx
-    solve(grid, basis, trace)
+    solve(grid, basis, trace, stuck_limit=stuck_limit)
     z = objective(grid)
     if z != 0:
         raise InfeasibleError(f"infeasible problem, artificial opt = {z}")
@@ -333,14 +335,14 @@ def find_bfs(grid: Grid, trace: Optional[list] = None) -> Tuple[Grid, List[int]]
     return grid, basis
 
 
-def simplex(c, A, b, z=0, num: Callable = Fraction, max_pivots: Optional[int] = None):
+def simplex(c, A, b, z=0, num: Callable = Fraction, max_pivots: Optional[int] = None, stuck_limit: Optional[int] = None):
     """`Simplex(tab); solve()` end to end.  Returns a dict of everything parity tests compare."""
     grid = make_grid(c, A, b, z, num)
     phase1: list = []
-    grid, basis = find_bfs(grid, phase1)
+    grid, basis = find_bfs(grid, phase1, stuck_limit)
     initial_basis = list(basis)
     trace: list = []
-    solve(grid, basis, trace, max_pivots)
+    solve(grid, basis, trace, max_pivots, stuck_limit)
     m, n = shape(grid)
     return {
         "grid": grid,
