@@ -182,12 +182,12 @@ int lps_exact_loop_state(lps_handle *h, int set, int *rule, long long *stuck, in
  * replace; what a B&B driver calls per node is `Simplex(tab); tab... solve()` (simplex.py:24-148) on a
  * small integer tableau.  A batch runs that WHOLE sequence -- phase 1 included (simplex.py:36-108) --
  * for `count` independent LPs of one shape in one kernel launch: one LP per thread-block cluster, the
- * exact-mode residue planes resident in (distributed) shared memory, `cluster` CTAs per LP
- * (0 = automatic; 1 when the planes of all primes fit one CTA).
+ * exact-mode residue planes resident in (distributed) shared memory, row-sharded over `cluster` CTAs
+ * per LP (0 = automatic; 1 = the whole LP in one CTA).
  *   grids      count x (m+1) x (n+1) int32 in the device layout above (integer coefficients)
  *   art_cap    artificial columns reserved per LP (rows without a basic column, simplex.py:54)
- *   primes     <= 32 distinct odd primes below 2^31 whose product exceeds twice the Hadamard bound of
- *              every LP's extended matrix (phase-1 objective included)
+ *   primes     an even number (2..16) of distinct odd primes below 2^31 in ASCENDING order whose product
+ *              exceeds twice the Hadamard bound of every LP's extended matrix (phase-1 objective included)
  * Per-LP status: LPS_OPTIMAL, LPS_UNBOUNDED, LPS_INFEASIBLE, LPS_REDUNDANT_ROW, LPS_MAX_PIVOTS,
  * LPS_BAD_PRIME (solve that LP alone with another prime set), LPS_NEED_ARTIFICIALS. */
 typedef struct lps_batch lps_batch;
@@ -209,7 +209,9 @@ int lps_batch_set_stuck_limit(lps_batch *b, long long limit);
  * rule 2 = phase-1 drive-out pivot. */
 int lps_batch_download(lps_batch *b, int *status, int *npiv, int *basis, signed char *sign, uint32_t *digits,
                        int *trace);
-int lps_batch_info(lps_batch *b, int *cluster, int *primes_per_cta, size_t *smem_bytes, int *resident_clusters,
+/* Profiling aid: cycles per kernel phase and LP (out[count][16]); out == NULL arms the collection. */
+int lps_batch_timing(lps_batch *b, long long *out);
+int lps_batch_info(lps_batch *b, int *cluster, int *rows_per_cta, size_t *smem_bytes, int *resident_clusters,
                    double *last_run_ms, long long *launches);
 
 /* Timing aid for bench.py: CUDA-event time (ms) and launch count of the

@@ -21,7 +21,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _native as N
-from .exact import MixedRadix, primes_for_bits
+from .exact import MixedRadix, primes_below_2_31, primes_for_bits
 
 MAX_PRIMES = 16
 
@@ -91,6 +91,20 @@ class BatchResult:
             self._ints[k] = self._codec.decode(self._sign[k], self._digits[k])
         return self._ints[k]
 
+    def _one(self, k: int, idx: int) -> int:
+        """Number `idx` of LP k alone (Horner over its mixed-radix digits, highest nonzero digit first)."""
+        if k in self._ints:
+            return self._ints[k][idx]
+        dig = self._digits[k, :, idx].tolist()
+        primes = self._codec.primes
+        top = len(dig) - 1
+        while top >= 0 and dig[top] == 0:
+            top -= 1
+        v = 0
+        for j in range(top, -1, -1):
+            v = v * primes[j] + dig[j]
+        return -v if self._sign[k, idx] < 0 else v
+
     def rhs(self, k: int) -> List[Fraction]:
         v = self.integers(k)
         D = v[self.m + 1]
@@ -98,8 +112,7 @@ class BatchResult:
 
     def objective(self, k: int) -> Fraction:
         """`Simplex.getObjValue` (simplex.py:188-190): minus the corner cell."""
-        v = self.integers(k)
-        return Fraction(-v[self.m], v[self.m + 1])
+        return Fraction(-self._one(k, self.m), self._one(k, self.m + 1))
 
     def bfs(self, k: int) -> Dict[int, Fraction]:
         """`Simplex.getBFS` (simplex.py:165-172)."""
@@ -139,7 +152,7 @@ class BatchExactSolver:
         self.device = int(torch.cuda.current_device() if device is None else device)
         self.count, self.m, self.n = int(count), int(m), int(n)
         self.art_cap, self.trace_cap = int(art_cap), int(trace_cap)
-        self.primes = [int(p) for p in primes]
+        self.primes = sorted(int(p) for p in primes)       # ascending: digit j of the mixed radix is < every later prime
         self.codec = MixedRadix(self.primes)
         arr = np.asarray(self.primes, dtype=np.uint32)
         h = c_void_p()
@@ -161,7 +174,7 @@ class BatchExactSolver:
     def info(self) -> dict:
         c, pl, sm, rc, ms, nl = c_int(0), c_int(0), c_size_t(0), c_int(0), c_double(0), c_longlong(0)
         N.check(self.L.lps_batch_info(self.h, byref(c), byref(pl), byref(sm), byref(rc), byref(ms), byref(nl)))
-        return {"cluster": c.value, "primes": len(self.primes), "primes_per_cta": pl.value, "smem_bytes": sm.value,
+        return {"cluster": c.value, "primes": len(self.primes), "rows_per_cta": pl.value, "smem_bytes": sm.value,
                 "resident_clusters": rc.value, "last_run_ms": ms.value, "launches": nl.value}
 
     def upload(self, grids: np.ndarray):
@@ -174,6 +187,18 @@ class BatchExactSolver:
 
     def sync(self):
         N.check(self.L.lps_batch_sync(self.h))
+
+    PHASES = ["price local", "barrier 1", "price fold", "ratio garner", "ratio local", "barrier 2", "ratio global",
+              "pivot consts+row bcast", "barrier 3", "update", "inverse", "loop", "setup", "phase-1 glue", "results"]
+
+    def timing(self, read: bool = True):
+        """Profiling aid: arm the per-phase cycle counters (read=False) or fetch [count, 16] cycles of the last run."""
+        if not read:
+            N.check(self.L.lps_batch_timing(self.h, None))
+            return None
+        out = np.zeros((self.count, 16), dtype=np.int64)
+        N.check(self.L.lps_batch_timing(self.h, out.ctypes.data))
+        return out
 
     def set_stuck_limit(self, limit: int = -1):
         """Degenerate Dantzig pivots before the switch to Bland; -1 = the reference's m + n (simplex.py:123)."""
@@ -207,6 +232,8 @@ def plan_batch(grids: np.ndarray, banned: Sequence[int] = ()):
     art_cap = int(missing.sum(axis=1).max(initial=0))
     bits = bound_bits(G, missing)
     primes = primes_for_bits(bits, banned)
+    if len(primes) & 1:                      # the kernel is instantiated for even prime counts
+        primes = primes_below_2_31(len(primes) + 1, banned)
     if len(primes) > MAX_PRIMES:
         raise ValueError(f"Hadamard bound of {bits} bits needs {len(primes)} primes; the batched kernel holds {MAX_PRIMES}")
     return art_cap, primes, bits

@@ -2,6 +2,7 @@
 // plan, precomputes the prime tables and launches k_bnb_nodes.  No arithmetic of the path runs here.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -13,7 +14,7 @@ struct lps_batch {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int count = 0, m = 0, n = 0, art_cap = 0, P = 0, PL = 0, C = 1, ld = 0, mr = 0, pmax = 16, trace_cap = 0;
+    int count = 0, m = 0, n = 0, art_cap = 0, P = 0, C = 1, mloc = 0, cw = 0, tb = 0, ld = 0, trace_cap = 0;
     size_t smem = 0;
     int ctas_per_sm = 0;
     PrimeQ* pr = nullptr;
@@ -24,35 +25,35 @@ struct lps_batch {
     int *status = nullptr, *npiv = nullptr, *basis = nullptr, *trace = nullptr;
     signed char* sign = nullptr;
     uint32_t* digits = nullptr;
+    long long* timing = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     long long launches = 0;
     long long stuck_limit = -1;
+    int threads = 256;
 };
 
-static const size_t kBatchSmemMax = 227 * 1024 - 2048;     // opt-in maximum minus the kernel's static shared memory
+static const size_t kBatchSmemMax = 227 * 1024 - 64;       // opt-in maximum (the kernel has no static shared memory)
 
-static int batch_ld(int m, int n, int art_cap) { return (std::max(n + art_cap + 1, m + 2) + 3) / 4 * 4; }
-static int batch_mr(int m) { return (m + 1 + 3) / 4 * 4; }
+static int batch_ld(int m, int n, int art_cap) { return (n + art_cap + 1 + 3) / 4 * 4; }
+static int batch_mloc(int m, int C) { return (m + C - 1) / C; }
+static int batch_cw(int n, int art_cap, int C) { return std::max(1, (n + art_cap + C - 1) / C); }
 
 static size_t batch_smem(int m, int n, int art_cap, int P, int C) {
-    const int PL = (P + C - 1) / C;
-    return batch_layout(m, P, PL, batch_ld(m, n, art_cap), batch_mr(m)).total;
+    const int mloc = batch_mloc(m, C);
+    return batch_ctx_bytes() + batch_layout(m, P, C, mloc, batch_cw(n, art_cap, C), batch_ld(m, n, art_cap), std::max(mloc, C)).total;
 }
 
-// smallest cluster whose per-CTA share fits; then wider while each CTA would still hold >= 2 planes and more
-// than 48 KB of them (more threads per LP at the same number of resident LPs)
+// Cluster width.  A pivot is a chain of short latency-bound phases (reconstruct, decide, exchange) around one
+// update, so what counts is how many LPs are resident (shared memory decides: one LP needs P (m + C) ld words) and
+// how many threads walk each LP's rows.  Measured on B200 (tools/bench_batch.py, 64 x 128 LPs, 12 primes): the
+// narrowest cluster that fits wins (C = 2, 74 resident LPs, 512 threads per CTA: 117 k LPs/s; C = 4: 61 k; C = 8: 48 k).
 static int batch_pick_cluster(int m, int n, int art_cap, int P) {
-    int C = 0;
-    for (int c = 1; c <= kBMaxCluster; c *= 2)
-        if (batch_smem(m, n, art_cap, P, c) <= kBatchSmemMax) { C = c; break; }
-    if (!C) return 0;
-    while (C * 2 <= kBMaxCluster) {
-        const int PL = (P + C - 1) / C;
-        const size_t plane_bytes = (size_t)PL * (m + 1) * batch_ld(m, n, art_cap) * 4;
-        if (PL >= 4 && plane_bytes > 48 * 1024) C *= 2; else break;
+    for (int c = 1; c <= kBMaxCluster; c *= 2) {
+        if (c > 1 && batch_mloc(m, c) * (c - 1) >= m) break;   // a CTA without rows
+        if (batch_smem(m, n, art_cap, P, c) <= kBatchSmemMax) return c;
     }
-    return C;
+    return 0;
 }
 
 /* Shared memory one CTA needs for this shape with `cluster` CTAs per LP (0: the automatic choice);
@@ -71,7 +72,7 @@ static void batch_free(lps_batch* b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->pr); cudaFree(b->invtab); cudaFree(b->half); cudaFree(b->wmant); cudaFree(b->wexp);
     cudaFree(b->grids); cudaFree(b->status); cudaFree(b->npiv); cudaFree(b->basis); cudaFree(b->trace);
-    cudaFree(b->sign); cudaFree(b->digits);
+    cudaFree(b->sign); cudaFree(b->digits); cudaFree(b->timing);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
@@ -87,21 +88,28 @@ static void batch_free(lps_batch* b) {
         }                                                                                           \
     } while (0)
 
-template <int PMAX>
-static cudaError_t batch_prepare_kernel(size_t smem) {
-    return cudaFuncSetAttribute(k_bnb_nodes<PMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
+// one instantiation per (even) number of primes: the Garner loops are fully unrolled over P
+#define BATCH_DISPATCH(P_, EXPR)                     \
+    switch (P_) {                                    \
+        case 2: { constexpr int PP = 2; EXPR; } break;   \
+        case 4: { constexpr int PP = 4; EXPR; } break;   \
+        case 6: { constexpr int PP = 6; EXPR; } break;   \
+        case 8: { constexpr int PP = 8; EXPR; } break;   \
+        case 10: { constexpr int PP = 10; EXPR; } break; \
+        case 12: { constexpr int PP = 12; EXPR; } break; \
+        case 14: { constexpr int PP = 14; EXPR; } break; \
+        default: { constexpr int PP = 16; EXPR; } break; \
+    }
 
 extern "C" int lps_batch_create(int count, int m, int n, int art_cap, int nprimes, const uint32_t* primes, int cluster,
                                 int trace_cap, int device, void* stream, lps_batch** out) {
     if (!out) return fail(LPS_E_INVALID, "null out");
     *out = nullptr;
     if (count <= 0 || m <= 0 || n <= 0 || art_cap < 0 || art_cap > m) return fail(LPS_E_INVALID, "bad batch shape (count %d, m %d, n %d, artificial columns %d)", count, m, n, art_cap);
-    if (nprimes <= 0 || nprimes > 16 || !primes) return fail(LPS_E_INVALID, "the batched kernel takes 1..16 primes (got %d): solve larger LPs one at a time", nprimes);
+    if (nprimes < 2 || nprimes > kBMaxPrimes || (nprimes & 1) || !primes) return fail(LPS_E_INVALID, "the batched kernel takes an even number of primes, 2..%d (got %d): solve larger LPs one at a time", kBMaxPrimes, nprimes);
     for (int k = 0; k < nprimes; ++k) {
         if (!(primes[k] & 1u) || primes[k] < 3u || primes[k] >= (1u << 31)) return fail(LPS_E_INVALID, "prime %u is not an odd number below 2^31", primes[k]);
-        for (int j = 0; j < k; ++j)
-            if (primes[j] == primes[k]) return fail(LPS_E_INVALID, "prime %u listed twice", primes[k]);
+        if (k > 0 && primes[k] <= primes[k - 1]) return fail(LPS_E_INVALID, "the batched kernel takes its primes in ascending order");
     }
     if (cluster != 0 && cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) return fail(LPS_E_INVALID, "cluster must be 0 (auto), 1, 2, 4 or 8");
     const int C = cluster ? cluster : batch_pick_cluster(m, n, art_cap, nprimes);
@@ -118,10 +126,13 @@ extern "C" int lps_batch_create(int count, int m, int n, int art_cap, int nprime
     if (stream) b->stream = (cudaStream_t)stream;
     else { CUB(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); b->own_stream = true; }
     const int P = nprimes;
-    b->count = count; b->m = m; b->n = n; b->art_cap = art_cap; b->P = P; b->C = C; b->PL = (P + C - 1) / C;
-    b->ld = batch_ld(m, n, art_cap); b->mr = batch_mr(m); b->trace_cap = trace_cap;
-    b->pmax = P <= 8 ? 8 : 16;
+    b->count = count; b->m = m; b->n = n; b->art_cap = art_cap; b->P = P; b->C = C;
+    b->mloc = batch_mloc(m, C); b->cw = batch_cw(n, art_cap, C); b->tb = std::max(b->mloc, C);
+    b->ld = batch_ld(m, n, art_cap); b->trace_cap = trace_cap;
     b->smem = batch_smem(m, n, art_cap, P, C);
+    // one CTA per SM by shared memory: 16 warps; several CTAs per SM: 8 warps each (128 registers per thread)
+    b->threads = (b->smem + 1024 > (227 * 1024) / 2) ? 512 : 256;
+    if (const char* e = getenv("LPS_BATCH_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= 512 && t % 32 == 0) b->threads = t; }
 
     std::vector<PrimeQ> pr(P);
     for (int k = 0; k < P; ++k) pr[k] = make_prime(primes[k]);
@@ -171,11 +182,8 @@ extern "C" int lps_batch_create(int count, int m, int n, int art_cap, int nprime
     CUB(cudaEventCreate(&b->ev0));
     CUB(cudaEventCreate(&b->ev1));
 
-    cudaError_t e;
-    switch (b->pmax) {
-        case 8: e = batch_prepare_kernel<8>(b->smem); break;
-        default: e = batch_prepare_kernel<16>(b->smem); break;
-    }
+    cudaError_t e = cudaSuccess;
+    BATCH_DISPATCH(P, e = cudaFuncSetAttribute(k_bnb_nodes<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     CUB(e);
     CUB(cudaStreamSynchronize(b->stream));
     *out = b;
@@ -206,14 +214,14 @@ extern "C" int lps_batch_upload(lps_batch* b, const int32_t* grids) {
 extern "C" int lps_batch_run(lps_batch* b, long long max_pivots) {
     USEB(b);
     BatchParams a;
-    a.count = b->count; a.m = b->m; a.n = b->n; a.art_cap = b->art_cap; a.P = b->P; a.PL = b->PL; a.C = b->C;
-    a.ld = b->ld; a.mr = b->mr; a.max_pivots = max_pivots; a.stuck_limit = b->stuck_limit;
+    a.count = b->count; a.m = b->m; a.n = b->n; a.art_cap = b->art_cap; a.C = b->C; a.mloc = b->mloc; a.cw = b->cw;
+    a.ld = b->ld; a.tb = b->tb; a.max_pivots = max_pivots; a.stuck_limit = b->stuck_limit;
     a.pr = b->pr; a.invtab = b->invtab; a.half = b->half; a.wmant = b->wmant; a.wexp = b->wexp;
     a.grids = b->grids; a.status = b->status; a.npiv = b->npiv; a.basis = b->basis; a.sign = b->sign; a.digits = b->digits;
-    a.trace = b->trace; a.trace_cap = b->trace_cap;
+    a.trace = b->trace; a.trace_cap = b->trace_cap; a.timing = b->timing;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)b->count * b->C, 1, 1);
-    cfg.blockDim = dim3(kBThreads, 1, 1);
+    cfg.blockDim = dim3(b->threads, 1, 1);
     cfg.dynamicSmemBytes = b->smem;
     cfg.stream = b->stream;
     cudaLaunchAttribute attr[1];
@@ -222,11 +230,8 @@ extern "C" int lps_batch_run(lps_batch* b, long long max_pivots) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     CU(cudaEventRecord(b->ev0, b->stream));
-    cudaError_t e;
-    switch (b->pmax) {
-        case 8: e = cudaLaunchKernelEx(&cfg, k_bnb_nodes<8>, a); break;
-        default: e = cudaLaunchKernelEx(&cfg, k_bnb_nodes<16>, a); break;
-    }
+    cudaError_t e = cudaSuccess;
+    BATCH_DISPATCH(b->P, e = cudaLaunchKernelEx(&cfg, k_bnb_nodes<PP>, a));
     if (e != cudaSuccess) return fail(LPS_E_CUDA, "k_bnb_nodes launch failed: %s", cudaGetErrorString(e));
     CU(cudaEventRecord(b->ev1, b->stream));
     b->timed = true;
@@ -259,6 +264,22 @@ extern "C" int lps_batch_set_stuck_limit(lps_batch* b, long long limit) {
     return LPS_OK;
 }
 
+/* Profiling aid: per-LP cycle counts of the kernel's phases (CTA 0 of each cluster, 16 slots, see b_tick in
+ * lps_batch.cuh).  out == NULL switches the collection on for the following runs; otherwise the counts of the
+ * last run are copied to out[count][16]. */
+extern "C" int lps_batch_timing(lps_batch* b, long long* out) {
+    USEB(b);
+    if (!b->timing) {
+        CU(cudaMalloc(&b->timing, (size_t)b->count * 16 * sizeof(long long)));
+        CU(cudaMemsetAsync(b->timing, 0, (size_t)b->count * 16 * sizeof(long long), b->stream));
+    }
+    if (out) {
+        CU(cudaMemcpyAsync(out, b->timing, (size_t)b->count * 16 * sizeof(long long), cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+    }
+    return LPS_OK;
+}
+
 extern "C" int lps_batch_sync(lps_batch* b) {
     USEB(b);
     CU(cudaStreamSynchronize(b->stream));
@@ -267,16 +288,16 @@ extern "C" int lps_batch_sync(lps_batch* b) {
 
 /* Plan of this batch: CTAs per cluster, primes per CTA, dynamic shared memory per CTA, resident clusters
  * per device (occupancy query), CUDA-event time of the last run in ms (after a sync), launches so far. */
-extern "C" int lps_batch_info(lps_batch* b, int* cluster, int* primes_per_cta, size_t* smem_bytes, int* resident_clusters,
+extern "C" int lps_batch_info(lps_batch* b, int* cluster, int* rows_per_cta, size_t* smem_bytes, int* resident_clusters,
                               double* last_run_ms, long long* launches) {
     USEB(b);
     if (cluster) *cluster = b->C;
-    if (primes_per_cta) *primes_per_cta = b->PL;
+    if (rows_per_cta) *rows_per_cta = b->mloc;
     if (smem_bytes) *smem_bytes = b->smem;
     if (resident_clusters) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)b->count * b->C, 1, 1);
-        cfg.blockDim = dim3(kBThreads, 1, 1);
+        cfg.blockDim = dim3(b->threads, 1, 1);
         cfg.dynamicSmemBytes = b->smem;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -284,11 +305,8 @@ extern "C" int lps_batch_info(lps_batch* b, int* cluster, int* primes_per_cta, s
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         int nc = 0;
-        cudaError_t e;
-        switch (b->pmax) {
-            case 8: e = cudaOccupancyMaxActiveClusters(&nc, k_bnb_nodes<8>, &cfg); break;
-            default: e = cudaOccupancyMaxActiveClusters(&nc, k_bnb_nodes<16>, &cfg); break;
-        }
+        cudaError_t e = cudaSuccess;
+        BATCH_DISPATCH(b->P, e = cudaOccupancyMaxActiveClusters(&nc, k_bnb_nodes<PP>, &cfg));
         if (e != cudaSuccess) { cudaGetLastError(); nc = -1; }
         *resident_clusters = nc;
     }
