@@ -126,6 +126,56 @@ def run(pkg, c, A, b, max_pivots=None):
     return out
 
 
+def lp_via_reference(c, A, b):
+    """Node-LP solver for the B&B oracle: reference `Simplex(tab); solve()`, exceptions mapped to outcomes."""
+    tab = build(ref, c, A, b)
+    try:
+        sx = ref.Simplex(tab)
+    except ValueError as e:
+        if str(e).startswith("infeasible problem"):
+            return ("infeasible",)
+        raise
+    try:
+        sx.solve()
+    except AssertionError as e:
+        if "unbounded" in str(e):
+            return ("unbounded",)
+        raise
+    return ("optimal", sx.getObjValue(), dict(sx.getBFS()))
+
+
+def make_milp():
+    import random
+    from oracle import bnb_oracle as B
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_bnb_oracle import random_ip
+    out = []
+    cases = []
+    for seed in range(14):
+        rng = random.Random(500 + seed)
+        cases.append(random_ip(rng, rng.randint(3, 6), rng.randint(2, 5), pure=(seed % 2 == 0)))
+    # a knapsack with a known optimum and an infeasible program
+    cases.append(([("a", True, 0, 1), ("b", True, 0, 1), ("c", True, 0, 1), ("d", True, 0, 1)],
+                  [({"a": 5, "b": 7, "c": 4, "d": 3}, "<=", 14)], ({"a": 8, "b": 11, "c": 6, "d": 4}, 0, "max")))
+    cases.append(([("x", True, 0, 5), ("y", True, 0, 5)],
+                  [({"x": 2, "y": 2}, "==", 3)], ({"x": 1, "y": 1}, 0, "min")))
+    for variables, cons, obj in cases:
+        got = B.branch_and_bound(variables, cons, obj, solve_lp=lp_via_reference)
+        out.append({
+            "variables": [[n, i, None if lb is None else str(Fraction(lb)), None if ub is None else str(Fraction(ub))]
+                          for n, i, lb, ub in variables],
+            "constraints": [[{k: str(Fraction(v)) for k, v in c.items()}, comp, str(Fraction(rhs))] for c, comp, rhs in cons],
+            "objective": [{k: str(Fraction(v)) for k, v in obj[0].items()}, str(Fraction(obj[1])), obj[2]],
+            "status": got["status"],
+            "objective_value": None if got["objective"] is None else str(got["objective"]),
+            "values": {k: str(v) for k, v in got["values"].items()},
+            "nodes": got["nodes"], "lps": got["lps"],
+            "trace": [[d, s_, None if o is None else str(o)] for d, s_, o in got["trace"]],
+        })
+        print("milp", got["status"], got["objective"], got["nodes"], flush=True)
+    return out
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -193,8 +243,15 @@ def main():
             phase1.append(rec)
             print("phase1", m, n, seed, rec.get("ctor_error"), len(rec.get("phase1_pivots", [])), rec.get("objective"), flush=True)
 
+    # 6. MILP layer: the branch-and-bound driver of oracle/bnb_oracle.py with every node LP solved by the
+    #    UNMODIFIED reference Simplex (the reference itself has no MILP solver: its LinProg is an empty stub)
+    milp = make_milp()
+
+    only = os.environ.get("GOLDEN_ONLY")
     for name, obj in [("textbook", textbook), ("dense_exact", dense), ("dense_float", dense_f),
-                      ("special", special), ("phase1", phase1)]:
+                      ("special", special), ("phase1", phase1), ("milp", milp)]:
+        if only and name not in only.split(","):
+            continue
         with open(os.path.join(out_dir, name + ".json"), "w") as f:
             json.dump(obj, f, separators=(",", ":"))
             f.write("\n")
