@@ -192,6 +192,9 @@ int lps_exact_loop_state(lps_handle *h, int set, int *rule, long long *stuck, in
  * LPS_BAD_PRIME (solve that LP alone with another prime set), LPS_NEED_ARTIFICIALS. */
 typedef struct lps_batch lps_batch;
 size_t lps_batch_smem_bytes(int m, int n, int art_cap, int nprimes, int cluster);
+/* Sizing on the device (bookkeeping, no pivot arithmetic): the largest number of artificial columns any LP of
+ * the batch needs and log2 of a Hadamard bound on every minor of every LP (phase-1 objective included). */
+int lps_batch_plan(int count, int m, int n, const int32_t *grids, int device, int *art_cap, double *bound_bits);
 int lps_batch_create(int count, int m, int n, int art_cap, int nprimes, const uint32_t *primes, int cluster,
                      int trace_cap, int device, void *stream, lps_batch **out);
 int lps_batch_destroy(lps_batch *b);

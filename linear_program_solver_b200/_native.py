@@ -67,6 +67,7 @@ SIGNATURES = {
     "lps_exact_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     "lps_exact_loop_state": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_longlong), POINTER(c_int), POINTER(c_int)]),
     "lps_batch_smem_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "lps_batch_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_int, POINTER(c_int), POINTER(c_double)]),
     "lps_batch_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, POINTER(c_void_p)]),
     "lps_batch_destroy": (c_int, [c_void_p]),
     "lps_batch_upload": (c_int, [c_void_p, c_void_p]),

@@ -36,16 +36,18 @@ STATUS_NAME = {N.OPTIMAL: "optimal", N.UNBOUNDED: "unbounded", N.MAX_PIVOTS: "ma
 def missing_basic_rows(G: np.ndarray) -> np.ndarray:
     """[count, m] bool: rows that lack a basic column after the sign normalisation of simplex.py:43-45,
     i.e. the rows that get an artificial column (tableau.py:466-496 decides what a basic column is)."""
-    m = G.shape[1] - 1
-    n = G.shape[2] - 1
-    sign = np.where(G[:, :m, n] < 0, -1, 1).astype(G.dtype)
-    A = G[:, :m, :n] * sign[:, :, None]
-    nonzero = A != 0
-    basic = (G[:, m, :n] == 0) & (nonzero.sum(axis=1) == 1) & ((A == 1).sum(axis=1) == 1)
-    hit = nonzero.argmax(axis=1)                                     # row of the single nonzero
-    has = np.zeros((G.shape[0], m), dtype=bool)
-    b_idx, j_idx = np.nonzero(basic)
-    has[b_idx, hit[b_idx, j_idx]] = True
+    cnt, m, n = G.shape[0], G.shape[1] - 1, G.shape[2] - 1
+    body = G[:, :m, :n]
+    # candidates: zero cost and exactly one nonzero in the column; only those are looked at more closely
+    cand = (G[:, m, :n] == 0) & (np.count_nonzero(body, axis=1) == 1)
+    b_idx, j_idx = np.nonzero(cand)
+    cols = body[b_idx, :, j_idx]                                     # [candidates, m]
+    hit = np.abs(cols).argmax(axis=1)                                # row of the single nonzero
+    val = cols[np.arange(cols.shape[0]), hit]
+    sign = np.where(G[b_idx, hit, n] < 0, -1, 1)                     # the row is negated when b_i < 0
+    ok = val * sign == 1
+    has = np.zeros((cnt, m), dtype=bool)
+    has[b_idx[ok], hit[ok]] = True
     return ~has
 
 
@@ -53,18 +55,24 @@ def bound_bits(G: np.ndarray, missing: np.ndarray) -> int:
     """Bits of a Hadamard bound on every minor of every LP's extended matrix, the phase-1 objective
     (minus the sum of the rows that get an artificial, simplex.py:56-60) included."""
     m = G.shape[1] - 1
-    A = G.astype(np.float64)
-    phase1_obj = -(np.abs(A[:, :m, :]) * missing[:, :, None]).sum(axis=1)      # |.| bounds both row signs
-    obj = np.maximum(np.abs(A[:, m, :]), np.abs(phase1_obj))
+    A = np.abs(G).astype(np.float32) if np.abs(G).max(initial=0) < (1 << 20) else np.abs(G).astype(np.float64)
     body = A[:, :m, :]
-    row_sq = np.concatenate([(body * body).sum(axis=2), (obj * obj).sum(axis=1)[:, None]], axis=1)
-    col_sq = (body * body).sum(axis=1) + obj * obj
+    obj = A[:, m, :].astype(np.float64)
+    if missing.any():                                                # |phase-1 objective| <= sum of |rows| with an artificial
+        obj = np.maximum(obj, np.einsum("bij,bi->bj", body, missing.astype(body.dtype)).astype(np.float64))
+    row_sq = np.concatenate([np.einsum("bij,bij->bi", body, body).astype(np.float64), (obj * obj).sum(axis=1)[:, None]], axis=1)
+    col_sq = np.einsum("bij,bij->bj", body, body).astype(np.float64) + obj * obj
     row_sq = np.maximum(row_sq, 1.0)
     col_sq = np.maximum(col_sq, 1.0)
     order = min(row_sq.shape[1], col_sq.shape[1])
-    by_rows = np.log2(np.sort(row_sq, axis=1)[:, ::-1][:, :order]).sum(axis=1) / 2
-    by_cols = np.log2(np.sort(col_sq, axis=1)[:, ::-1][:, :order]).sum(axis=1) / 2
-    return int(math.ceil(float(np.minimum(by_rows, by_cols).max()))) + 3
+
+    def top_log_sum(sq):
+        if sq.shape[1] > order:
+            sq = -np.partition(-sq, order - 1, axis=1)[:, :order]
+        return np.log2(sq).sum(axis=1) / 2
+
+    bits = np.minimum(top_log_sum(row_sq), top_log_sum(col_sq)).max()
+    return int(math.ceil(float(bits) * (1 + 1e-6))) + 3             # float32 norms: a relative 1e-6 covers their rounding
 
 
 class BatchResult:
@@ -224,13 +232,22 @@ class BatchExactSolver:
         return self.download()
 
 
-def plan_batch(grids: np.ndarray, banned: Sequence[int] = ()):
-    """(art_cap, primes) for a batch of integer tableaux, or raises ValueError when the Hadamard bound
-    needs more primes than the batched kernel holds (solve those LPs one at a time)."""
-    G = np.ascontiguousarray(grids)
-    missing = missing_basic_rows(G)
-    art_cap = int(missing.sum(axis=1).max(initial=0))
-    bits = bound_bits(G, missing)
+def plan_batch(grids: np.ndarray, banned: Sequence[int] = (), device: Optional[int] = None, on_device: bool = True):
+    """(art_cap, primes, bound bits) for a batch of integer tableaux, or raises ValueError when the Hadamard bound
+    needs more primes than the batched kernel holds (solve those LPs one at a time).  The counting runs on
+    the device (`lps_batch_plan`); `on_device=False` uses the numpy statement of the same rule (tests compare them)."""
+    G = np.ascontiguousarray(grids, dtype=np.int32)
+    if on_device:
+        import torch
+        L = N.lib()
+        dev = int(torch.cuda.current_device() if device is None else device)
+        k, b = c_int(0), c_double(0.0)
+        N.check(L.lps_batch_plan(G.shape[0], G.shape[1] - 1, G.shape[2] - 1, G.ctypes.data, dev, byref(k), byref(b)))
+        art_cap, bits = k.value, int(math.ceil(b.value * (1 + 1e-9))) + 3
+    else:
+        missing = missing_basic_rows(G)
+        art_cap = int(missing.sum(axis=1).max(initial=0))
+        bits = bound_bits(G, missing)
     primes = primes_for_bits(bits, banned)
     if len(primes) & 1:                      # the kernel is instantiated for even prime counts
         primes = primes_below_2_31(len(primes) + 1, banned)
@@ -243,13 +260,14 @@ def solve_batch(grids, trace_cap: int = 0, cluster: int = 0, device: Optional[in
                 stuck_limit: int = -1) -> BatchResult:
     """`Simplex(tab); solve()` of the reference for every integer tableau of `grids`
     ([count, m+1, n+1], device layout: row m = costs, column n = rhs, cell (m, n) = minus the objective)."""
-    G = np.ascontiguousarray(np.asarray(grids), dtype=np.int64)
+    G = np.asarray(grids)
     if G.ndim != 3:
         raise ValueError("grids must be [count, m+1, n+1]")
-    if np.abs(G).max(initial=0) >= 2 ** 31:
-        raise ValueError("batched tableaux take 32-bit integer coefficients")
+    if G.dtype != np.int32:
+        if G.size and (G.max() >= 2 ** 31 or G.min() < -(2 ** 31)):
+            raise ValueError("batched tableaux take 32-bit integer coefficients")
     G32 = np.ascontiguousarray(G, dtype=np.int32)
-    art_cap, primes, _ = plan_batch(G32)
+    art_cap, primes, _ = plan_batch(G32, device=device)
     solver = BatchExactSolver(G.shape[0], G.shape[1] - 1, G.shape[2] - 1, primes, art_cap=art_cap, cluster=cluster,
                               trace_cap=trace_cap, device=device)
     if max_pivots < 0:                       # Bland's rule terminates; the cap only bounds a run gone wrong

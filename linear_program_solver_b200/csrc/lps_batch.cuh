@@ -1143,4 +1143,85 @@ __global__ void __launch_bounds__(kBMaxThreads, LPS_BATCH_MINB) k_bnb_nodes(Batc
     b_csync();                                                // nobody leaves while a peer may still write into it
 }
 
+// ------------------------------------------------------------------------------------------------
+// sizing of a batch on the device (one CTA per LP): how many rows get an artificial column (same rule as the
+// set-up of k_bnb_nodes) and log2 of a Hadamard bound on every minor of the LP's extended matrix -- the
+// smaller of the product of all row norms and the product of the min(m+1, n+1) largest column norms, each norm
+// at least 1, the objective row taken as max(|costs|, sum of |rows that get an artificial|) so that it covers
+// the phase-1 objective too.  Pure bookkeeping: no pivot arithmetic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_batch_plan(const int32_t* grids, int m, int n, int* out_k, double* out_bits) {
+    extern __shared__ __align__(16) unsigned char plan_smem[];
+    int* basis = reinterpret_cast<int*>(plan_smem);                  // m
+    int* rowsign = basis + m;                                        // m
+    double* colsq = reinterpret_cast<double*>(rowsign + m + ((2 * m) & 1));   // n + 1
+    double* rowlog = colsq + (n + 1);                                // m + 1 partial sums
+    __shared__ double s_sum[2];
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int32_t* G = grids + (size_t)blockIdx.x * (m + 1) * (n + 1);
+    for (int i = tid; i < m; i += T) { basis[i] = INT_MAX; rowsign[i] = (G[(size_t)i * (n + 1) + n] < 0) ? -1 : 1; }
+    if (tid < 2) s_sum[tid] = 0.0;
+    __syncthreads();
+    for (int j = tid; j < n; j += T) {
+        if (G[(size_t)m * (n + 1) + j] != 0) continue;
+        int hit = -1;
+        bool clean = true;
+        for (int i = 0; clean && i < m; ++i) {
+            const int v = G[(size_t)i * (n + 1) + j] * rowsign[i];
+            if (v == 0) continue;
+            if (v == 1 && hit == -1) hit = i; else clean = false;
+        }
+        if (clean && hit != -1) atomicMin(&basis[hit], j);
+    }
+    __syncthreads();
+    // column norms (objective entry: max of the cost and the phase-1 cost bound) and row norms
+    for (int j = tid; j <= n; j += T) {
+        double sq = 0.0, art = 0.0;
+        for (int i = 0; i < m; ++i) {
+            const double v = fabs((double)G[(size_t)i * (n + 1) + j]);
+            sq += v * v;
+            if (basis[i] == INT_MAX) art += v;
+        }
+        const double o = fmax(fabs((double)G[(size_t)m * (n + 1) + j]), art);
+        colsq[j] = fmax(sq + o * o, 1.0);
+        rowlog[0] = 0.0;
+        atomicAdd(&s_sum[1], o * o);                               // squared norm of the objective row
+    }
+    __syncthreads();
+    double part = 0.0;
+    int k_art = 0;
+    for (int i = tid; i < m; i += T) {
+        double sq = 0.0;
+        for (int j = 0; j <= n; ++j) { const double v = (double)G[(size_t)i * (n + 1) + j]; sq += v * v; }
+        part += log2(fmax(sq, 1.0));
+        k_art += basis[i] == INT_MAX;
+    }
+    // rows: all m + 1 of them when m + 1 <= n + 1, else the n + 1 largest -- the second case (more rows than
+    // columns) is bounded by the column product alone, so the row product is only used in the first
+    atomicAdd(&s_sum[0], part);
+    __syncthreads();
+    const int order = min(m + 1, n + 1);
+    double by_cols = 0.0;
+    for (int j = tid; j <= n; j += T) {                              // the `order` largest column norms (rank by counting)
+        const double v = colsq[j];
+        int rank = 0;
+        for (int i = 0; i <= n; ++i) rank += (colsq[i] > v) || (colsq[i] == v && i < j);
+        if (rank < order) by_cols += log2(v);
+    }
+    __shared__ double s_cols;
+    __shared__ int s_k;
+    if (tid == 0) { s_cols = 0.0; s_k = 0; }
+    __syncthreads();
+    atomicAdd(&s_cols, by_cols);
+    atomicAdd(&s_k, k_art);
+    __syncthreads();
+    if (tid == 0) {
+        const double by_rows = (s_sum[0] + log2(fmax(s_sum[1], 1.0))) / 2;
+        double bits = s_cols / 2;
+        if (m + 1 <= n + 1) bits = fmin(bits, by_rows);
+        out_bits[blockIdx.x] = bits;
+        out_k[blockIdx.x] = s_k;
+    }
+}
+
 }  // namespace lps

@@ -190,6 +190,40 @@ extern "C" int lps_batch_create(int count, int m, int n, int art_cap, int nprime
     return LPS_OK;
 }
 
+/* Sizing of a batch on the device (bookkeeping only, see k_batch_plan): the largest number of artificial columns
+ * any LP needs and the bits of a Hadamard bound that covers every LP, from host grids [count][(m+1)][(n+1)]. */
+extern "C" int lps_batch_plan(int count, int m, int n, const int32_t* grids, int device, int* art_cap, double* bound_bits) {
+    if (count <= 0 || m <= 0 || n <= 0 || !grids || !art_cap || !bound_bits) return fail(LPS_E_INVALID, "bad arguments");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(LPS_E_INVALID, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    const size_t bytes = (size_t)count * (m + 1) * (n + 1) * sizeof(int32_t);
+    const size_t smem = (size_t)(2 * m + 2) * sizeof(int) + (size_t)(n + m + 4) * sizeof(double);
+    if (smem > 200 * 1024) return fail(LPS_E_INVALID, "LP too large for the batch planner");
+    int32_t* d_g = nullptr;
+    int* d_k = nullptr;
+    double* d_b = nullptr;
+    cudaError_t e = cudaMalloc(&d_g, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_k, (size_t)count * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_b, (size_t)count * sizeof(double));
+    std::vector<int> hk(count);
+    std::vector<double> hb(count);
+    if (e == cudaSuccess) e = cudaMemcpy(d_g, grids, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(k_batch_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        k_batch_plan<<<count, 256, smem>>>(d_g, m, n, d_k, d_b);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(hk.data(), d_k, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(hb.data(), d_b, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_g); cudaFree(d_k); cudaFree(d_b);
+    if (e != cudaSuccess) return fail(LPS_E_CUDA, "batch planning failed: %s", cudaGetErrorString(e));
+    *art_cap = *std::max_element(hk.begin(), hk.end());
+    *bound_bits = *std::max_element(hb.begin(), hb.end());
+    return LPS_OK;
+}
+
 extern "C" int lps_batch_destroy(lps_batch* b) {
     batch_free(b);
     return LPS_OK;

@@ -203,7 +203,7 @@ class LinProg:
     def _solve_nodes(forms: Sequence[StandardForm], device=None, stats=None):
         """`Simplex(tab); solve()` for every lowered node: [(status, tableau objective, bfs)], batched by shape."""
         from . import _native as N
-        from .batch import plan_batch, solve_batch
+        from .batch import solve_batch
         out: List[Optional[tuple]] = [None] * len(forms)
         by_shape: Dict[Tuple[int, int], List[int]] = {}
         for idx, f in enumerate(forms):
@@ -215,7 +215,6 @@ class LinProg:
             if small:
                 g32 = np.ascontiguousarray(grids.astype(np.int64), dtype=np.int32)
                 try:
-                    plan_batch(g32)
                     res = solve_batch(g32, device=device)
                 except ValueError:
                     res = None                                       # too many primes / too large for shared memory

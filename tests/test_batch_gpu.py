@@ -224,3 +224,17 @@ def test_c5_batch_of_64x128_nodes():
             assert sum(A[i][j] * x[j] for j in range(2 * m)) == b[i]
         assert sum(c[j] * x[j] for j in range(2 * m)) == res.objective(k)
         assert len(res.pivots(k)) == int(res.npiv[k, 2])
+
+
+def test_device_planner_agrees_with_the_numpy_statement():
+    """`lps_batch_plan` (artificial columns to reserve, Hadamard bound) against batch.missing_basic_rows / bound_bits."""
+    from linear_program_solver_b200.batch import plan_batch
+    rng = random.Random(5)
+    dense = np.stack([_grid(*problems.dense_lp(20, seed)) for seed in range(40)]).astype(np.int32)
+    eq = np.stack([_grid(*problems.equality_lp(8, 14, seed)) for seed in range(40)]).astype(np.int32)
+    mixed = np.stack([_grid(*_random_lp(rng, 6, 6, False)) for _ in range(64)]).astype(np.int32)
+    for grids in (dense, eq, mixed):
+        k1, p1, b1 = plan_batch(grids, on_device=True)
+        k2, p2, b2 = plan_batch(grids, on_device=False)
+        assert k1 == k2
+        assert abs(b1 - b2) <= 1 and abs(len(p1) - len(p2)) <= 2
