@@ -210,7 +210,7 @@ def run_ours(a):
 
     m, n, B = a.m, 2 * a.m, a.pivots_per_step
     row0, m_loc = shard_rows(m, rank, world)
-    solver = ShardedF64Solver(m, n, rank, world, device=local)
+    solver = ShardedF64Solver(m, n, rank, world, device=local, exchange=a.exchange)
     eng = solver.eng
     eng.fill_dense(a.seed, 1, 9)
     basis = np.arange(m, 2 * m, dtype=np.int32)
@@ -302,6 +302,9 @@ def run_ours(a):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C4 fp64 {m}x{n} dense tableau, seed {a.seed}", "m": m, "n": n,
                        "pivots_per_step": B, "sharding": f"rows/{world}", "rows_per_gpu": m_loc,
+                       "exchange": ("none (one rank)" if world == 1 else
+                                    "peer stores over NVLink inside the pivot kernels" if a.exchange == "p2p" else
+                                    "one NCCL all-gather per pivot"),
                        "l2": "tableau (17.2 GB total) is larger than L2; no flush needed",
                        "status_after": int(status), "pivots_timed": int(pivots)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -334,6 +337,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
+                    help="N > 1: how the ranks exchange the leaving-row candidates and the pivot row")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

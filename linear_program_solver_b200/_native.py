@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liblps_b200.so")
 
 OK, OPTIMAL, UNBOUNDED, ZERO_PIVOT, MAX_PIVOTS, BAD_PRIME, STALLED = 0, 1, 2, 3, 4, 5, 6
 INFEASIBLE, REDUNDANT_ROW, NEED_ARTIFICIALS = 7, 8, 9
-E_INVALID, E_CUDA, E_NOMEM, E_STATE = -1, -2, -3, -4
+E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_PEER = -1, -2, -3, -4, -5
 RULE_DANTZIG, RULE_BLAND = 0, 1
 
 
@@ -57,6 +57,9 @@ SIGNATURES = {
     "lps_solve_begin": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong]),
     "lps_step_select": (c_int, [c_void_p]),
     "lps_step_update": (c_int, [c_void_p]),
+    "lps_step_exchange": (c_int, [c_void_p]),
+    "lps_p2p_export": (c_int, [c_void_p, c_void_p]),
+    "lps_p2p_attach": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_void_p]),
     "lps_solve_poll": (c_int, [c_void_p, POINTER(c_int), POINTER(c_longlong)]),
     "lps_solve_end": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, POINTER(c_longlong)]),
     "lps_exact_ld": (c_size_t, [c_int]),

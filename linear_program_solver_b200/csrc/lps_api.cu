@@ -95,6 +95,14 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
     CU(cudaMemsetAsync(h->cand_send, 0, h->cand_stride, h->stream));
     h->cand_all = h->cand_send;
     h->own_cand = true;
+    {
+        const size_t xb = sizeof(XchgBlock) + h->ld * sizeof(double);
+        CU(cudaMalloc(&h->xchg, xb));
+        CU(cudaMemsetAsync(h->xchg, 0, xb, h->stream));
+        CU(cudaMalloc(&h->d_peers, kMaxRanks * sizeof(XchgBlock*)));
+        CU(cudaMemcpyAsync(h->d_peers, &h->xchg, sizeof(XchgBlock*), cudaMemcpyHostToDevice, h->stream));
+        h->bcast_blocks = (int)std::max<size_t>(1, std::min<size_t>((h->ld + kThreads - 1) / kThreads, 148));
+    }
     const int maxchunks = (int)((h->ld + kNarrowChunk - 1) / kNarrowChunk);
     CU(cudaMalloc(&h->pd_val, maxchunks * sizeof(double)));
     CU(cudaMalloc(&h->pd_idx, maxchunks * sizeof(int)));
@@ -125,6 +133,7 @@ extern "C" int lps_set_shard(lps_handle* h, long long row0, long long m_total, i
         h->cand_send = (unsigned char*)cand_send;
         h->cand_all = (unsigned char*)cand_all;
     }
+    h->use_xchg = false;                // candidate slots + the caller's all-gather
     CU(cudaFree(h->basis));
     CU(cudaMalloc(&h->basis, (size_t)m_total * sizeof(int)));
     CU(cudaMemsetAsync(h->basis, 0xff, (size_t)m_total * sizeof(int), h->stream));
@@ -140,6 +149,8 @@ extern "C" int lps_destroy(lps_handle* h) {
     if (h->own_T) cudaFree(h->T);
     cudaFree(h->ucol);
     if (h->own_cand) cudaFree(h->cand_send);
+    for (void* p : h->ipc_open) cudaIpcCloseMemHandle(p);
+    cudaFree(h->xchg); cudaFree(h->d_peers);
     cudaFree(h->pd_val); cudaFree(h->pd_idx); cudaFree(h->pb_idx);
     cudaFree(h->sel_blk); cudaFree(h->st); cudaFreeHost(h->st_host);
     cudaFree(h->basis); cudaFree(h->marks); cudaFree(h->trace); cudaFree(h->scratch_i);
@@ -222,15 +233,26 @@ static int launch_select(lps_handle* h) {
     SelectArgs a;
     a.g = grid_of(h); a.pp = partials_of(h); a.nchunks = h->nchunks; a.st = h->st; a.ucol = h->ucol;
     a.blk = h->sel_blk; a.cand = (CandHeader*)h->cand_send;
+    a.peers = h->use_xchg ? h->d_peers : nullptr; a.rank = h->rank; a.nranks = h->nranks;
     k_select_f64<<<h->sel_blocks, kThreads, 0, h->stream>>>(a);
     h->launches_all++;
     CU(cudaGetLastError());
     return LPS_OK;
 }
-static int launch_update(lps_handle* h, int commit) {
+static int launch_bcast(lps_handle* h, bool force = false) {
+    if (!h->use_xchg && !force) return LPS_OK;       // candidate-slot exchange: the caller all-gathers the candidates
+    BcastArgs a;
+    a.g = grid_of(h); a.st = h->st; a.xchg = h->xchg; a.peers = h->d_peers; a.rank = h->rank; a.nranks = h->nranks;
+    k_bcast_f64<<<h->bcast_blocks, kThreads, 0, h->stream>>>(a);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+static int launch_update(lps_handle* h, int commit, bool force_xchg = false) {
     UpdateArgs a;
     a.g = grid_of(h); a.pp = partials_of(h); a.st = h->st; a.ucol = h->ucol;
     a.cand_all = h->cand_all; a.cand_stride = h->cand_stride; a.nranks = h->nranks;
+    a.xchg = (h->use_xchg || force_xchg) ? h->xchg : nullptr;
     a.rows_per_cta = h->rows_per_cta; a.basis = h->basis; a.marks = h->use_marks ? h->marks : nullptr; a.trace = h->trace; a.trace_cap = h->trace_cap;
     a.commit = commit;
     dim3 grid(h->nchunks, (h->m + 1 + h->rows_per_cta - 1) / h->rows_per_cta);
@@ -268,14 +290,16 @@ extern "C" int lps_pivot(lps_handle* h, int r, int c) {
     if (h->mode == 1) return lpsx_pivot(h, r, c);
     if (h->nranks != 1) return fail(LPS_E_STATE, "explicit pivots are not supported on a sharded handle");
     if (r < 0 || r >= h->m || c < 0 || c >= h->n) return fail(LPS_E_INVALID, "pivot (%d,%d) out of range", r, c);
+    TRY(read_state(h));
     SolveState s{};
-    s.status = LPS_OK; s.max_pivots = -1;
+    s.status = LPS_OK; s.max_pivots = -1; s.xseq = h->st_host->xseq;
     TRY(write_state(h, s));
     const int blocks = std::max(1, std::min((int)((std::max((size_t)h->m + 1, h->ld) + kThreads - 1) / kThreads), 148 * 2));
-    k_forced_f64<<<blocks, kThreads, 0, h->stream>>>(grid_of(h), h->st, h->ucol, (CandHeader*)h->cand_send, r, c);
+    k_forced_f64<<<blocks, kThreads, 0, h->stream>>>(grid_of(h), h->st, h->ucol, h->d_peers, r, c);
     h->launches_all++;
     CU(cudaGetLastError());
-    TRY(launch_update(h, 0));
+    TRY(launch_bcast(h, true));                      // an explicit pivot always goes through the exchange block
+    TRY(launch_update(h, 0, true));
     TRY(read_state(h));
     const int st = h->st_host->status;
     return st == LPS_ZERO_PIVOT ? LPS_ZERO_PIVOT : LPS_OK;
@@ -307,9 +331,10 @@ extern "C" int lps_find_pivot(lps_handle* h, int rule, int* r, int* c) {
     if (!r || !c || (rule != LPS_RULE_DANTZIG && rule != LPS_RULE_BLAND)) return fail(LPS_E_INVALID, "bad arguments");
     if (h->mode == 1) return lpsx_find_pivot(h, rule, r, c);
     if (h->nranks != 1) return fail(LPS_E_STATE, "find_pivot on a sharded handle: use the stepping calls");
+    TRY(read_state(h));
     SolveState s{};
     s.status = LPS_OK; s.rule = rule; s.max_pivots = -1; s.dry_run = 1;
-    s.stuck = 0; s.last_r = -1; s.last_c = -1;
+    s.stuck = 0; s.last_r = -1; s.last_c = -1; s.xseq = h->st_host->xseq;
     TRY(write_state(h, s));
     TRY(launch_price(h));
     TRY(launch_select(h));
@@ -381,9 +406,11 @@ extern "C" int lps_solve_begin(lps_handle* h, long long max_pivots, const int* b
     double zcell = 0.0;
     CU(cudaMemcpyAsync(&zcell, h->T + (size_t)h->m * h->ld + h->n, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    TRY(read_state(h));
     SolveState s{};
     s.status = LPS_OK; s.rule = LPS_RULE_DANTZIG; s.stuck = 0; s.z_entry_cell = zcell; s.npiv = 0;
     s.max_pivots = max_pivots; s.pending_zcheck = 0; s.ticket = 0; s.dry_run = 0; s.last_r = -1; s.last_c = -1;
+    s.xseq = h->st_host->xseq;
     TRY(write_state(h, s));
     TRY(launch_price(h));
     h->solving = true;
@@ -394,6 +421,12 @@ extern "C" int lps_step_select(lps_handle* h) {
     NEED_MODE(h, 0);
     if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
     return launch_select(h);
+}
+extern "C" int lps_step_exchange(lps_handle* h) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
+    return launch_bcast(h);
 }
 extern "C" int lps_step_update(lps_handle* h) {
     USE(h);
@@ -443,6 +476,7 @@ extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* m
         const long long now = std::min(burst, room);
         for (long long k = 0; k < now; ++k) {
             TRY(launch_select(h));
+            TRY(launch_bcast(h));
             TRY(launch_update(h, 1));
         }
         enqueued += now;
@@ -451,6 +485,47 @@ extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* m
         if (h->st_host->status != LPS_OK) break;
     }
     return lps_solve_end(h, basis, marks, trace, trace_cap, npiv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// peer-store exchange over CUDA IPC
+// ------------------------------------------------------------------------------------------------
+extern "C" int lps_p2p_export(lps_handle* h, unsigned char* ipc_handle64) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (!ipc_handle64) return fail(LPS_E_INVALID, "null handle buffer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t ih;
+    CU(cudaIpcGetMemHandle(&ih, h->xchg));
+    memcpy(ipc_handle64, &ih, 64);
+    return LPS_OK;
+}
+
+extern "C" int lps_p2p_attach(lps_handle* h, long long row0, long long m_total, int rank, int nranks, const unsigned char* ipc_handles) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(LPS_E_INVALID, "bad rank %d of %d", rank, nranks);
+    if (row0 < 0 || row0 + h->m > m_total) return fail(LPS_E_INVALID, "rows [%lld,%lld) outside 0..%lld", row0, row0 + h->m, m_total);
+    if (nranks > 1 && !ipc_handles) return fail(LPS_E_INVALID, "null IPC handles");
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<XchgBlock*> peers(nranks, nullptr);
+    for (int k = 0; k < nranks; ++k) {
+        if (k == rank) { peers[k] = h->xchg; continue; }
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, ipc_handles + (size_t)k * 64, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(LPS_E_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", k, cudaGetErrorString(e));
+        h->ipc_open.push_back(p);
+        peers[k] = (XchgBlock*)p;
+    }
+    CU(cudaMemcpy(h->d_peers, peers.data(), (size_t)nranks * sizeof(XchgBlock*), cudaMemcpyHostToDevice));
+    h->row0 = row0; h->m_total = m_total; h->rank = rank; h->nranks = nranks;
+    h->use_xchg = (nranks > 1);          // one rank: k_select writes the normalised row itself, no exchange launch
+    CU(cudaFree(h->basis));
+    CU(cudaMalloc(&h->basis, (size_t)m_total * sizeof(int)));
+    CU(cudaMemsetAsync(h->basis, 0xff, (size_t)m_total * sizeof(int), h->stream));
+    return LPS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -35,6 +35,50 @@ struct alignas(16) CandHeader {
 };
 static_assert(sizeof(CandHeader) == 64, "candidate header must stay 64 bytes");
 
+// Exchange block: one per rank, in memory every peer GPU can write (cudaMalloc + CUDA IPC over NVLink).  Per pivot
+//   1. every rank writes the 64-byte header of its best leaving row into slot `rank` of EVERY rank's block and
+//      then releases hdr_seq[rank] = pivot sequence number;
+//   2. the rank that owns the winning row normalises it and writes it into EVERY rank's vrow, then releases
+//      row_seq = sequence number;
+// so the argmin "all-reduce" and the pivot-row "broadcast" are plain peer stores issued by the pivot kernels
+// themselves -- no collective call, no host step.  Headers are double buffered by sequence parity (a rank can be at
+// most one pivot ahead of a peer), vrow is single buffered (it is rewritten only after every rank has published
+// the next header, i.e. finished the previous update).
+struct XchgBlock {
+    CandHeader hdr[2][kMaxRanks];
+    unsigned long long hdr_seq[kMaxRanks];
+    unsigned long long row_seq;
+    unsigned long long pad[15];
+    // followed by vrow: ld doubles (128-byte aligned)
+};
+static_assert(sizeof(XchgBlock) % 128 == 0, "vrow must stay 128-byte aligned");
+__host__ __device__ __forceinline__ double* xchg_vrow(XchgBlock* x) { return reinterpret_cast<double*>(x + 1); }
+__host__ __device__ __forceinline__ const double* xchg_vrow(const XchgBlock* x) { return reinterpret_cast<const double*>(x + 1); }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *p >= want; false after ten seconds (a peer died or never enqueued this pivot: do not hang the GPU)
+__device__ __forceinline__ bool wait_seq(const unsigned long long* p, unsigned long long want) {
+    if (ld_acquire_sys(p) >= want) return true;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(p) < want) {
+        if (global_ns() - t0 > 10000000000ull) return false;
+        __nanosleep(32);
+    }
+    return true;
+}
+
 struct SolveState {
     int status;              // LPS_OK while running
     int rule;                // committed rule (Dantzig until the stuck counter trips)
@@ -46,7 +90,8 @@ struct SolveState {
     unsigned int ticket;     // last-block election of k_select
     int dry_run;             // find_pivot: select only, nothing is committed
     int last_r, last_c;      // last selected / committed pivot (global row)
-    int pad;
+    unsigned int ticket2;    // last-block election of k_bcast
+    unsigned long long xseq; // exchange rounds published so far (k_select / k_forced bump it, the later kernels read it)
 };
 
 struct F64Grid {
@@ -103,8 +148,24 @@ struct SelectArgs {
     SolveState* st;
     double* ucol;            // m+1 (+pad): column c of the local grid, gathered here for the update
     ArgMinF64* blk;          // gridDim.x per-block ratio partials
-    CandHeader* cand;        // this rank's candidate slot (header + ld doubles)
+    CandHeader* cand;        // this rank's candidate slot (header + ld doubles); legacy all-gather exchange
+    XchgBlock* const* peers; // peer-store exchange: every rank's exchange block (NULL: legacy exchange)
+    int rank, nranks;
 };
+
+// header of this rank's candidate into slot `rank` of every rank's exchange block, then the sequence flag
+__device__ __forceinline__ void publish_header(XchgBlock* const* peers, int rank, int nranks, const CandHeader& h,
+                                               unsigned long long seq) {
+    if ((int)threadIdx.x < nranks) {
+        XchgBlock* pb = peers[threadIdx.x];
+        const int4* src = reinterpret_cast<const int4*>(&h);
+        int4* dst = reinterpret_cast<int4*>(&pb->hdr[seq & 1][rank]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = src[q];
+        __threadfence_system();
+        st_release_sys(&pb->hdr_seq[rank], seq);
+    }
+}
 
 __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
     __shared__ ArgMinF64 s_arg[32];
@@ -174,6 +235,23 @@ __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
     }
     best = block_argmin(best, s_arg);
     const int r = best.idx;
+    if (a.peers) {                                             // peer-store exchange: 64-byte header only
+        if (st->dry_run) {
+            if (threadIdx.x == 0) { st->ticket = 0; st->last_r = (r == INT_MAX) ? -1 : (int)(g.row0 + r); st->last_c = c; }
+            return;
+        }
+        CandHeader h{};
+        h.ratio = best.key; h.row = (r == INT_MAX) ? -1 : g.row0 + r; h.c = c; h.rule = rule; h.stuck = stuck;
+        const unsigned long long seq = st->xseq + 1;
+        publish_header(a.peers, a.rank, a.nranks, h, seq);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            st->ticket = 0;
+            a.ucol[g.m] = g.T[(size_t)g.m * g.ld + c];
+            st->xseq = seq;
+        }
+        return;
+    }
     double* vrow = reinterpret_cast<double*>(a.cand + 1);
     if (threadIdx.x == 0) {
         st->ticket = 0;
@@ -193,25 +271,91 @@ __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
 }
 
 // Explicit pivot (Tableau.pivot(r,c)): gather column c and build the candidate for a caller-chosen (r,c).
-__global__ void __launch_bounds__(kThreads) k_forced_f64(F64Grid g, SolveState* st, double* ucol, CandHeader* cand, int r, int c) {
+__global__ void __launch_bounds__(kThreads) k_forced_f64(F64Grid g, SolveState* st, double* ucol, XchgBlock* const* peers, int r, int c) {
     const double p = g.T[(size_t)r * g.ld + c];
     if (p == 0.0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) st->status = LPS_ZERO_PIVOT;
         return;
     }
     for (int i = blockIdx.x * kThreads + threadIdx.x; i <= g.m; i += gridDim.x * kThreads) ucol[i] = g.T[(size_t)i * g.ld + c];
-    double* vrow = reinterpret_cast<double*>(cand + 1);
-    const double* src = g.T + (size_t)r * g.ld;
-    const double inv = 1.0 / p;
-    for (int j = blockIdx.x * kThreads + threadIdx.x; j < (int)g.ld; j += gridDim.x * kThreads)
-        vrow[j] = (inv == 1.0) ? src[j] : src[j] * inv;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        cand->ratio = 0.0;
-        cand->row = g.row0 + r;
-        cand->c = c;
-        cand->rule = 2;
-        cand->stuck = st->stuck;
+    if (blockIdx.x == 0) {
+        CandHeader h{};
+        h.ratio = 0.0; h.row = g.row0 + r; h.c = c; h.rule = 2; h.stuck = st->stuck;
+        const unsigned long long seq = st->xseq + 1;
+        publish_header(peers, 0, 1, h, seq);
+        __syncthreads();
+        if (threadIdx.x == 0) st->xseq = seq;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exchange: wait for every rank's header, pick the global leaving row (lowest ratio, then lowest global row:
+// simplex.py:277); the owner normalises that row (row r times the reciprocal of the pivot, tableau.py:262-267)
+// and stores it into EVERY rank's exchange block over NVLink, the others wait until it has arrived.  When this
+// kernel ends on a rank, that rank holds everything its update needs.
+// ------------------------------------------------------------------------------------------------
+struct BcastArgs {
+    F64Grid g;
+    SolveState* st;
+    XchgBlock* xchg;         // this rank's block
+    XchgBlock* const* peers; // every rank's block
+    int rank, nranks;
+};
+
+__device__ __forceinline__ int pick_winner(const XchgBlock* x, int par, int nranks) {
+    int w = -1;
+    double w_ratio = 0.0;
+    long long w_row = -1;
+    for (int k = 0; k < nranks; ++k) {
+        const CandHeader* h = &x->hdr[par][k];
+        const long long row = h->row;
+        if (row < 0) continue;
+        const double ratio = h->ratio;
+        if (w < 0 || ratio < w_ratio || (ratio == w_ratio && row < w_row)) { w = k; w_ratio = ratio; w_row = row; }
+    }
+    return w;
+}
+
+__global__ void __launch_bounds__(kThreads) k_bcast_f64(BcastArgs a) {
+    __shared__ int s_w, s_fail, s_last;
+    SolveState* st = a.st;
+    const F64Grid& g = a.g;
+    if (st->status != LPS_OK) return;
+    const unsigned long long seq = st->xseq;
+    const int par = (int)(seq & 1);
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        for (int k = 0; k < a.nranks; ++k) ok &= wait_seq(&a.xchg->hdr_seq[k], seq) ? 1 : 0;
+        s_fail = !ok;
+        s_w = ok ? pick_winner(a.xchg, par, a.nranks) : -1;
+    }
+    __syncthreads();
+    if (s_fail) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->status = LPS_E_PEER;
+        return;
+    }
+    const int w = s_w;
+    if (w < 0) return;                                         // no row with a_ic > 0 anywhere: k_update reports unbounded
+    if (w != a.rank) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && !wait_seq(&a.xchg->row_seq, seq)) st->status = LPS_E_PEER;
+        return;
+    }
+    const CandHeader* hw = &a.xchg->hdr[par][w];
+    const int c = hw->c;
+    const double* src = g.T + (size_t)(hw->row - g.row0) * g.ld;
+    const double inv = 1.0 / src[c];
+    for (int j = blockIdx.x * kThreads + threadIdx.x; j < (int)g.ld; j += gridDim.x * kThreads) {
+        const double v = (inv == 1.0) ? src[j] : src[j] * inv;
+        for (int k = 0; k < a.nranks; ++k) xchg_vrow(a.peers[k])[j] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket2, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if ((int)threadIdx.x < a.nranks) st_release_sys(&a.peers[threadIdx.x]->row_seq, seq);
+    if (threadIdx.x == 0) st->ticket2 = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -222,8 +366,9 @@ struct UpdateArgs {
     PricePartials pp;
     SolveState* st;
     const double* ucol;
-    const unsigned char* cand_all;   // nranks slots of cand_stride bytes
+    const unsigned char* cand_all;   // legacy exchange: nranks slots of cand_stride bytes
     size_t cand_stride;
+    const XchgBlock* xchg;           // peer-store exchange: this rank's block (NULL: legacy)
     int nranks;
     int rows_per_cta;                // <= kMaxRowBlock, multiple of RU
     int* basis;                      // m_total entries, replicated
@@ -250,22 +395,32 @@ __global__ void __launch_bounds__(kThreads) k_update_f64(UpdateArgs a) {
 
     // global leaving row: lowest ratio, then lowest global row (simplex.py:277), over all ranks' candidates
     int w = -1;
-    double w_ratio = 0.0;
     long long w_row = -1;
-    for (int k = 0; k < a.nranks; ++k) {
-        const CandHeader* h = reinterpret_cast<const CandHeader*>(a.cand_all + (size_t)k * a.cand_stride);
-        const long long row = h->row;
-        if (row < 0) continue;
-        const double ratio = h->ratio;
-        if (w < 0 || ratio < w_ratio || (ratio == w_ratio && row < w_row)) { w = k; w_ratio = ratio; w_row = row; }
+    const CandHeader* hw = nullptr;
+    const double* vrow = nullptr;
+    if (a.xchg) {
+        const int par = (int)(st->xseq & 1);
+        w = pick_winner(a.xchg, par, a.nranks);
+        if (w >= 0) { hw = &a.xchg->hdr[par][w]; w_row = hw->row; vrow = xchg_vrow(a.xchg); }
+    } else {
+        double w_ratio = 0.0;
+        for (int k = 0; k < a.nranks; ++k) {
+            const CandHeader* h = reinterpret_cast<const CandHeader*>(a.cand_all + (size_t)k * a.cand_stride);
+            const long long row = h->row;
+            if (row < 0) continue;
+            const double ratio = h->ratio;
+            if (w < 0 || ratio < w_ratio || (ratio == w_ratio && row < w_row)) { w = k; w_ratio = ratio; w_row = row; }
+        }
+        if (w >= 0) {
+            hw = reinterpret_cast<const CandHeader*>(a.cand_all + (size_t)w * a.cand_stride);
+            vrow = reinterpret_cast<const double*>(hw + 1);
+        }
     }
     const bool lead = (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
     if (w < 0) {
         if (lead) st->status = LPS_UNBOUNDED;
         return;
     }
-    const CandHeader* hw = reinterpret_cast<const CandHeader*>(a.cand_all + (size_t)w * a.cand_stride);
-    const double* vrow = reinterpret_cast<const double*>(hw + 1);
     const int c = hw->c;
     const long long r_local_ll = w_row - g.row0;
     const int r_local = (r_local_ll >= 0 && r_local_ll < g.m) ? (int)r_local_ll : -1;

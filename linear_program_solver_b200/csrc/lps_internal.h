@@ -46,6 +46,12 @@ struct lps_handle {
     unsigned char* cand_all = nullptr;
     bool own_cand = false;
     size_t cand_stride = 0;
+    // peer-store exchange (lps_f64.cuh XchgBlock): this rank's block, every rank's block (device array), IPC mappings
+    XchgBlock* xchg = nullptr;
+    XchgBlock** d_peers = nullptr;
+    std::vector<void*> ipc_open;
+    bool use_xchg = false;   // set by lps_p2p_attach with more than one rank
+    int bcast_blocks = 64;
 
     int chunk = kWideChunk, nchunks = 0, rows_per_cta = 64, sel_blocks = 1;
     bool stream_hint = false;

@@ -80,6 +80,19 @@ class F64Engine:
         N.check(self.L.lps_set_shard(self.h, row0, m_total, rank, nranks, self.cand_send.data_ptr(), self.cand_all.data_ptr()))
         self.row0, self.m_total, self.rank, self.nranks = row0, m_total, rank, nranks
 
+    def p2p_export(self) -> np.ndarray:
+        """64-byte CUDA IPC handle of this engine's exchange block (peer-store exchange, include/lps_b200.h)."""
+        out = np.zeros(64, dtype=np.uint8)
+        N.check(self.L.lps_p2p_export(self.h, out.ctypes.data))
+        return out
+
+    def p2p_attach(self, row0: int, m_total: int, rank: int, nranks: int, handles: np.ndarray):
+        """Map every rank's exchange block (handles: uint8 [nranks, 64] in rank order) and switch to peer stores."""
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        assert handles.size == 64 * nranks
+        N.check(self.L.lps_p2p_attach(self.h, row0, m_total, rank, nranks, handles.ctypes.data))
+        self.row0, self.m_total, self.rank, self.nranks = row0, m_total, rank, nranks
+
     # -- transfers -----------------------------------------------------------------------------
     def upload(self, host: np.ndarray):
         """host: float64 (m+1, >= n+1) array in grid layout (C-contiguous rows)."""
@@ -156,6 +169,9 @@ class F64Engine:
 
     def step_select(self):
         N.check(self.L.lps_step_select(self.h))
+
+    def step_exchange(self):
+        N.check(self.L.lps_step_exchange(self.h))
 
     def step_update(self):
         N.check(self.L.lps_step_update(self.h))

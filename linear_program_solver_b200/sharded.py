@@ -2,11 +2,18 @@
 
 Rank g holds constraint rows [g*m/G, (g+1)*m/G) plus its own replica of the objective row.  Per
 pivot: every rank prices the (identical) objective row and ratio-tests its own rows
-(`lps_step_select`), the candidates -- 64-byte header (ratio, global row, column, rule) followed
-by the normalised candidate row -- are all-gathered over NCCL/NVLink, and every rank picks the
-same winner (lowest ratio, then lowest global row: simplex.py:277) and applies the rank-1 update
-to its rows (`lps_step_update`).  The all-gather is the argmin-allreduce and the pivot-row
-broadcast of the north star in one collective.  No host round trip inside a burst of pivots.
+(`lps_step_select`), the ranks exchange their candidates, every rank picks the same winner (lowest
+ratio, then lowest global row: simplex.py:277) and applies the rank-1 update to its rows
+(`lps_step_update`).  No host round trip inside a burst of pivots.  Two exchanges:
+
+  exchange="p2p"   (default on GPUs) the pivot kernels do it themselves with peer stores over NVLink:
+                   each rank writes a 64-byte header into every peer's exchange block, the owner of the
+                   winning row writes the normalised row into every peer (`lps_step_exchange`).  The
+                   argmin all-reduce and the pivot-row broadcast fused into the kernels; torch.distributed
+                   is used once, to pass the CUDA IPC handles around.
+  exchange="nccl"  the candidates -- header followed by the normalised candidate row -- are all-gathered
+                   with one NCCL collective per pivot (the baseline the p2p path is measured against, and
+                   the protocol the CPU/gloo test exercises).
 
 `engine_factory` exists so that the host-side protocol can be exercised on CPU (gloo) with a
 stand-in engine supplied by the tests; the product default is the CUDA `F64Engine`.
@@ -29,7 +36,8 @@ def shard_rows(m_total: int, rank: int, nranks: int) -> Tuple[int, int]:
 
 class ShardedF64Solver:
     def __init__(self, m_total: int, n: int, rank: int = 0, nranks: int = 1, device: Optional[int] = None,
-                 group=None, engine_factory: Optional[Callable] = None, burst: Optional[int] = None):
+                 group=None, engine_factory: Optional[Callable] = None, burst: Optional[int] = None,
+                 exchange: Optional[str] = None):
         self.m_total, self.n, self.rank, self.nranks, self.group = int(m_total), int(n), rank, nranks, group
         self.row0, self.m_local = shard_rows(m_total, rank, nranks)
         if self.m_local <= 0:
@@ -38,8 +46,16 @@ class ShardedF64Solver:
             from .engine import F64Engine
             engine_factory = F64Engine
         self.eng = engine_factory(self.m_local, self.n, device)
+        if exchange is None:
+            exchange = "p2p" if hasattr(self.eng, "p2p_export") else "nccl"
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.exchange = exchange
         if nranks > 1:
-            self.eng.set_shard(self.row0, self.m_total, rank, nranks)
+            if exchange == "p2p":
+                self._attach_peers()
+            else:
+                self.eng.set_shard(self.row0, self.m_total, rank, nranks)
         # pivots enqueued between two host checks: ~2 ms of device work, between 4 and 256
         est_us = max(4.0, (self.m_local + 1) * (self.n + 1) * 16.0 / 5.0e6)
         self.burst = burst or int(max(4, min(256, 2000.0 / est_us)))
@@ -48,8 +64,21 @@ class ShardedF64Solver:
     def close(self):
         self.eng.close()
 
+    def _attach_peers(self):
+        """All-gather the 64-byte CUDA IPC handles of the exchange blocks, map the peers' blocks."""
+        import torch
+        import torch.distributed as dist
+        mine = torch.from_numpy(self.eng.p2p_export()).to(f"cuda:{self.eng.device}")
+        everyone = torch.empty(64 * self.nranks, dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        self.eng.p2p_attach(self.row0, self.m_total, self.rank, self.nranks, everyone.cpu().numpy())
+        dist.barrier(group=self.group)            # every rank has mapped every block before the first peer store
+
     # -- one pivot: select, exchange, update -------------------------------------------------------
     def _exchange(self):
+        if self.exchange == "p2p":
+            self.eng.step_exchange()
+            return
         if self.nranks > 1:
             import torch.distributed as dist
             if hasattr(self.eng, "on_stream"):        # order the collective on the engine's own stream

@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=512)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -27,7 +28,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m, n = a.rows, 2 * a.rows
-    sv = ShardedF64Solver(m, n, rank, world, device=local)
+    sv = ShardedF64Solver(m, n, rank, world, device=local, exchange=a.exchange)
     sv.eng.fill_dense(a.seed, 1, 9)
     basis = np.arange(m, n, dtype=np.int32)
     st, k, trace = sv.solve(basis, None, trace_cap=1 << 20)
@@ -40,7 +41,7 @@ def main():
     flag = torch.tensor([1 if good else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"sharded nccl check: world={world} m={m} pivots={k} status={st} -> {'OK' if flag.item() else 'MISMATCH'}", flush=True)
+        print(f"sharded check ({a.exchange} exchange): world={world} m={m} pivots={k} status={st} -> {'OK' if flag.item() else 'MISMATCH'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
 
