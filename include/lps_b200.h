@@ -141,18 +141,16 @@ int lps_solve(lps_handle *h, long long max_pivots, int *basis, int *marks, int *
 int lps_solve_begin(lps_handle *h, long long max_pivots, const int *basis, const int *marks,
                     long long trace_cap);
 int lps_step_select(lps_handle *h);
-/* Peer-store exchange (no collective call): after lps_p2p_attach, lps_step_select writes this rank's 64-byte
- * candidate header straight into every peer GPU's exchange block over NVLink, and lps_step_exchange -- to be
- * enqueued between lps_step_select and lps_step_update -- waits for all headers, lets the owner of the winning
- * row normalise it and store it into every peer, and returns (on the stream) once this rank has the row.  It
- * replaces the caller's all-gather; it is the argmin all-reduce + pivot-row broadcast of SURVEY.md section 8e fused
- * into the pivot kernels.  lps_p2p_export allocates this handle's exchange block and returns its 64-byte CUDA IPC
- * handle; the caller gathers the handles of all ranks (any transport) and passes them, in rank order, to
- * lps_p2p_attach on every rank. */
+/* Peer-store exchange (no collective call): after lps_p2p_attach, lps_step_select itself writes this rank's 64-byte
+ * candidate header straight into every peer GPU's exchange block over NVLink, waits for the peers' headers, and the
+ * rank that owns the winning row normalises it and stores it into every peer; the launch ends on a rank once that
+ * rank holds the row.  It replaces the caller's all-gather between lps_step_select and lps_step_update: the argmin
+ * all-reduce + pivot-row broadcast of SURVEY.md section 8e fused into the select kernel.  lps_p2p_export returns the
+ * 64-byte CUDA IPC handle of this handle's exchange block; the caller gathers the handles of all ranks (any
+ * transport) and passes them, in rank order, to lps_p2p_attach on every rank. */
 int lps_p2p_export(lps_handle *h, unsigned char *ipc_handle64);
 int lps_p2p_attach(lps_handle *h, long long row0, long long m_total, int rank, int nranks,
                    const unsigned char *ipc_handles);
-int lps_step_exchange(lps_handle *h);
 int lps_step_update(lps_handle *h);
 int lps_solve_poll(lps_handle *h, int *status, long long *npiv);
 int lps_solve_end(lps_handle *h, int *basis, int *marks, int *trace, long long trace_cap,

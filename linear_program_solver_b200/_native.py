@@ -57,7 +57,6 @@ SIGNATURES = {
     "lps_solve_begin": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong]),
     "lps_step_select": (c_int, [c_void_p]),
     "lps_step_update": (c_int, [c_void_p]),
-    "lps_step_exchange": (c_int, [c_void_p]),
     "lps_p2p_export": (c_int, [c_void_p, c_void_p]),
     "lps_p2p_attach": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_void_p]),
     "lps_solve_poll": (c_int, [c_void_p, POINTER(c_int), POINTER(c_longlong)]),

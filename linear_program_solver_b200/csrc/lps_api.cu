@@ -59,7 +59,8 @@ static void plan(lps_handle* h) {
     if (tiles_wide >= 148 * 8) { h->chunk = kWideChunk; h->rows_per_cta = 64; }
     else { h->chunk = kNarrowChunk; h->rows_per_cta = ((size_t)(h->m + 1) * h->ld >= (1u << 20)) ? 16 : 8; }
     h->nchunks = (int)((h->ld + h->chunk - 1) / h->chunk);
-    h->sel_blocks = std::max(1, std::min((h->m + kThreads - 1) / kThreads, 148 * 4));
+    // k_select_f64 spins on an in-kernel flag: never more CTAs than SMs, so all of them are resident
+    h->sel_blocks = std::max(1, std::min(std::max((h->m + kThreads - 1) / kThreads, (int)(h->ld / (8 * kThreads))), 148));
 }
 
 extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* stream, lps_handle** out) {
@@ -101,7 +102,6 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
         CU(cudaMemsetAsync(h->xchg, 0, xb, h->stream));
         CU(cudaMalloc(&h->d_peers, kMaxRanks * sizeof(XchgBlock*)));
         CU(cudaMemcpyAsync(h->d_peers, &h->xchg, sizeof(XchgBlock*), cudaMemcpyHostToDevice, h->stream));
-        h->bcast_blocks = (int)std::max<size_t>(1, std::min<size_t>((h->ld + kThreads - 1) / kThreads, 148));
     }
     const int maxchunks = (int)((h->ld + kNarrowChunk - 1) / kNarrowChunk);
     CU(cudaMalloc(&h->pd_val, maxchunks * sizeof(double)));
@@ -233,26 +233,17 @@ static int launch_select(lps_handle* h) {
     SelectArgs a;
     a.g = grid_of(h); a.pp = partials_of(h); a.nchunks = h->nchunks; a.st = h->st; a.ucol = h->ucol;
     a.blk = h->sel_blk; a.cand = (CandHeader*)h->cand_send;
-    a.peers = h->use_xchg ? h->d_peers : nullptr; a.rank = h->rank; a.nranks = h->nranks;
+    a.xchg = h->use_xchg ? h->xchg : nullptr; a.peers = h->d_peers; a.rank = h->rank; a.nranks = h->nranks;
     k_select_f64<<<h->sel_blocks, kThreads, 0, h->stream>>>(a);
     h->launches_all++;
     CU(cudaGetLastError());
     return LPS_OK;
 }
-static int launch_bcast(lps_handle* h, bool force = false) {
-    if (!h->use_xchg && !force) return LPS_OK;       // candidate-slot exchange: the caller all-gathers the candidates
-    BcastArgs a;
-    a.g = grid_of(h); a.st = h->st; a.xchg = h->xchg; a.peers = h->d_peers; a.rank = h->rank; a.nranks = h->nranks;
-    k_bcast_f64<<<h->bcast_blocks, kThreads, 0, h->stream>>>(a);
-    h->launches_all++;
-    CU(cudaGetLastError());
-    return LPS_OK;
-}
-static int launch_update(lps_handle* h, int commit, bool force_xchg = false) {
+static int launch_update(lps_handle* h, int commit) {
     UpdateArgs a;
     a.g = grid_of(h); a.pp = partials_of(h); a.st = h->st; a.ucol = h->ucol;
     a.cand_all = h->cand_all; a.cand_stride = h->cand_stride; a.nranks = h->nranks;
-    a.xchg = (h->use_xchg || force_xchg) ? h->xchg : nullptr;
+    a.xchg = h->use_xchg ? h->xchg : nullptr;
     a.rows_per_cta = h->rows_per_cta; a.basis = h->basis; a.marks = h->use_marks ? h->marks : nullptr; a.trace = h->trace; a.trace_cap = h->trace_cap;
     a.commit = commit;
     dim3 grid(h->nchunks, (h->m + 1 + h->rows_per_cta - 1) / h->rows_per_cta);
@@ -295,11 +286,10 @@ extern "C" int lps_pivot(lps_handle* h, int r, int c) {
     s.status = LPS_OK; s.max_pivots = -1; s.xseq = h->st_host->xseq;
     TRY(write_state(h, s));
     const int blocks = std::max(1, std::min((int)((std::max((size_t)h->m + 1, h->ld) + kThreads - 1) / kThreads), 148 * 2));
-    k_forced_f64<<<blocks, kThreads, 0, h->stream>>>(grid_of(h), h->st, h->ucol, h->d_peers, r, c);
+    k_forced_f64<<<blocks, kThreads, 0, h->stream>>>(grid_of(h), h->st, h->ucol, (CandHeader*)h->cand_send, r, c);
     h->launches_all++;
     CU(cudaGetLastError());
-    TRY(launch_bcast(h, true));                      // an explicit pivot always goes through the exchange block
-    TRY(launch_update(h, 0, true));
+    TRY(launch_update(h, 0));
     TRY(read_state(h));
     const int st = h->st_host->status;
     return st == LPS_ZERO_PIVOT ? LPS_ZERO_PIVOT : LPS_OK;
@@ -422,12 +412,6 @@ extern "C" int lps_step_select(lps_handle* h) {
     if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
     return launch_select(h);
 }
-extern "C" int lps_step_exchange(lps_handle* h) {
-    USE(h);
-    NEED_MODE(h, 0);
-    if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
-    return launch_bcast(h);
-}
 extern "C" int lps_step_update(lps_handle* h) {
     USE(h);
     NEED_MODE(h, 0);
@@ -476,7 +460,6 @@ extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* m
         const long long now = std::min(burst, room);
         for (long long k = 0; k < now; ++k) {
             TRY(launch_select(h));
-            TRY(launch_bcast(h));
             TRY(launch_update(h, 1));
         }
         enqueued += now;

@@ -100,6 +100,7 @@ struct XMeta {               // per reconstructed number
 template <int NB>
 struct GarnerShared {
     uint32_t v[2][NB];
+    uint32_t done[3];
     int hi[NB], lo[NB], top[NB], neg[NB];
     uint32_t d3[NB][3];
 };
@@ -117,8 +118,33 @@ __device__ __forceinline__ void block_garner(const XGrid& g, uint32_t (&t)[SPT][
         q[s] = k < P ? g.pr[k].q : 3u;
         qi[s] = k < P ? g.pr[k].qinv : 0u;
     }
+    // Early exit: after round j-1 lane k >= j holds (x - X_j) / (p_0 ... p_{j-1}) mod p_k, X_j the number made of the
+    // digits found so far.  When every such lane holds 0 the quotient is 0 (it is smaller than the product of the
+    // remaining primes), when every lane holds p_k - 1 it is -1 (x negative, |x| below the product of the first j
+    // primes); in both cases the lanes already hold their final digits and the remaining rounds would not change
+    // them.  Tableau entries are usually far below the Hadamard bound that sized the prime set, so the conversion
+    // costs O(P * digits of |x|) instead of O(P^2).  Checked every fourth round (one warp vote + one shared atomic).
+    if (tid == 0) S.done[0] = S.done[1] = S.done[2] = 0xffffffffu;
+    __syncthreads();
     for (int j = 0; j < P; ++j) {
         const int os = j / bd, ot = j - os * bd;
+        const bool vote = (j & 3) == 0;
+        if (vote) {
+            uint32_t mask = 0xffffffffu;                       // bit b: my lanes of number b are all 0; bit NB+b: all p_k - 1
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) {
+                const int k = tid + s * bd;
+                if (k >= j && k < P) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        if (t[s][b] != 0u) mask &= ~(1u << b);
+                        if (t[s][b] != q[s] - 1u) mask &= ~(1u << (NB + b));
+                    }
+                }
+            }
+            mask = __reduce_and_sync(0xffffffffu, mask);
+            if ((tid & 31) == 0 && mask != 0xffffffffu) atomicAnd(&S.done[(j >> 2) % 3], mask);
+        }
         if (tid == ot) {
 #pragma unroll
             for (int s = 0; s < SPT; ++s)
@@ -128,6 +154,11 @@ __device__ __forceinline__ void block_garner(const XGrid& g, uint32_t (&t)[SPT][
                 }
         }
         __syncthreads();
+        if (vote) {
+            const uint32_t d = S.done[(j >> 2) % 3];
+            if ((((d | (d >> NB)) & ((1u << NB) - 1u)) == ((1u << NB) - 1u))) break;
+            if (tid == 0) S.done[((j >> 2) + 2) % 3] = 0xffffffffu;   // slot of the vote after next; last read before this round's barrier
+        }
         const uint32_t* invrow = g.invtab + (size_t)j * P;
 #pragma unroll
         for (int s = 0; s < SPT; ++s) {

@@ -68,6 +68,14 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // spin until *p >= want; false after ten seconds (a peer died or never enqueued this pivot: do not hang the GPU)
 __device__ __forceinline__ bool wait_seq(const unsigned long long* p, unsigned long long want) {
     if (ld_acquire_sys(p) >= want) return true;
@@ -75,6 +83,16 @@ __device__ __forceinline__ bool wait_seq(const unsigned long long* p, unsigned l
     while (ld_acquire_sys(p) < want) {
         if (global_ns() - t0 > 10000000000ull) return false;
         __nanosleep(32);
+    }
+    return true;
+}
+// same on a flag raised by another CTA of this kernel (twenty seconds: outlasts wait_seq)
+__device__ __forceinline__ bool wait_seq_gpu(const unsigned long long* p, unsigned long long want) {
+    if (ld_acquire_gpu(p) >= want) return true;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_gpu(p) < want) {
+        if (global_ns() - t0 > 20000000000ull) return false;
+        __nanosleep(20);
     }
     return true;
 }
@@ -90,8 +108,11 @@ struct SolveState {
     unsigned int ticket;     // last-block election of k_select
     int dry_run;             // find_pivot: select only, nothing is committed
     int last_r, last_c;      // last selected / committed pivot (global row)
-    unsigned int ticket2;    // last-block election of k_bcast
-    unsigned long long xseq; // exchange rounds published so far (k_select / k_forced bump it, the later kernels read it)
+    unsigned int ticket2;    // last-block election of the pivot-row broadcast
+    unsigned long long xseq; // select rounds decided so far; raised inside k_select as its "decision published" flag
+    int sel_w;               // decision of the current round: winning rank, -1 nothing to normalise, -2 peer time-out
+    int pad;
+    long long sel_row;       // global row of the winner
 };
 
 struct F64Grid {
@@ -148,8 +169,9 @@ struct SelectArgs {
     SolveState* st;
     double* ucol;            // m+1 (+pad): column c of the local grid, gathered here for the update
     ArgMinF64* blk;          // gridDim.x per-block ratio partials
-    CandHeader* cand;        // this rank's candidate slot (header + ld doubles); legacy all-gather exchange
-    XchgBlock* const* peers; // peer-store exchange: every rank's exchange block (NULL: legacy exchange)
+    CandHeader* cand;        // this rank's candidate slot (header + ld doubles): one rank, or the all-gather exchange
+    XchgBlock* xchg;         // peer-store exchange: this rank's exchange block (NULL: candidate slots)
+    XchgBlock* const* peers; //                      every rank's exchange block
     int rank, nranks;
 };
 
@@ -167,10 +189,35 @@ __device__ __forceinline__ void publish_header(XchgBlock* const* peers, int rank
     }
 }
 
+__device__ __forceinline__ int pick_winner(const XchgBlock* x, int par, int nranks) {
+    int w = -1;
+    double w_ratio = 0.0;
+    long long w_row = -1;
+    for (int k = 0; k < nranks; ++k) {
+        const CandHeader* h = &x->hdr[par][k];
+        const long long row = h->row;
+        if (row < 0) continue;
+        const double ratio = h->ratio;
+        if (w < 0 || ratio < w_ratio || (ratio == w_ratio && row < w_row)) { w = k; w_ratio = ratio; w_row = row; }
+    }
+    return w;
+}
+
+// One launch per pivot decision, three phases separated by an in-kernel flag (the grid is at most one CTA per SM,
+// so every CTA is resident and spinning on the flag cannot starve the CTA that raises it):
+//   A  every CTA: rule / entering column from the pricing partials, ratio test over its rows, column c -> ucol
+//   B  the CTA that finishes last: reduces the partials to this rank's best leaving row; with the peer-store
+//      exchange it writes the 64-byte header into every peer GPU and waits for theirs (the argmin all-reduce),
+//      then publishes the decision (winning rank, row) and raises the flag
+//   C  every CTA of the rank that owns the winning row: normalises its slice of that row (row r times the
+//      reciprocal of the pivot, tableau.py:262-267) and stores it where the update reads it -- the local candidate
+//      slot, or straight into EVERY rank's exchange block over NVLink (the pivot-row broadcast); the other ranks
+//      wait for the row's sequence flag.  When the kernel ends on a rank, that rank holds all its update needs.
 __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
     __shared__ ArgMinF64 s_arg[32];
     __shared__ int s_int[32];
-    __shared__ int s_last;
+    __shared__ int s_last, s_w;
+    __shared__ long long s_row;
     SolveState* st = a.st;
     const F64Grid& g = a.g;
     if (st->status != LPS_OK) return;
@@ -178,6 +225,9 @@ __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && !st->dry_run) st->status = LPS_MAX_PIVOTS;
         return;
     }
+    // this round's sequence number: read before the ticket below, i.e. before the last CTA can advance it
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(&st->xseq) + 1;
+    const int dry = st->dry_run;
     // stuck counter and rule (simplex.py:123,132-137), recomputed identically by every block
     int rule = st->rule;
     long long stuck = st->stuck;
@@ -198,13 +248,13 @@ __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
     }
     if (c == INT_MAX) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
-            if (st->dry_run) { st->last_r = -1; st->last_c = -1; }
+            if (dry) { st->last_r = -1; st->last_c = -1; }
             st->status = LPS_OPTIMAL;
         }
         return;
     }
 
-    // ratio test over this block's rows; column c is gathered into ucol on the way
+    // ---- A: ratio test over this block's rows; column c is gathered into ucol on the way ----
     ArgMinF64 best{0.0, INT_MAX};
     for (int i = blockIdx.x * kThreads + threadIdx.x; i < g.m; i += gridDim.x * kThreads) {
         const double aic = g.T[(size_t)i * g.ld + c];
@@ -222,132 +272,78 @@ __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
         s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (!s_last) return;
 
-    // ---- last block: reduce the per-block partials, publish the candidate ----
-    __threadfence();
-    best = ArgMinF64{0.0, INT_MAX};
-    for (int k = threadIdx.x; k < (int)gridDim.x; k += kThreads) {
-        ArgMinF64 o;
-        o.key = __ldcg(&a.blk[k].key);
-        o.idx = __ldcg(&a.blk[k].idx);
-        best = argmin_pick(best, o);
-    }
-    best = block_argmin(best, s_arg);
-    const int r = best.idx;
-    if (a.peers) {                                             // peer-store exchange: 64-byte header only
-        if (st->dry_run) {
-            if (threadIdx.x == 0) { st->ticket = 0; st->last_r = (r == INT_MAX) ? -1 : (int)(g.row0 + r); st->last_c = c; }
-            return;
+    if (s_last) {
+        // ---- B: reduce the per-block partials, exchange, publish the decision ----
+        __threadfence();
+        best = ArgMinF64{0.0, INT_MAX};
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += kThreads) {
+            ArgMinF64 o;
+            o.key = __ldcg(&a.blk[k].key);
+            o.idx = __ldcg(&a.blk[k].idx);
+            best = argmin_pick(best, o);
         }
+        best = block_argmin(best, s_arg);
+        const int r = best.idx;
         CandHeader h{};
         h.ratio = best.key; h.row = (r == INT_MAX) ? -1 : g.row0 + r; h.c = c; h.rule = rule; h.stuck = stuck;
-        const unsigned long long seq = st->xseq + 1;
-        publish_header(a.peers, a.rank, a.nranks, h, seq);
-        __syncthreads();
+        int w;
+        long long w_row;
+        if (a.xchg && !dry) {
+            publish_header(a.peers, a.rank, a.nranks, h, seq);
+            int ok = 1;
+            if ((int)threadIdx.x < a.nranks) ok = wait_seq(&a.xchg->hdr_seq[threadIdx.x], seq) ? 1 : 0;
+            ok = __syncthreads_and(ok);
+            w = ok ? pick_winner(a.xchg, (int)(seq & 1), a.nranks) : -2;
+            w_row = (w >= 0) ? a.xchg->hdr[seq & 1][w].row : -1;
+        } else {
+            if (threadIdx.x == 0) *a.cand = h;
+            w = (r == INT_MAX || dry) ? -1 : a.rank;
+            w_row = h.row;
+        }
         if (threadIdx.x == 0) {
             st->ticket = 0;
             a.ucol[g.m] = g.T[(size_t)g.m * g.ld + c];
-            st->xseq = seq;
+            if (dry) { st->last_r = (r == INT_MAX) ? -1 : (int)(g.row0 + r); st->last_c = c; }
+            if (w == -2) st->status = LPS_E_PEER;
+            st->sel_w = w;
+            st->sel_row = w_row;
+            __threadfence();
+            st_release_gpu(&st->xseq, seq);
         }
-        return;
     }
-    double* vrow = reinterpret_cast<double*>(a.cand + 1);
+
+    // ---- C: the decision, then the normalised pivot row ----
     if (threadIdx.x == 0) {
-        st->ticket = 0;
-        a.ucol[g.m] = g.T[(size_t)g.m * g.ld + c];
-        a.cand->ratio = best.key;
-        a.cand->row = (r == INT_MAX) ? -1 : g.row0 + r;
-        a.cand->c = c;
-        a.cand->rule = rule;
-        a.cand->stuck = stuck;
-        if (st->dry_run) { st->last_r = (r == INT_MAX) ? -1 : (int)(g.row0 + r); st->last_c = c; }
-    }
-    if (r == INT_MAX || st->dry_run) return;
-    // normalised pivot row: row r times the reciprocal of the pivot (tableau.py:262-267, :254-260)
-    const double* src = g.T + (size_t)r * g.ld;
-    const double inv = 1.0 / src[c];
-    for (int j = threadIdx.x; j < (int)g.ld; j += kThreads) vrow[j] = (inv == 1.0) ? src[j] : src[j] * inv;
-}
-
-// Explicit pivot (Tableau.pivot(r,c)): gather column c and build the candidate for a caller-chosen (r,c).
-__global__ void __launch_bounds__(kThreads) k_forced_f64(F64Grid g, SolveState* st, double* ucol, XchgBlock* const* peers, int r, int c) {
-    const double p = g.T[(size_t)r * g.ld + c];
-    if (p == 0.0) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) st->status = LPS_ZERO_PIVOT;
-        return;
-    }
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i <= g.m; i += gridDim.x * kThreads) ucol[i] = g.T[(size_t)i * g.ld + c];
-    if (blockIdx.x == 0) {
-        CandHeader h{};
-        h.ratio = 0.0; h.row = g.row0 + r; h.c = c; h.rule = 2; h.stuck = st->stuck;
-        const unsigned long long seq = st->xseq + 1;
-        publish_header(peers, 0, 1, h, seq);
-        __syncthreads();
-        if (threadIdx.x == 0) st->xseq = seq;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// exchange: wait for every rank's header, pick the global leaving row (lowest ratio, then lowest global row:
-// simplex.py:277); the owner normalises that row (row r times the reciprocal of the pivot, tableau.py:262-267)
-// and stores it into EVERY rank's exchange block over NVLink, the others wait until it has arrived.  When this
-// kernel ends on a rank, that rank holds everything its update needs.
-// ------------------------------------------------------------------------------------------------
-struct BcastArgs {
-    F64Grid g;
-    SolveState* st;
-    XchgBlock* xchg;         // this rank's block
-    XchgBlock* const* peers; // every rank's block
-    int rank, nranks;
-};
-
-__device__ __forceinline__ int pick_winner(const XchgBlock* x, int par, int nranks) {
-    int w = -1;
-    double w_ratio = 0.0;
-    long long w_row = -1;
-    for (int k = 0; k < nranks; ++k) {
-        const CandHeader* h = &x->hdr[par][k];
-        const long long row = h->row;
-        if (row < 0) continue;
-        const double ratio = h->ratio;
-        if (w < 0 || ratio < w_ratio || (ratio == w_ratio && row < w_row)) { w = k; w_ratio = ratio; w_row = row; }
-    }
-    return w;
-}
-
-__global__ void __launch_bounds__(kThreads) k_bcast_f64(BcastArgs a) {
-    __shared__ int s_w, s_fail, s_last;
-    SolveState* st = a.st;
-    const F64Grid& g = a.g;
-    if (st->status != LPS_OK) return;
-    const unsigned long long seq = st->xseq;
-    const int par = (int)(seq & 1);
-    if (threadIdx.x == 0) {
-        int ok = 1;
-        for (int k = 0; k < a.nranks; ++k) ok &= wait_seq(&a.xchg->hdr_seq[k], seq) ? 1 : 0;
-        s_fail = !ok;
-        s_w = ok ? pick_winner(a.xchg, par, a.nranks) : -1;
+        int w = -3;
+        if (wait_seq_gpu(&st->xseq, seq)) { w = st->sel_w; s_row = st->sel_row; }
+        s_w = w;
     }
     __syncthreads();
-    if (s_fail) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) st->status = LPS_E_PEER;
+    const int w = s_w;
+    if (w == -3) {                                             // the deciding CTA never showed up: do not hang
+        if (threadIdx.x == 0) st->status = LPS_E_PEER;
         return;
     }
-    const int w = s_w;
-    if (w < 0) return;                                         // no row with a_ic > 0 anywhere: k_update reports unbounded
+    if (w < 0) return;                                         // dry run, peer time-out, or no row with a_ic > 0 (k_update reports unbounded)
     if (w != a.rank) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && !wait_seq(&a.xchg->row_seq, seq)) st->status = LPS_E_PEER;
         return;
     }
-    const CandHeader* hw = &a.xchg->hdr[par][w];
-    const int c = hw->c;
-    const double* src = g.T + (size_t)(hw->row - g.row0) * g.ld;
+    const double* src = g.T + (size_t)(s_row - g.row0) * g.ld;
     const double inv = 1.0 / src[c];
-    for (int j = blockIdx.x * kThreads + threadIdx.x; j < (int)g.ld; j += gridDim.x * kThreads) {
-        const double v = (inv == 1.0) ? src[j] : src[j] * inv;
-        for (int k = 0; k < a.nranks; ++k) xchg_vrow(a.peers[k])[j] = v;
+    const bool spread = (a.xchg != nullptr);
+    double* local = spread ? nullptr : reinterpret_cast<double*>(a.cand + 1);
+    for (int j = 2 * (blockIdx.x * kThreads + threadIdx.x); j < (int)g.ld; j += 2 * gridDim.x * kThreads) {
+        double2 x = *reinterpret_cast<const double2*>(src + j);
+        if (inv != 1.0) { x.x = x.x * inv; x.y = x.y * inv; }
+        if (spread) {
+            for (int k = 0; k < a.nranks; ++k) *reinterpret_cast<double2*>(xchg_vrow(a.peers[k]) + j) = x;
+        } else {
+            *reinterpret_cast<double2*>(local + j) = x;
+        }
     }
+    if (!spread) return;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket2, 1u) == gridDim.x - 1);
@@ -356,6 +352,28 @@ __global__ void __launch_bounds__(kThreads) k_bcast_f64(BcastArgs a) {
     __threadfence_system();
     if ((int)threadIdx.x < a.nranks) st_release_sys(&a.peers[threadIdx.x]->row_seq, seq);
     if (threadIdx.x == 0) st->ticket2 = 0;
+}
+
+// Explicit pivot (Tableau.pivot(r,c)): gather column c and build the candidate for a caller-chosen (r,c).
+__global__ void __launch_bounds__(kThreads) k_forced_f64(F64Grid g, SolveState* st, double* ucol, CandHeader* cand, int r, int c) {
+    const double p = g.T[(size_t)r * g.ld + c];
+    if (p == 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->status = LPS_ZERO_PIVOT;
+        return;
+    }
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i <= g.m; i += gridDim.x * kThreads) ucol[i] = g.T[(size_t)i * g.ld + c];
+    double* vrow = reinterpret_cast<double*>(cand + 1);
+    const double* src = g.T + (size_t)r * g.ld;
+    const double inv = 1.0 / p;
+    for (int j = blockIdx.x * kThreads + threadIdx.x; j < (int)g.ld; j += gridDim.x * kThreads)
+        vrow[j] = (inv == 1.0) ? src[j] : src[j] * inv;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cand->ratio = 0.0;
+        cand->row = g.row0 + r;
+        cand->c = c;
+        cand->rule = 2;
+        cand->stuck = st->stuck;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -51,7 +51,6 @@ struct lps_handle {
     XchgBlock** d_peers = nullptr;
     std::vector<void*> ipc_open;
     bool use_xchg = false;   // set by lps_p2p_attach with more than one rank
-    int bcast_blocks = 64;
 
     int chunk = kWideChunk, nchunks = 0, rows_per_cta = 64, sel_blocks = 1;
     bool stream_hint = false;

@@ -170,9 +170,6 @@ class F64Engine:
     def step_select(self):
         N.check(self.L.lps_step_select(self.h))
 
-    def step_exchange(self):
-        N.check(self.L.lps_step_exchange(self.h))
-
     def step_update(self):
         N.check(self.L.lps_step_update(self.h))
 

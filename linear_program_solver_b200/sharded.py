@@ -6,11 +6,12 @@ pivot: every rank prices the (identical) objective row and ratio-tests its own r
 ratio, then lowest global row: simplex.py:277) and applies the rank-1 update to its rows
 (`lps_step_update`).  No host round trip inside a burst of pivots.  Two exchanges:
 
-  exchange="p2p"   (default on GPUs) the pivot kernels do it themselves with peer stores over NVLink:
-                   each rank writes a 64-byte header into every peer's exchange block, the owner of the
-                   winning row writes the normalised row into every peer (`lps_step_exchange`).  The
-                   argmin all-reduce and the pivot-row broadcast fused into the kernels; torch.distributed
-                   is used once, to pass the CUDA IPC handles around.
+  exchange="p2p"   (default on GPUs) the select kernel does it itself with peer stores over NVLink: each
+                   rank writes a 64-byte header into every peer's exchange block and waits for theirs, the
+                   owner of the winning row writes the normalised row into every peer.  The argmin
+                   all-reduce and the pivot-row broadcast are fused into `lps_step_select`: two launches
+                   per pivot, no collective call; torch.distributed is used once, to pass the CUDA IPC
+                   handles around.
   exchange="nccl"  the candidates -- header followed by the normalised candidate row -- are all-gathered
                    with one NCCL collective per pivot (the baseline the p2p path is measured against, and
                    the protocol the CPU/gloo test exercises).
@@ -77,8 +78,7 @@ class ShardedF64Solver:
     # -- one pivot: select, exchange, update -------------------------------------------------------
     def _exchange(self):
         if self.exchange == "p2p":
-            self.eng.step_exchange()
-            return
+            return                                    # fused into lps_step_select
         if self.nranks > 1:
             import torch.distributed as dist
             if hasattr(self.eng, "on_stream"):        # order the collective on the engine's own stream

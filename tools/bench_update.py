@@ -24,26 +24,27 @@ def fill_dense(eng, seed=0):
     g.manual_seed(seed)
     T = eng.grid
     T.zero_()
-    T[:m, :m] = torch.randint(1, 10, (m, m), generator=g, device=T.device).to(torch.float64)
+    T[:m, :n - m] = torch.randint(1, 10, (m, n - m), generator=g, device=T.device).to(torch.float64)
     idx = torch.arange(m, device=T.device)
-    T[idx, m + idx] = 1.0
+    T[idx, n - m + idx] = 1.0
     T[:m, n] = torch.randint(9 * m // 4, 9 * m // 2 + 1, (m,), generator=g, device=T.device).to(torch.float64)
-    T[m, :m] = -torch.randint(1, 10, (m,), generator=g, device=T.device).to(torch.float64)
+    T[m, :n - m] = -torch.randint(1, 10, (n - m,), generator=g, device=T.device).to(torch.float64)
     torch.cuda.synchronize()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--m", type=int, default=32768)
+    ap.add_argument("--n", type=int, default=0, help="variables (default 2m); wider than 2m = the shape of one shard")
     ap.add_argument("--pivots", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()
     import torch
     from linear_program_solver_b200.engine import F64Engine
-    m, n = a.m, 2 * a.m
+    m, n = a.m, (a.n or 2 * a.m)
     eng = F64Engine(m, n)
     fill_dense(eng)
-    basis = np.arange(m, 2 * m, dtype=np.int32)
+    basis = np.arange(n - m, n, dtype=np.int32)
     st, k, _ = eng.solve(basis, None, max_pivots=a.warmup)
     eng.prof_reset()
     torch.cuda.synchronize()
