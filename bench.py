@@ -251,31 +251,44 @@ def run_ours(a):
     e2e_steps = max(1, min(a.steps, a.e2e_steps))
     h2d = (m_loc + 1) * (n + 1) * 8
     d2h_box = [0]
+    parts = []                                   # per e2e step: (upload + setup, pivots, read-back) seconds on this rank
 
     if world == 1:
         from linear_program_solver_b200 import Simplex, Tableau
         solver.close()
 
         def e2e_step():
+            t0 = time.perf_counter()
             t = Tableau.from_grid(host_np, mode="fp64", device=local)
             s = Simplex(t)                      # reads b, uploads, checks canonical form on the device
+            t1 = time.perf_counter()
             s.solve(max_pivots=B)
+            t2 = time.perf_counter()
             z = s.getObjValue()
             x = s.getBFS()
             d2h_box[0] = 8 * (n + 1) + 8 * (m + 1) + 4 * m + 4 * n + 12 * B
             t._drop_engine()
+            t3 = time.perf_counter()
+            parts.append((t1 - t0, t2 - t1, t3 - t2))
             return z, len(x)
     else:
         def e2e_step():
+            t0 = time.perf_counter()
             N.check(eng.L.lps_upload_f64(eng.h, host.data_ptr(), n + 1))
+            eng.sync()
+            t1 = time.perf_counter()
             bs = np.arange(m, 2 * m, dtype=np.int32)
             st_, k_, _ = solver.solve(bs, None, max_pivots=B)
+            t2 = time.perf_counter()
             z = -eng.read_row(m_loc)[n]
             x = eng.read_col(n)
             d2h_box[0] = 8 * (n + 1) + 8 * (m_loc + 1) + 4 * m
+            t3 = time.perf_counter()
+            parts.append((t1 - t0, t2 - t1, t3 - t2))
             return z, len(x)
 
     e2e_step()                                   # warm-up (engine creation, pinned mappings)
+    parts.clear()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -314,6 +327,9 @@ def run_ours(a):
                          "loop_frac": bytes_launch * pivots / (ms * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
                     "d2h_bytes_per_step": d2h_box[0], "steps": e2e_steps, "pivots_per_step": B,
+                    "seconds_per_step": {"upload_and_setup": float(np.mean([p[0] for p in parts])),
+                                         "pivots": float(np.mean([p[1] for p in parts])),
+                                         "read_back": float(np.mean([p[2] for p in parts]))},
                     "api": "Tableau.from_grid + Simplex + solve(max_pivots)" if world == 1 else
                            "ShardedF64Solver: lps_upload_f64 + solve + read-back per rank"},
             "gpu_launches": int(all_launches),
@@ -333,7 +349,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--m", type=int, default=32768, help="constraint rows (n = 2m); default is config C4")
-    ap.add_argument("--pivots-per-step", type=int, default=32)
+    ap.add_argument("--pivots-per-step", type=int, default=256,
+                    help="consecutive simplex pivots per step (a solve of this size runs tens of thousands)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

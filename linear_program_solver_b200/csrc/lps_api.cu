@@ -113,7 +113,7 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
     CU(cudaMallocHost(&h->st_host, sizeof(SolveState)));
     CU(cudaMalloc(&h->basis, (size_t)m * sizeof(int)));
     CU(cudaMemsetAsync(h->basis, 0xff, (size_t)m * sizeof(int), h->stream));
-    CU(cudaMalloc(&h->scratch_i, ((size_t)n + 8) * sizeof(int)));
+    CU(cudaMalloc(&h->scratch_i, (2 * (size_t)n + 16) * sizeof(int)));
     CU(cudaMalloc(&h->marks, (size_t)n * sizeof(int)));
     CU(cudaMemsetAsync(h->marks, 0, (size_t)n * sizeof(int), h->stream));
     *out = h;
@@ -358,12 +358,16 @@ extern "C" int lps_is_canonical(lps_handle* h, int* bcols, int* canonical) {
     CU(cudaStreamSynchronize(h->stream));
     h->launches_all++;
     if (neg) { *canonical = 0; return LPS_OK; }   // bcols untouched, like tableau.py:476-477
-    k_canon_cols_f64<<<(h->n + 127) / 128, 128, 0, h->stream>>>(grid_of(h), h->scratch_i);
+    int* bad = h->scratch_i + h->n + 8;
+    const int slabs = std::max(1, std::min((h->m + 63) / 64, 64));
+    const int rows_per_slab = (h->m + slabs - 1) / slabs;
+    k_canon_init_f64<<<(h->n + 255) / 256, 256, 0, h->stream>>>(grid_of(h), h->scratch_i, bad);
+    k_canon_cols_f64<<<dim3((h->n + 127) / 128, slabs), 128, 0, h->stream>>>(grid_of(h), rows_per_slab, h->scratch_i, bad);
     int* d_bcols = nullptr;
     CU(cudaMalloc(&d_bcols, (size_t)h->m * sizeof(int)));
     CU(cudaMemsetAsync(d_bcols, 0x7f, (size_t)h->m * sizeof(int), h->stream));
-    k_canon_rows<<<std::max(1, std::min((h->n + 255) / 256, 592)), 256, 0, h->stream>>>(h->scratch_i, h->n, d_bcols);
-    h->launches_all += 2;
+    k_canon_rows<<<std::max(1, std::min((h->n + 255) / 256, 592)), 256, 0, h->stream>>>(h->scratch_i, bad, h->n, d_bcols);
+    h->launches_all += 3;
     std::vector<int> tmp(h->m);
     CU(cudaMemcpyAsync(tmp.data(), d_bcols, (size_t)h->m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));

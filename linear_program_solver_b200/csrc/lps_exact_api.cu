@@ -437,7 +437,7 @@ int lpsx_is_canonical(lps_handle* h, int* bcols, int* canonical) {
     int* d_bcols = nullptr;
     CU(cudaMalloc(&d_bcols, (size_t)h->m * sizeof(int)));
     CU(cudaMemsetAsync(d_bcols, 0x7f, (size_t)h->m * sizeof(int), h->stream));
-    k_canon_rows<<<std::max(1, std::min((h->n + 255) / 256, 592)), 256, 0, h->stream>>>(h->scratch_i, h->n, d_bcols);
+    k_canon_rows<<<std::max(1, std::min((h->n + 255) / 256, 592)), 256, 0, h->stream>>>(h->scratch_i, nullptr, h->n, d_bcols);
     h->launches_all += 4;
     std::vector<int> tmp(h->m);
     CU(cudaMemcpyAsync(tmp.data(), d_bcols, (size_t)h->m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));

@@ -574,19 +574,29 @@ __global__ void k_gather_col_f64(F64Grid g, int j, double* out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= g.m; i += gridDim.x * blockDim.x) out[i] = g.T[(size_t)i * g.ld + j];
 }
 
-// Tableau.isCanonical (tableau.py:466-496), column scan.  One thread per column walks the rows
-// (coalesced across the warp).  colrow[j] = row of the single exact 1 if column j is basic, else -1.
-__global__ void k_canon_cols_f64(F64Grid g, int* colrow) {
+// Tableau.isCanonical (tableau.py:466-496), column scan over a (column block) x (row slab) grid.  A column is basic
+// when its cost is exactly 0 and it holds one exact 1 and zeros elsewhere.  colrow[j] = row of the 1 (claimed with a
+// compare-and-swap, a second claim spoils the column), bad[j] != 0 once the column is known not to be basic -- the
+// other slabs of a dense column then stop after one probe, so the scan reads little more than the basic columns.
+__global__ void k_canon_init_f64(F64Grid g, int* colrow, int* bad) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= g.n) return;
+    colrow[j] = -1;
+    bad[j] = !(g.T[(size_t)g.m * g.ld + j] == 0.0);
+}
+__global__ void k_canon_cols_f64(F64Grid g, int rows_per_slab, int* colrow, int* bad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.n) return;
+    const int i0 = blockIdx.y * rows_per_slab, i1 = min(g.m, i0 + rows_per_slab);
     int hit = -1;
-    bool clean = (g.T[(size_t)g.m * g.ld + j] == 0.0);
-    for (int i = 0; clean && i < g.m; ++i) {
+    for (int i = i0; i < i1; ++i) {
+        if (((i - i0) & 15) == 0 && __ldcg(&bad[j])) return;
         const double v = g.T[(size_t)i * g.ld + j];
         if (v == 0.0) continue;
-        if (v == 1.0 && hit == -1) hit = i; else clean = false;
+        if (v == 1.0 && hit == -1) hit = i;
+        else { bad[j] = 1; return; }
     }
-    colrow[j] = (clean && hit != -1) ? hit : -1;
+    if (hit != -1 && atomicCAS(&colrow[j], -1, hit) != -1) bad[j] = 1;
 }
 // any b_i < 0 ?  (tableau.py:476-477)
 __global__ void k_any_neg_rhs_f64(F64Grid g, int* flag) {
@@ -596,9 +606,9 @@ __global__ void k_any_neg_rhs_f64(F64Grid g, int* flag) {
     if (__any_sync(0xffffffffu, neg) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 // bcols[i] = lowest basic column of row i (tableau.py:490-495)
-__global__ void k_canon_rows(const int* colrow, int n, int* bcols) {
+__global__ void k_canon_rows(const int* colrow, const int* bad, int n, int* bcols) {
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const int i = colrow[j];
+        const int i = (bad && bad[j]) ? -1 : colrow[j];
         if (i >= 0) atomicMin(&bcols[i], j);
     }
 }

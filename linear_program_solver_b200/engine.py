@@ -139,8 +139,11 @@ class F64Engine:
             return "unbounded"
         return r.value, c.value
 
-    def is_canonical(self, want_cols: bool = True):
-        cols = np.full(self.m, -1, dtype=np.int32)
+    def is_canonical(self, want_cols: bool = True, cols: Optional[np.ndarray] = None):
+        """(canonical?, bcols).  The library leaves bcols untouched when some b_i < 0 (tableau.py:476-477): pass
+        `cols` pre-filled to tell."""
+        if cols is None:
+            cols = np.full(self.m, -1, dtype=np.int32)
         flag = c_int(0)
         N.check(self.L.lps_is_canonical(self.h, cols.ctypes.data if want_cols else None, byref(flag)))
         return bool(flag.value), cols

@@ -439,7 +439,7 @@ class Tableau:
             self._host_row_axpy(rd, rs, mult)
 
     def rowSub(self, rd: int, rs: int, m: Any = 1):
-        self.rowAdd(rd, rs, -self._num(m))
+        self.rowAdd(rd, rs, -m)            # negated before coercion, like tableau.py:278-280 (a str raises TypeError)
 
     def rowAddToObj(self, r: int, m: Any = 1):
         mult = self._num(m)
@@ -452,7 +452,7 @@ class Tableau:
             self._host_row_axpy(self._m, r, mult)
 
     def rowSubFromObj(self, r: int, m: Any = 1):
-        self.rowAddToObj(r, -self._num(m))
+        self.rowAddToObj(r, -m)            # tableau.py:291-293
 
     def pivot(self, r: int, c: int):
         """simplex pivot on (r, c), assuming nothing about the tableau (tableau.py:295-308)"""
@@ -564,8 +564,9 @@ class Tableau:
     def isCanonical(self, bcols: Optional[List[int]] = None) -> bool:
         """canonical form?  bcols[i] receives the lowest basic column of row i or -1; it is left
         untouched when some b_i < 0 (tableau.py:476-477).  Runs on the device."""
-        ok, cols = self._need_dev().is_canonical()
-        if cols is not None and bcols is not None:
+        cols = np.full(self._m, -2, dtype=np.int32)          # -2: not written by the library
+        ok, cols = self._need_dev().is_canonical(cols=cols)
+        if bcols is not None and not (cols == -2).all():
             for i in range(self._m):
                 bcols[i] = int(cols[i])
         return ok
