@@ -43,6 +43,7 @@ extern "C" {
 #define LPS_INFEASIBLE       7   /* simplex.py:64-67 ValueError('infeasible problem, artificial opt = z') */
 #define LPS_REDUNDANT_ROW    8   /* simplex.py:84-93 dependent row dropped: the reference then fails with IndexError */
 #define LPS_NEED_ARTIFICIALS 9   /* batched solve: more artificial columns needed than the batch reserved */
+#define LPS_NEED_PRIMES     10   /* exact mode, internal: the pending pivot needs a larger working prime set */
 #define LPS_E_INVALID    -1   /* bad argument                                              */
 #define LPS_E_CUDA       -2   /* CUDA runtime error, see lps_last_error()                  */
 #define LPS_E_NOMEM      -3
@@ -182,6 +183,17 @@ int lps_upload_exact(lps_handle *h, const uint32_t *limbs, int nlimbs, const uns
 int lps_read_exact(lps_handle *h, int what, int index, signed char *sign_out, uint32_t *digits_out);
 int lps_read_alive(lps_handle *h, int *alive);   /* m+1 flags: row still carries its sigma_i */
 int lps_exact_info(lps_handle *h, int *nprimes, int *bad_prime, size_t *residue_bytes);
+/* Working prime set.  lps_create_exact allocates the primes a static Hadamard bound of the uploaded matrix asks for;
+ * the numbers of a tableau are minors over the CURRENT basis columns only, usually far smaller.  After
+ * lps_exact_set_weights (right after lps_upload_exact; wcol[j] >= 256 log2 of the 2-norm of column j of the uploaded
+ * integer matrix over all m+1 rows, j = 0..n; guard_bits covers the row scales) every kernel runs on a prefix of
+ * the primes sized by the product of the current basis columns' norms, and the library extends the prefix on the
+ * device (Garner + Horner, no host round trip of the tableau) before a pivot that would not fit.  Results are
+ * unchanged -- the residues are those of the same integers.  lps_exact_working reports the prefix length, the
+ * allocated primes and the number of extensions so far.  lps_exact_info's nprimes / residue_bytes describe the
+ * working set. */
+int lps_exact_set_weights(lps_handle *h, const int *wcol, int guard_bits);
+int lps_exact_working(lps_handle *h, int *working, int *allocated, int *extensions);
 /* Loop state of Simplex.solve (simplex.py:117-137: rule in force, stuck counter, whether the
  * objective has moved since entry, pending objective check).  set == 0 reads it; set != 0 writes it
  * and makes the next lps_solve continue from it (resuming after LPS_BAD_PRIME on a re-encoded

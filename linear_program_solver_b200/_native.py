@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblps_b200.so")
 
 OK, OPTIMAL, UNBOUNDED, ZERO_PIVOT, MAX_PIVOTS, BAD_PRIME, STALLED = 0, 1, 2, 3, 4, 5, 6
-INFEASIBLE, REDUNDANT_ROW, NEED_ARTIFICIALS = 7, 8, 9
+INFEASIBLE, REDUNDANT_ROW, NEED_ARTIFICIALS, NEED_PRIMES = 7, 8, 9, 10
 E_INVALID, E_CUDA, E_NOMEM, E_STATE, E_PEER = -1, -2, -3, -4, -5
 RULE_DANTZIG, RULE_BLAND = 0, 1
 
@@ -67,6 +67,8 @@ SIGNATURES = {
     "lps_read_exact": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lps_read_alive": (c_int, [c_void_p, c_void_p]),
     "lps_exact_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
+    "lps_exact_set_weights": (c_int, [c_void_p, c_void_p, c_int]),
+    "lps_exact_working": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "lps_exact_loop_state": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_longlong), POINTER(c_int), POINTER(c_int)]),
     "lps_batch_smem_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "lps_batch_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_int, POINTER(c_int), POINTER(c_double)]),

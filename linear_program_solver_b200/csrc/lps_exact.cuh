@@ -63,9 +63,10 @@ __host__ __device__ inline uint32_t minv_mont(uint32_t a_m, const PrimeQ& p) {
 struct XGrid {
     uint32_t* R;             // [P][(m+1)][ld]
     size_t ld, plane;        // plane = (m+1) * ld
-    int m, n, P;
-    const PrimeQ* pr;        // [P]
-    const uint32_t* invtab;  // [P][P]: invtab[j*P+k] = Montgomery form of p_j^-1 mod p_k  (j < k)
+    int m, n, P;             // P = primes of the WORKING set (a prefix of the allocated set, see XState::wlimit)
+    int Pld;                 // allocated primes = row stride of invtab
+    const PrimeQ* pr;        // [Pld]
+    const uint32_t* invtab;  // [Pld][Pld]: invtab[j*Pld+k] = Montgomery form of p_j^-1 mod p_k  (j < k)
     const uint32_t* half;    // [P] mixed-radix digits of (M-1)/2
     const double* wmant;     // [P+1] W_t = prod_{k<t} p_k = wmant[t] * 2^wexp[t], wmant in [0.5,1)
     const int* wexp;
@@ -86,6 +87,13 @@ struct XState {
     int last_r, last_c;
     int bad_prime;           // index of a prime dividing the pivot, or -1
     int obj_increased;       // a Dantzig pivot raised the objective above its value at entry (simplex.py:133)
+    // Working prime set.  Every entry of the tableau (and D) is, up to sign, a minor of the uploaded integer matrix
+    // whose columns are the last pivot columns of the rows pivoted since the upload plus at most one more column
+    // (two for the tie-break quantity, an entry one pivot away), so |entry| <= product of those columns' 2-norms
+    // (Hadamard).  wsum = sum over those rows of w[column], w = ceil(256 log2 norm); a pivot is applied only while
+    // wnext <= wlimit = 256 (bits of the working set) - 2 max w - guard; otherwise LPS_NEED_PRIMES is reported with
+    // nothing modified and the host extends the working set (k_xextend) before the loop continues.
+    long long wsum, wnext, wlimit;
 };
 
 struct XMeta {               // per reconstructed number
@@ -159,7 +167,7 @@ __device__ __forceinline__ void block_garner(const XGrid& g, uint32_t (&t)[SPT][
             if ((((d | (d >> NB)) & ((1u << NB) - 1u)) == ((1u << NB) - 1u))) break;
             if (tid == 0) S.done[((j >> 2) + 2) % 3] = 0xffffffffu;   // slot of the vote after next; last read before this round's barrier
         }
-        const uint32_t* invrow = g.invtab + (size_t)j * P;
+        const uint32_t* invrow = g.invtab + (size_t)j * g.Pld;
 #pragma unroll
         for (int s = 0; s < SPT; ++s) {
             const int k = tid + s * bd;
@@ -316,6 +324,73 @@ __global__ void __launch_bounds__(kLaneThreads) k_garner(XGrid g, const XState* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Extension of the working prime set from g.P to Pnew primes: every number is reconstructed from its residues
+// modulo the first g.P primes (Garner, with the early exit) and evaluated modulo each new prime by Horner's rule
+// on its mixed-radix digits, x = d_0 + p_0 (d_1 + p_1 (d_2 + ...)).  Source and destination are the residue
+// planes (vec == NULL: entry e = i (n+1) + j of the grid, rows 0..m, columns 0..n) or a vector with one number
+// per prime (vec[k], e.g. the denominator D).  Dynamic shared memory: NB * g.P words.
+// ------------------------------------------------------------------------------------------------
+template <int NB, int SPT>
+__global__ void __launch_bounds__(kLaneThreads) k_xextend(XGrid g, int Pnew, uint32_t* vec, long long count) {
+    extern __shared__ uint32_t s_dig[];
+    __shared__ GarnerShared<NB> S;
+    const int bd = blockDim.x, tid = threadIdx.x, P = g.P, ncol = g.n + 1;
+    const long long e0 = (long long)blockIdx.x * NB;
+    uint32_t t[SPT][NB];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        const int k = tid + s * bd;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const long long e = e0 + b;
+            uint32_t v = 0u;
+            if (k < P && e < count) {
+                if (vec) v = vec[k];
+                else {
+                    const long long i = e / ncol, j = e - i * ncol;
+                    v = g.R[(size_t)k * g.plane + (size_t)i * g.ld + j];
+                }
+            }
+            t[s][b] = v;
+        }
+    }
+    block_garner<NB, SPT>(g, t, S);
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        const int k = tid + s * bd;
+        if (k < P) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) s_dig[b * P + k] = t[s][b];
+        }
+    }
+    __syncthreads();
+    const int dP = Pnew - P;
+    for (int idx = tid; idx < NB * dP; idx += bd) {
+        const int b = idx / dP, kk = P + (idx - b * dP);
+        const long long e = e0 + b;
+        if (e >= count) continue;
+        const PrimeQ p = g.pr[kk];
+        const int top = S.top[b];
+        uint32_t acc = 0u;
+        if (top >= 0) {
+            const uint32_t* dg = s_dig + b * P;
+            acc = dg[top] % p.q;
+            for (int u = top - 1; u >= 0; --u) {
+                const uint32_t ptm = mmul(g.pr[u].q % p.q, p.r2, p.q, p.qinv);   // Montgomery form of p_u mod q
+                acc = mmul(acc, ptm, p.q, p.qinv) + dg[u] % p.q;                 // acc p_u + d_u
+                if (acc >= p.q) acc -= p.q;
+            }
+            if (S.neg[b] && acc) acc = p.q - acc;
+        }
+        if (vec) vec[kk] = acc;
+        else {
+            const long long i = e / ncol, j = e - i * ncol;
+            g.R[(size_t)kk * g.plane + (size_t)i * g.ld + j] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pricing on the reconstructed objective row (single block)
 // ------------------------------------------------------------------------------------------------
 // exact comparison of |x_a| and |x_b| from their mixed-radix digits: >0 if |x_a| > |x_b|
@@ -456,6 +531,8 @@ struct XRatioArgs {
     XMeta cr;                // 2(m+1) numbers: column c rows 0..m, then rhs rows 0..m
     XPivotConst pc;
     int* cand;               // m ints of scratch
+    const int* wcol;         // [n+1] column weights, NULL: fixed prime set
+    const int* xbasis;       // [m] last pivot column of each row since the upload, -1: never pivoted
 };
 
 template <int SPT>
@@ -562,6 +639,16 @@ __global__ void __launch_bounds__(kLaneThreads) k_xratio(XRatioArgs a) {
         if (tid == 0) { st->last_r = r; st->last_c = c; st->r = r; }
         return;
     }
+    if (a.wcol) {                                                // room in the working prime set for this pivot?
+        const int old = a.xbasis[r];
+        const long long wn = st->wsum + a.wcol[c] - (old >= 0 ? a.wcol[old] : 0);
+        if (wn > st->wlimit) {                                   // block-uniform: nothing has been modified yet
+            __syncthreads();
+            if (tid == 0) { st->r = r; st->wnext = wn; st->status = LPS_NEED_PRIMES; }
+            return;
+        }
+        if (tid == 0) st->wnext = wn;
+    }
     const int bad = compute_alpha(g, a.pc, r, c, &s_flag);
     if (tid == 0) {
         st->r = r;
@@ -573,7 +660,8 @@ __global__ void __launch_bounds__(kLaneThreads) k_xratio(XRatioArgs a) {
 
 // Explicit pivot (Tableau.pivot(r,c)): sign / zero test of N_rc, pivot constants.
 template <int SPT>
-__global__ void __launch_bounds__(kLaneThreads) k_xforced(XGrid g, XState* st, XPivotConst pc, int r, int c) {
+__global__ void __launch_bounds__(kLaneThreads) k_xforced(XGrid g, XState* st, XPivotConst pc, int r, int c, const int* wcol,
+                                                          const int* xbasis) {
     __shared__ GarnerShared<1> S;
     __shared__ int s_flag;
     const int tid = threadIdx.x;
@@ -588,6 +676,16 @@ __global__ void __launch_bounds__(kLaneThreads) k_xforced(XGrid g, XState* st, X
     if (sg == 0) {
         if (tid == 0) st->status = LPS_ZERO_PIVOT;
         return;
+    }
+    if (wcol) {
+        const int old = xbasis[r];
+        const long long wn = st->wsum + wcol[c] - (old >= 0 ? wcol[old] : 0);
+        if (wn > st->wlimit) {
+            __syncthreads();
+            if (tid == 0) { st->r = r; st->c = c; st->wnext = wn; st->status = LPS_NEED_PRIMES; }
+            return;
+        }
+        if (tid == 0) st->wnext = wn;
     }
     compute_dinv(g, pc);
     __syncthreads();
@@ -631,6 +729,7 @@ struct XUpdateArgs {
     int* trace;
     long long trace_cap;
     int* alive;              // per row: sigma_i still applies (row not pivoted since the upload)
+    int* xbasis;             // [m] last pivot column per row since the upload (working prime set), or NULL
     int commit;
 };
 
@@ -710,6 +809,7 @@ __global__ void __launch_bounds__(kXThreads) k_xupdate(XUpdateArgs a) {
         st->last_r = r; st->last_c = c;
         st->sgnD = st->sgn_p;
         a.alive[r] = 0;
+        if (a.xbasis) { a.xbasis[r] = c; st->wsum = st->wnext; }
         if (a.commit) {                                          // Simplex._pivot simplex.py:192-197
             const long long kk = st->npiv;
             if (a.trace && kk < a.trace_cap) { a.trace[3 * kk] = r; a.trace[3 * kk + 1] = c; a.trace[3 * kk + 2] = st->sel_rule; }

@@ -11,7 +11,15 @@
 #include "lps_exact.cuh"
 
 struct ExactData {
-    int P = 0, spt = 1, lane_threads = 1024;
+    int P = 0, spt = 1, lane_threads = 1024;   // P: primes of the working set (all kernels run on these)
+    int Pcap = 0;                               // allocated primes (sized by the caller's static bound)
+    std::vector<uint32_t> primes_h;             // host copies for the working-set arithmetic
+    std::vector<int> wexp_h;
+    int* wcol = nullptr;                        // device [n+1] column weights (NULL until lps_exact_set_weights)
+    int* xbasis = nullptr;                      // device [m] last pivot column per row since the upload
+    bool adaptive = false;
+    long long wmax256 = 0, guard256 = 0;
+    int grows = 0;
     PrimeQ* pr = nullptr;
     uint32_t* invtab = nullptr;
     uint32_t* half = nullptr;
@@ -41,7 +49,7 @@ struct ExactData {
 static XGrid xgrid_of(const lps_handle* h) {
     const ExactData* x = h->x;
     XGrid g;
-    g.R = x->R; g.ld = x->ld; g.plane = x->plane; g.m = h->m; g.n = h->n; g.P = x->P;
+    g.R = x->R; g.ld = x->ld; g.plane = x->plane; g.m = h->m; g.n = h->n; g.P = x->P; g.Pld = x->Pcap;
     g.pr = x->pr; g.invtab = x->invtab; g.half = x->half; g.wmant = x->wmant; g.wexp = x->wexp;
     return g;
 }
@@ -91,7 +99,8 @@ extern "C" int lps_create_exact(int m, int n, int nprimes, const uint32_t* prime
     if (stream) h->stream = (cudaStream_t)stream;
     else { CUX(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
     const int P = nprimes;
-    x->P = P;
+    x->P = P; x->Pcap = P;
+    x->primes_h.assign(primes, primes + P);
     x->spt = P <= 1024 ? 1 : kMaxSPT;
     x->lane_threads = P <= 1024 ? std::max(32, (P + 31) / 32 * 32) : 1024;
     x->ld = lps_exact_ld(n);
@@ -123,6 +132,7 @@ extern "C" int lps_create_exact(int m, int n, int nprimes, const uint32_t* prime
             wm[t] = (double)mant; we[t] = ex;
         }
     }
+    x->wexp_h = we;
     CUX(cudaMalloc(&x->pr, P * sizeof(PrimeQ)));
     CUX(cudaMemcpyAsync(x->pr, pr.data(), P * sizeof(PrimeQ), cudaMemcpyHostToDevice, h->stream));
     CUX(cudaMalloc(&x->half, P * sizeof(uint32_t)));
@@ -167,6 +177,8 @@ extern "C" int lps_create_exact(int m, int n, int nprimes, const uint32_t* prime
     CUX(cudaMalloc(&x->obj_dig, (size_t)P * x->obj_dstride * sizeof(uint32_t)));
     CUX(cudaMalloc(&x->rd_dig, (size_t)P * x->rd_stride * sizeof(uint32_t)));
     CUX(cudaMalloc(&x->cand, (size_t)m * sizeof(int)));
+    CUX(cudaMalloc(&x->wcol, ((size_t)n + 1) * sizeof(int)));
+    CUX(cudaMalloc(&x->xbasis, (size_t)m * sizeof(int)));
     CUX(cudaMalloc(&x->st, sizeof(XState)));
     CUX(cudaMallocHost(&x->st_host, sizeof(XState)));
     CUX(cudaMalloc(&h->basis, (size_t)m * sizeof(int)));
@@ -191,7 +203,7 @@ int lpsx_destroy(lps_handle* h) {
         cudaFree(x->obj_sign); cudaFree(x->obj_top); cudaFree(x->obj_mant); cudaFree(x->obj_dig);
         cudaFree(x->cr_sign); cudaFree(x->cr_top); cudaFree(x->cr_mant);
         cudaFree(x->rd_sign); cudaFree(x->rd_top); cudaFree(x->rd_mant); cudaFree(x->rd_dig);
-        cudaFree(x->cand); cudaFree(x->st);
+        cudaFree(x->cand); cudaFree(x->wcol); cudaFree(x->xbasis); cudaFree(x->st);
         if (x->st_host) cudaFreeHost(x->st_host);
         delete x;
     }
@@ -217,6 +229,106 @@ static int xwrite_state(lps_handle* h) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// working prime set (XState::wlimit): the first P of the Pcap allocated primes
+// ------------------------------------------------------------------------------------------------
+// bits (x 256) a number may have under the first P primes: |x| <= (M - 1) / 2, log2 M >= wexp[P] - 1
+static long long cap256(const ExactData* x, int P) { return 256LL * ((long long)x->wexp_h[P] - 2); }
+
+static int set_working(lps_handle* h, int P) {
+    ExactData* x = h->x;
+    x->P = P;
+    x->spt = P <= 1024 ? 1 : kMaxSPT;
+    x->lane_threads = P <= 1024 ? std::max(32, (P + 31) / 32 * 32) : 1024;
+    std::vector<uint32_t> half(P);
+    uint64_t carry = 0;                                   // (M-1)/2 in the mixed radix (p_0, ..., p_(P-1))
+    for (int k = P - 1; k >= 0; --k) {
+        const uint64_t cur = carry * x->primes_h[k] + (x->primes_h[k] - 1u);
+        half[k] = (uint32_t)(cur / 2);
+        carry = cur & 1u;
+    }
+    CU(cudaMemcpyAsync(x->half, half.data(), P * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const size_t bytes = (size_t)P * x->plane * sizeof(uint32_t), cells = x->plane * P;
+    x->stream_hint = bytes > kL2Bytes;
+    if (cells >= (size_t)148 * 8 * 2048 * 64) { x->chunk = 2048; x->rows_per_cta = 64; }
+    else if (cells >= (size_t)148 * 4 * 1024 * 16) { x->chunk = 1024; x->rows_per_cta = 16; }
+    else { x->chunk = 1024; x->rows_per_cta = 8; }
+    return LPS_OK;
+}
+
+// smallest working set that leaves `head` (x 256 bits) of room above `need`
+static int pick_working(const ExactData* x, long long need, int at_least) {
+    const long long target = need + std::max(need / 2, 256LL * 96);
+    for (int P = std::max(1, at_least); P <= x->Pcap; ++P)
+        if (cap256(x, P) >= target) return P;
+    return x->Pcap;
+}
+static long long wlimit_of(const ExactData* x, int P) {
+    return P >= x->Pcap ? (1LL << 62) : cap256(x, P) - 2 * x->wmax256 - x->guard256;   // all primes: the static bound holds
+}
+
+template <int NB>
+static int launch_extend(lps_handle* h, int Pnew, uint32_t* vec, long long count) {
+    ExactData* x = h->x;
+    const size_t smem = (size_t)NB * x->P * sizeof(uint32_t);
+    const unsigned blocks = (unsigned)((count + NB - 1) / NB);
+    if (x->spt == 1) {
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_xextend<NB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_xextend<NB, 1><<<blocks, x->lane_threads, smem, h->stream>>>(xgrid_of(h), Pnew, vec, count);
+    } else {
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_xextend<NB, kMaxSPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_xextend<NB, kMaxSPT><<<blocks, x->lane_threads, smem, h->stream>>>(xgrid_of(h), Pnew, vec, count);
+    }
+    h->launches_all++;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+
+// LPS_NEED_PRIMES was reported (nothing modified): extend the working set so that the pending pivot fits, with
+// head-room, and clear the status.  The residues modulo the new primes are computed on the device.
+static int grow_working(lps_handle* h) {
+    ExactData* x = h->x;
+    TRY(xread_state(h));
+    XState& s = *x->st_host;
+    const long long need = s.wnext + 2 * x->wmax256 + x->guard256;
+    const int Pnew = pick_working(x, need, x->P + 1);
+    if (Pnew > x->P) {
+        TRY(launch_extend<4>(h, Pnew, nullptr, (long long)(h->m + 1) * (h->n + 1)));
+        TRY(launch_extend<4>(h, Pnew, x->Dres, 1));
+        TRY(set_working(h, Pnew));
+        x->grows++;
+    }
+    s.wlimit = wlimit_of(x, x->P);
+    s.status = LPS_OK;
+    TRY(xwrite_state(h));
+    return LPS_OK;
+}
+
+// Column weights of the uploaded integer matrix (wcol[j] >= 256 log2 of the 2-norm of column j over all m+1 rows,
+// j = 0..n) and the guard (bits x 256: row scales sigma_i and rounding slack).  Switches the handle to the smallest
+// working set that holds the uploaded matrix with head-room; pivots then extend it on demand.  Call right after
+// lps_upload_exact; without it every kernel runs on all the primes of lps_create_exact.
+extern "C" int lps_exact_set_weights(lps_handle* h, const int* wcol, int guard_bits) {
+    USE(h);
+    NEED_MODE(h, 1);
+    ExactData* x = h->x;
+    if (!wcol || guard_bits < 0) return fail(LPS_E_INVALID, "bad weights");
+    long long wmax = 0;
+    for (int j = 0; j <= h->n; ++j) {
+        if (wcol[j] < 0) return fail(LPS_E_INVALID, "negative weight");
+        wmax = std::max<long long>(wmax, wcol[j]);
+    }
+    x->wmax256 = wmax; x->guard256 = 256LL * guard_bits; x->adaptive = true; x->grows = 0;
+    CU(cudaMemcpyAsync(x->wcol, wcol, ((size_t)h->n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(x->xbasis, 0xff, (size_t)h->m * sizeof(int), h->stream));
+    TRY(set_working(h, pick_working(x, 2 * wmax + x->guard256, 1)));
+    TRY(xread_state(h));
+    x->st_host->wsum = 0; x->st_host->wnext = 0; x->st_host->wlimit = wlimit_of(x, x->P);
+    TRY(xwrite_state(h));
+    return LPS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // upload / read-out
 // ------------------------------------------------------------------------------------------------
 extern "C" int lps_upload_exact(lps_handle* h, const uint32_t* limbs, int nlimbs, const unsigned char* neg, size_t ld_host,
@@ -226,6 +338,8 @@ extern "C" int lps_upload_exact(lps_handle* h, const uint32_t* limbs, int nlimbs
     ExactData* x = h->x;
     if (!limbs || !neg || nlimbs <= 0 || ld_host < (size_t)h->n + 1) return fail(LPS_E_INVALID, "bad host grid");
     if (!sigma_limbs || sigma_nlimbs <= 0) return fail(LPS_E_INVALID, "bad row scales");
+    x->adaptive = false;
+    TRY(set_working(h, x->Pcap));                        // encode for every allocated prime
     const size_t entries = (size_t)(h->m + 1) * ld_host;
     uint32_t* d_limbs = nullptr;
     unsigned char* d_neg = nullptr;
@@ -248,6 +362,7 @@ extern "C" int lps_upload_exact(lps_handle* h, const uint32_t* limbs, int nlimbs
     CU(cudaMemcpyAsync(x->alive, alive.data(), alive.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     XState s{};
     s.status = LPS_OK; s.max_pivots = -1; s.sgnD = 1; s.c = s.r = s.last_r = s.last_c = -1; s.bad_prime = -1;
+    s.wlimit = 1LL << 62;
     *x->st_host = s;
     CU(cudaMemcpyAsync(x->st, x->st_host, sizeof(XState), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -313,6 +428,15 @@ extern "C" int lps_exact_info(lps_handle* h, int* nprimes, int* bad_prime, size_
     return LPS_OK;
 }
 
+extern "C" int lps_exact_working(lps_handle* h, int* working, int* allocated, int* extensions) {
+    USE(h);
+    NEED_MODE(h, 1);
+    if (working) *working = h->x->P;
+    if (allocated) *allocated = h->x->Pcap;
+    if (extensions) *extensions = h->x->grows;
+    return LPS_OK;
+}
+
 // Loop state of Simplex.solve (rule, stuck counter, "objective moved", pending objective check):
 // set == 0 reads it; set != 0 writes it and makes the next lps_solve continue from it instead of
 // starting over (used when a solve is resumed on a re-encoded tableau after LPS_BAD_PRIME).
@@ -345,7 +469,7 @@ static int xlaunch_select(lps_handle* h) {
     cj.src = XSRC_COLPAIR; cj.index = -1; cj.count = 2 * (h->m + 1); cj.check_status = 1;
     cj.meta = XMeta{x->cr_sign, x->cr_top, x->cr_mant};
     TRY(launch_garner<8>(h, cj));
-    XRatioArgs ra{xgrid_of(h), x->st, cj.meta, pconst_of(h), x->cand};
+    XRatioArgs ra{xgrid_of(h), x->st, cj.meta, pconst_of(h), x->cand, x->adaptive ? x->wcol : nullptr, x->xbasis};
     if (x->spt == 1) k_xratio<1><<<1, kLaneThreads, 0, h->stream>>>(ra);
     else k_xratio<kMaxSPT><<<1, kLaneThreads, 0, h->stream>>>(ra);
     h->launches_all += 2;
@@ -360,7 +484,7 @@ static int xlaunch_apply(lps_handle* h, int commit) {
     XUpdateArgs a;
     a.g = g; a.st = x->st; a.alpha_m = x->alpha_m; a.nbeta = x->nbeta; a.nbeta_ld = x->nbeta_ld;
     a.rows_per_cta = x->rows_per_cta; a.basis = h->basis; a.marks = h->use_marks ? h->marks : nullptr;
-    a.trace = h->trace; a.trace_cap = h->trace_cap; a.alive = x->alive; a.commit = commit;
+    a.trace = h->trace; a.trace_cap = h->trace_cap; a.alive = x->alive; a.xbasis = x->adaptive ? x->xbasis : nullptr; a.commit = commit;
     dim3 grid((unsigned)((x->ld + x->chunk - 1) / x->chunk), (unsigned)((h->m + 1 + x->rows_per_cta - 1) / x->rows_per_cta), (unsigned)x->P);
     const bool timed = h->prof && h->ev_used + 2 <= h->ev.size();
     if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
@@ -387,12 +511,17 @@ int lpsx_pivot(lps_handle* h, int r, int c) {
     TRY(xread_state(h));
     x->st_host->status = LPS_OK; x->st_host->dry_run = 0; x->st_host->bad_prime = -1;
     TRY(xwrite_state(h));
-    if (x->spt == 1) k_xforced<1><<<1, kLaneThreads, 0, h->stream>>>(xgrid_of(h), x->st, pconst_of(h), r, c);
-    else k_xforced<kMaxSPT><<<1, kLaneThreads, 0, h->stream>>>(xgrid_of(h), x->st, pconst_of(h), r, c);
-    h->launches_all++;
-    CU(cudaGetLastError());
-    TRY(xlaunch_apply(h, 0));
-    TRY(xread_state(h));
+    for (int attempt = 0;; ++attempt) {
+        const int* wc = x->adaptive ? x->wcol : nullptr;
+        if (x->spt == 1) k_xforced<1><<<1, kLaneThreads, 0, h->stream>>>(xgrid_of(h), x->st, pconst_of(h), r, c, wc, x->xbasis);
+        else k_xforced<kMaxSPT><<<1, kLaneThreads, 0, h->stream>>>(xgrid_of(h), x->st, pconst_of(h), r, c, wc, x->xbasis);
+        h->launches_all++;
+        CU(cudaGetLastError());
+        TRY(xlaunch_apply(h, 0));
+        TRY(xread_state(h));
+        if (x->st_host->status != LPS_NEED_PRIMES || attempt > 0) break;
+        TRY(grow_working(h));                            // nothing was modified: extend the working set, try again
+    }
     const int st = x->st_host->status;
     return (st == LPS_ZERO_PIVOT || st == LPS_BAD_PRIME) ? st : LPS_OK;
 }
@@ -484,6 +613,11 @@ int lpsx_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int*
         enqueued += now;
         if (now == 0) TRY(xlaunch_select(h));
         TRY(xread_state(h));
+        if (x->st_host->status == LPS_NEED_PRIMES) {     // the pending pivot needs a larger working prime set
+            enqueued = x->st_host->npiv;                 // the launches behind it were no-ops
+            TRY(grow_working(h));
+            continue;
+        }
         if (x->st_host->status != LPS_OK) break;
     }
     const long long k = x->st_host->npiv;

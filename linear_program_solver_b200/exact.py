@@ -98,6 +98,24 @@ def hadamard_bits_np(G: np.ndarray) -> int:
     return int(math.ceil(min(by_rows, by_cols))) + 3
 
 
+def column_weights(G) -> List[int]:
+    """w[j] >= 256 * log2 of the 2-norm of column j (all m+1 rows) of the integer matrix G (ndarray or nested
+    lists), 0 for a zero column: the weights of `lps_exact_set_weights`."""
+    import math
+    if isinstance(G, np.ndarray):
+        sq = (G.astype(np.float64) ** 2).sum(axis=0) * (1.0 + 1e-9)
+        out = np.zeros(G.shape[1], dtype=np.int64)
+        nzc = sq > 0
+        out[nzc] = np.ceil(128.0 * np.log2(sq[nzc])).astype(np.int64) + 1
+        return [int(max(v, 0)) for v in out]
+    cols = len(G[0])
+    sums = [0] * cols
+    for row in G:
+        for j, v in enumerate(row):
+            sums[j] += v * v
+    return [0 if s == 0 else max(0, math.ceil(128.0 * math.log2(s) * (1.0 + 1e-12)) + 1) for s in sums]
+
+
 def primes_for_bits(bits: int, skip: Sequence[int] = ()) -> List[int]:
     """Enough primes that their product exceeds 2^(bits+2): symmetric range plus one guard bit."""
     need = bits + 2
@@ -182,6 +200,7 @@ class ExactEngine:
         self.banned: List[int] = []
         self.reencodes = 0
         self.last_bits = 0
+        self.adaptive = True          # False: every kernel runs on all the primes the static bound asks for
 
     # -- lifetime ------------------------------------------------------------------------------
     def _create(self, primes: Sequence[int]):
@@ -212,6 +231,7 @@ class ExactEngine:
         """grid: (m+1) x (n+1) Fractions / ints in device layout, or an int64 numpy array."""
         if isinstance(grid, np.ndarray) and grid.dtype.kind in "iu":
             G = np.ascontiguousarray(grid, dtype=np.int64)
+            ints = None
             bits = hadamard_bits_np(G)
             sigma = [1] * (self.m + 1)
             mags = np.abs(G).astype(np.uint64)
@@ -222,12 +242,14 @@ class ExactEngine:
                 limbs[..., 1] = (mags >> np.uint64(32)).astype(np.uint32)
             neg = (G < 0).astype(np.uint8)
         else:
+            G = None
             rows = [[x if isinstance(x, Fraction) else Fraction(x) for x in row] for row in grid]
             ints, sigma = clear_denominators(rows)
             bits = hadamard_bits(ints)
             flat = [v for row in ints for v in row]
             limbs, neg, nl = to_limbs(flat)
-        bits += max(s.bit_length() for s in sigma)       # "== 1" tests compare with D * sigma_i
+        sigma_bits = max(s.bit_length() for s in sigma)
+        bits += sigma_bits                               # "== 1" tests compare with D * sigma_i
         self.last_bits = bits
         primes = self.forced_primes if self.forced_primes is not None else primes_for_bits(bits, self.banned)
         if self.h is None or primes != self.primes:
@@ -237,10 +259,14 @@ class ExactEngine:
         N.check(self.L.lps_upload_exact(self.h, limbs.ctypes.data, nl, np.ascontiguousarray(neg).ctypes.data, self.n + 1,
                                         sl.ctypes.data, snl))
         self.sigma = sigma
+        if self.adaptive and self.forced_primes is None:
+            # working prime set: sized by the norms of the current basis columns, extended on the device on demand
+            wcol = np.ascontiguousarray(column_weights(G if G is not None else ints), dtype=np.int32)
+            N.check(self.L.lps_exact_set_weights(self.h, wcol.ctypes.data, sigma_bits + 3))
 
     def _read(self, what: int, index: int, count: int) -> List[int]:
         sign = np.empty(count, dtype=np.int8)
-        digits = np.empty((len(self.primes), count), dtype=np.uint32)
+        digits = np.zeros((len(self.primes), count), dtype=np.uint32)     # rows beyond the working set stay 0
         N.check(self.L.lps_read_exact(self.h, what, index, sign.ctypes.data, digits.ctypes.data))
         return self.codec.decode(sign, digits)
 
@@ -280,7 +306,10 @@ class ExactEngine:
     def info(self):
         p, bad, nbytes = c_int(0), c_int(-1), c_size_t(0)
         N.check(self.L.lps_exact_info(self.h, byref(p), byref(bad), byref(nbytes)))
-        return {"primes": p.value, "bad_prime": bad.value, "residue_bytes": nbytes.value, "bound_bits": self.last_bits}
+        w, a, g = c_int(0), c_int(0), c_int(0)
+        N.check(self.L.lps_exact_working(self.h, byref(w), byref(a), byref(g)))
+        return {"primes": p.value, "bad_prime": bad.value, "residue_bytes": nbytes.value, "bound_bits": self.last_bits,
+                "allocated_primes": a.value, "extensions": g.value}
 
     # -- re-encoding when a prime divides a pivot element -----------------------------------------
     def _reencode(self):

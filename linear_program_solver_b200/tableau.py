@@ -56,6 +56,7 @@ class Tableau:
         self._eng = None
         self._host_ok, self._dev_ok = True, False
         self._peek: dict = {}
+        self._int_grid = None        # exact mode, from_grid(integer ndarray): uploaded as is, Fractions only on demand
 
     # -- number handling -----------------------------------------------------------------
     def _num(self, x):
@@ -94,19 +95,24 @@ class Tableau:
 
     def _need_host(self):
         if not self._host_ok:
-            self._grid = self._eng.download()
+            if self._int_grid is not None and not self._dev_ok:
+                self._grid = [[Fraction(int(x)) for x in row] for row in self._int_grid]
+            else:
+                self._grid = self._need_dev().download()
+            self._int_grid = None
             self._host_ok = True
 
     def _touch_host(self):
         """About to edit the host copy: it becomes the only valid one."""
         self._need_host()
         self._dev_ok = False
+        self._int_grid = None
         self._peek.clear()
 
     def _need_dev(self):
         eng = self._engine()
         if not self._dev_ok:
-            eng.upload(self._grid)
+            eng.upload(self._grid if self._host_ok else self._int_grid)
             self._dev_ok = True
         return eng
 
@@ -114,6 +120,7 @@ class Tableau:
         """About to edit the device copy."""
         eng = self._need_dev()
         self._host_ok = False
+        self._int_grid = None
         self._peek.clear()
         return eng
 
@@ -123,7 +130,7 @@ class Tableau:
             return self._grid[i]
         key = ("r", i)
         if key not in self._peek:
-            self._peek[key] = self._eng.read_row(i)
+            self._peek[key] = self._need_dev().read_row(i)
         return self._peek[key]
 
     def _col(self, j: int):
@@ -134,7 +141,7 @@ class Tableau:
             return [row[j] for row in self._grid]
         key = ("c", j)
         if key not in self._peek:
-            self._peek[key] = self._eng.read_col(j)
+            self._peek[key] = self._need_dev().read_col(j)
         return self._peek[key]
 
     # ------------------------------------------------------------------------------------
@@ -302,6 +309,11 @@ class Tableau:
         t = cls(rows - 1, cols - 1, mode, device)
         if mode == "fp64":
             t._grid = np.ascontiguousarray(grid, dtype=np.float64)
+        elif isinstance(grid, np.ndarray) and grid.dtype.kind in "iu":
+            # integer input goes to the device as it is; Fractions are only built if a host-side method asks
+            t._int_grid = np.ascontiguousarray(grid, dtype=np.int64)
+            t._grid = None
+            t._host_ok = False
         else:
             t._grid = [[x if isinstance(x, Fraction) else Fraction(x) for x in row] for row in grid]
         if names:

@@ -216,3 +216,50 @@ def test_prime_dividing_a_pivot_forces_a_reencode_and_keeps_the_answer():
     assert basis.tolist() == want["basis"]
     assert -e.read_row(8)[16] == want["objective"]
     e.close()
+
+
+# ---- working prime set (lps_exact_set_weights): same integers on a prefix of the primes ------------------------
+@pytest.mark.parametrize("m,seed,hi", [(24, 0, 9), (60, 1, 127), (120, 2, 127)])
+def test_working_prime_set_gives_the_same_integers_as_the_full_set(m, seed, hi):
+    from linear_program_solver_b200.exact import ExactEngine
+    c, A, b = problems.dense_lp(m, seed, 1, hi)
+    grid = np.array(problems.to_grid(c, A, b), dtype=np.int64)
+    runs = []
+    for adaptive in (True, False):
+        e = ExactEngine(m, 2 * m)
+        e.adaptive = adaptive
+        e.upload(grid)
+        info0 = e.info()
+        basis = np.arange(m, 2 * m, dtype=np.int32)
+        st, k, trace = e.solve(basis, None, trace_cap=1 << 14)
+        runs.append((st, k, trace.tolist(), basis.tolist(), e.integer_state(), info0, e.info()))
+        e.close()
+    (st_a, k_a, tr_a, bs_a, ints_a, i0_a, i1_a), (st_f, k_f, tr_f, bs_f, ints_f, i0_f, i1_f) = runs
+    assert (st_a, k_a, tr_a, bs_a) == (st_f, k_f, tr_f, bs_f)
+    assert ints_a == ints_f                                     # every N_ij and D, as Python ints
+    assert i0_f["primes"] == i0_f["allocated_primes"] == i1_f["primes"] and i1_f["extensions"] == 0
+    assert i0_a["primes"] < i0_a["allocated_primes"]            # starts on a short prefix ...
+    assert i0_a["primes"] <= i1_a["primes"] <= i1_a["allocated_primes"]
+    if m >= 60:                                                 # ... and grows once the basis holds enough dense columns
+        assert i1_a["extensions"] >= 1 and i0_a["primes"] < i1_a["primes"]
+
+
+def test_working_prime_set_covers_every_integer_of_a_solve():
+    """The bound behind the working set: |entry| <= product of the norms of the basis columns and two more."""
+    import math
+    from linear_program_solver_b200.exact import column_weights
+    from oracle import lpsol_oracle as O
+    m = 12
+    c, A, b = problems.dense_lp(m, 5, 1, 99)
+    grid = [list(map(int, row)) for row in problems.to_grid(c, A, b)]
+    w = column_weights(grid)
+    assert w == column_weights(np.array(grid, dtype=np.int64)) or all(abs(x - y) <= 1 for x, y in zip(w, column_weights(np.array(grid, dtype=np.int64))))
+    N, D = [row[:] for row in grid], 1
+    xbasis = [-1] * m
+    want = O.simplex(c, A, b, num=Fraction)
+    for r, cc, _rule in want["pivots"]:
+        D = O.bareiss_pivot(N, D, r, cc)
+        xbasis[r] = cc
+        cap = sum(w[j] for j in xbasis if j >= 0) + max(w)
+        big = max(max(abs(v) for row in N for v in row), abs(D))
+        assert 256 * math.log2(big) <= cap

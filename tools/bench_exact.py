@@ -45,9 +45,11 @@ def main():
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     ms, nu, na = eng.prof_read()
-    P = info["primes"]
+    info_end = eng.info()
+    P = info_end["primes"]
     bytes_per = 8 * P * (m + 1) * (n + 1)
-    out = {"m": m, "n": n, "hi": a.hi, "primes": P, "bound_bits": info["bound_bits"], "residue_GB": info["residue_bytes"] / 1e9,
+    out = {"m": m, "n": n, "hi": a.hi, "primes": P, "primes_at_upload": info["primes"], "allocated_primes": info_end["allocated_primes"],
+           "extensions": info_end["extensions"], "bound_bits": info["bound_bits"], "residue_GB": info["residue_bytes"] / 1e9,
            "upload_s": up, "status": st, "pivots": k, "wall_s": wall, "pivots_per_s": k / wall,
            "update_ms_avg": ms / max(nu, 1), "update_launches_timed": nu, "launches": na,
            "update_GBps": bytes_per / (ms / max(nu, 1) * 1e-3) / 1e9 if nu else None,
