@@ -152,6 +152,11 @@ int lps_step_select(lps_handle *h);
 int lps_p2p_export(lps_handle *h, unsigned char *ipc_handle64);
 int lps_p2p_attach(lps_handle *h, long long row0, long long m_total, int rank, int nranks,
                    const unsigned char *ipc_handles);
+/* The same exchange for ranks living in one process (one thread driving several handles, on one or several
+ * GPUs): the blocks are passed as device pointers (lps_p2p_block of every rank, in rank order). */
+int lps_p2p_block(lps_handle *h, void **block);
+int lps_p2p_attach_local(lps_handle *h, long long row0, long long m_total, int rank, int nranks,
+                         void *const *blocks);
 int lps_step_update(lps_handle *h);
 int lps_solve_poll(lps_handle *h, int *status, long long *npiv);
 int lps_solve_end(lps_handle *h, int *basis, int *marks, int *trace, long long trace_cap,

@@ -59,6 +59,8 @@ SIGNATURES = {
     "lps_step_update": (c_int, [c_void_p]),
     "lps_p2p_export": (c_int, [c_void_p, c_void_p]),
     "lps_p2p_attach": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_void_p]),
+    "lps_p2p_block": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "lps_p2p_attach_local": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_void_p]),
     "lps_solve_poll": (c_int, [c_void_p, POINTER(c_int), POINTER(c_longlong)]),
     "lps_solve_end": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, POINTER(c_longlong)]),
     "lps_exact_ld": (c_size_t, [c_int]),

@@ -488,11 +488,26 @@ extern "C" int lps_p2p_export(lps_handle* h, unsigned char* ipc_handle64) {
     return LPS_OK;
 }
 
+static int attach_blocks(lps_handle* h, long long row0, long long m_total, int rank, int nranks, const std::vector<XchgBlock*>& peers) {
+    CU(cudaMemcpy(h->d_peers, peers.data(), (size_t)nranks * sizeof(XchgBlock*), cudaMemcpyHostToDevice));
+    h->row0 = row0; h->m_total = m_total; h->rank = rank; h->nranks = nranks;
+    h->use_xchg = (nranks > 1);          // one rank: k_select writes the normalised row itself, no exchange
+    CU(cudaFree(h->basis));
+    CU(cudaMalloc(&h->basis, (size_t)m_total * sizeof(int)));
+    CU(cudaMemsetAsync(h->basis, 0xff, (size_t)m_total * sizeof(int), h->stream));
+    return LPS_OK;
+}
+
+static int check_shard(lps_handle* h, long long row0, long long m_total, int rank, int nranks) {
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(LPS_E_INVALID, "bad rank %d of %d", rank, nranks);
+    if (row0 < 0 || row0 + h->m > m_total) return fail(LPS_E_INVALID, "rows [%lld,%lld) outside 0..%lld", row0, row0 + h->m, m_total);
+    return LPS_OK;
+}
+
 extern "C" int lps_p2p_attach(lps_handle* h, long long row0, long long m_total, int rank, int nranks, const unsigned char* ipc_handles) {
     USE(h);
     NEED_MODE(h, 0);
-    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(LPS_E_INVALID, "bad rank %d of %d", rank, nranks);
-    if (row0 < 0 || row0 + h->m > m_total) return fail(LPS_E_INVALID, "rows [%lld,%lld) outside 0..%lld", row0, row0 + h->m, m_total);
+    TRY(check_shard(h, row0, m_total, rank, nranks));
     if (nranks > 1 && !ipc_handles) return fail(LPS_E_INVALID, "null IPC handles");
     CU(cudaStreamSynchronize(h->stream));
     std::vector<XchgBlock*> peers(nranks, nullptr);
@@ -506,13 +521,39 @@ extern "C" int lps_p2p_attach(lps_handle* h, long long row0, long long m_total, 
         h->ipc_open.push_back(p);
         peers[k] = (XchgBlock*)p;
     }
-    CU(cudaMemcpy(h->d_peers, peers.data(), (size_t)nranks * sizeof(XchgBlock*), cudaMemcpyHostToDevice));
-    h->row0 = row0; h->m_total = m_total; h->rank = rank; h->nranks = nranks;
-    h->use_xchg = (nranks > 1);          // one rank: k_select writes the normalised row itself, no exchange launch
-    CU(cudaFree(h->basis));
-    CU(cudaMalloc(&h->basis, (size_t)m_total * sizeof(int)));
-    CU(cudaMemsetAsync(h->basis, 0xff, (size_t)m_total * sizeof(int), h->stream));
+    return attach_blocks(h, row0, m_total, rank, nranks, peers);
+}
+
+// Same exchange for ranks that live in ONE process (one thread driving several handles, on one or several GPUs):
+// the exchange blocks are passed as device pointers (lps_p2p_block of every rank, in rank order) instead of IPC
+// handles; peer access between the devices involved is enabled here.
+extern "C" int lps_p2p_block(lps_handle* h, void** block) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (!block) return fail(LPS_E_INVALID, "null output");
+    *block = h->xchg;
     return LPS_OK;
+}
+extern "C" int lps_p2p_attach_local(lps_handle* h, long long row0, long long m_total, int rank, int nranks, void* const* blocks) {
+    USE(h);
+    NEED_MODE(h, 0);
+    TRY(check_shard(h, row0, m_total, rank, nranks));
+    if (!blocks) return fail(LPS_E_INVALID, "null blocks");
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<XchgBlock*> peers(nranks, nullptr);
+    for (int k = 0; k < nranks; ++k) {
+        if (!blocks[k]) return fail(LPS_E_INVALID, "null block for rank %d", k);
+        cudaPointerAttributes at;
+        CU(cudaPointerGetAttributes(&at, blocks[k]));
+        if (at.device != h->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(LPS_E_CUDA, "no peer access from device %d to %d: %s", h->device, at.device, cudaGetErrorString(e));
+        }
+        peers[k] = (XchgBlock*)blocks[k];
+    }
+    if (peers[rank] != h->xchg) return fail(LPS_E_INVALID, "blocks[%d] is not this handle's block", rank);
+    return attach_blocks(h, row0, m_total, rank, nranks, peers);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -93,6 +93,20 @@ class F64Engine:
         N.check(self.L.lps_p2p_attach(self.h, row0, m_total, rank, nranks, handles.ctypes.data))
         self.row0, self.m_total, self.rank, self.nranks = row0, m_total, rank, nranks
 
+    def p2p_block(self) -> int:
+        """Device address of this engine's exchange block (ranks of one process: `p2p_attach_local`)."""
+        from ctypes import c_void_p
+        out = c_void_p()
+        N.check(self.L.lps_p2p_block(self.h, byref(out)))
+        return int(out.value)
+
+    def p2p_attach_local(self, row0: int, m_total: int, rank: int, nranks: int, blocks):
+        """Peer-store exchange between engines driven by one process; blocks: `p2p_block()` of every rank."""
+        from ctypes import c_void_p
+        arr = (c_void_p * nranks)(*[int(b) for b in blocks])
+        N.check(self.L.lps_p2p_attach_local(self.h, row0, m_total, rank, nranks, arr))
+        self.row0, self.m_total, self.rank, self.nranks = row0, m_total, rank, nranks
+
     # -- transfers -----------------------------------------------------------------------------
     def upload(self, host: np.ndarray):
         """host: float64 (m+1, >= n+1) array in grid layout (C-contiguous rows)."""

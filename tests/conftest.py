@@ -5,6 +5,10 @@ import sys
 
 import pytest
 
+# engines of one process that wait for each other inside kernels (tests/test_sharded_gpu.py) need their streams on
+# separate hardware queues; must be set before CUDA initialises
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

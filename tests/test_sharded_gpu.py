@@ -52,3 +52,52 @@ def test_shards_emulated_on_one_gpu_match_oracle(m, parts, seed):
         got = e.download()
         assert got[:ml].tobytes() == T[row0:row0 + ml].tobytes() and got[ml].tobytes() == T[m].tobytes()
         e.close()
+
+
+@pytest.mark.parametrize("m,parts,seed", [(64, 2, 0), (250, 4, 2), (333, 3, 3)])
+def test_peer_store_exchange_between_engines_of_one_process(m, parts, seed):
+    """The fused exchange of k_select_f64 (headers and the pivot row written straight into every rank's exchange
+    block, sequence flags) with all ranks on the visible GPU(s): each engine has its own stream, so the select
+    kernels of a pivot run concurrently and wait for each other exactly like ranks on different GPUs do."""
+    import torch
+    from linear_program_solver_b200.engine import F64Engine
+    from linear_program_solver_b200.sharded import shard_rows
+    from oracle import c_oracle as C
+    n = 2 * m
+    ndev = torch.cuda.device_count()
+    engs = []
+    for g in range(parts):
+        row0, ml = shard_rows(m, g, parts)
+        engs.append(F64Engine(ml, n, device=g % ndev))
+    blocks = [e.p2p_block() for e in engs]
+    for g, e in enumerate(engs):
+        row0, ml = shard_rows(m, g, parts)
+        e.p2p_attach_local(row0, m, g, parts, blocks)
+        e.fill_dense(seed, 1, 9)
+    basis = np.arange(m, n, dtype=np.int32)
+    for e in engs:
+        e.solve_begin(basis, None, -1, 4096)
+    done = False
+    for _ in range(40 * m // 16 + 2):
+        for _ in range(16):                                         # a burst without any host synchronisation
+            for e in engs:
+                e.step_select()
+            for e in engs:
+                e.step_update()
+        st = {e.poll() for e in engs}
+        assert len(st) == 1, st
+        if next(iter(st))[0] != 0:
+            done = True
+            break
+    assert done
+    T = problems.hashed_dense_grid(m, seed).astype(np.float64)
+    ob = np.arange(m, n, dtype=np.int32)
+    ost, ok, otrace = C.solve(T, ob)
+    for g, e in enumerate(engs):
+        b = basis.copy()
+        st, k, trace = e.solve_end(b, None, 4096)
+        assert (st, k) == (ost, ok) and trace.tolist() == otrace.tolist() and b.tolist() == ob.tolist()
+        row0, ml = shard_rows(m, g, parts)
+        got = e.download()
+        assert got[:ml].tobytes() == T[row0:row0 + ml].tobytes() and got[ml].tobytes() == T[m].tobytes()
+        e.close()
