@@ -211,6 +211,7 @@ def run_ours(a):
     m, n, B = a.m, 2 * a.m, a.pivots_per_step
     row0, m_loc = shard_rows(m, rank, world)
     solver = ShardedF64Solver(m, n, rank, world, device=local, exchange=a.exchange)
+    solver_exchange = solver.exchange            # "nccl" when the peers' exchange blocks could not be mapped
     eng = solver.eng
     eng.fill_dense(a.seed, 1, 9)
     basis = np.arange(m, 2 * m, dtype=np.int32)
@@ -316,7 +317,7 @@ def run_ours(a):
             "config": {"workload": f"C4 fp64 {m}x{n} dense tableau, seed {a.seed}", "m": m, "n": n,
                        "pivots_per_step": B, "sharding": f"rows/{world}", "rows_per_gpu": m_loc,
                        "exchange": ("none (one rank)" if world == 1 else
-                                    "peer stores over NVLink inside the pivot kernels" if a.exchange == "p2p" else
+                                    "peer stores over NVLink inside the pivot kernels" if solver_exchange == "p2p" else
                                     "one NCCL all-gather per pivot"),
                        "l2": "tableau (17.2 GB total) is larger than L2; no flush needed",
                        "status_after": int(status), "pivots_timed": int(pivots)},

@@ -112,6 +112,13 @@ int lps_row_axpy_f64(lps_handle *h, int rd, int rs, double mult);
  * (simplex.py:251-284, :218-249).  Returns LPS_OK with (*r,*c) set, or
  * LPS_OPTIMAL / LPS_UNBOUNDED. */
 int lps_find_pivot(lps_handle *h, int rule, int *r, int *c);
+/* Whole-tableau pivot rules, fp64 mode (exact mode evaluates them on host snapshots): the ratio test of every
+ * column in one pass.  lps_find_pivot_max_increase = Simplex.findPivotMaxIncrease simplex.py:286-328 (largest
+ * objective decrease -c_j * ratio, first column among equals; LPS_OPTIMAL / LPS_UNBOUNDED like the literals).
+ * lps_find_pivot_all = Simplex.findPivotAll simplex.py:330-360: every (row, column) of minimum ratio, column by
+ * column, rows ascending; *count = how many exist, at most cap are written. */
+int lps_find_pivot_max_increase(lps_handle *h, int *r, int *c);
+int lps_find_pivot_all(lps_handle *h, int *rows, int *cols, long long cap, long long *count);
 
 /* Tableau.isCanonical(bcols) tableau.py:466-496.  bcols (m ints, may be NULL)
  * receives the lowest basic column per row or -1; *canonical is 0/1. */

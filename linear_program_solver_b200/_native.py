@@ -51,6 +51,8 @@ SIGNATURES = {
     "lps_row_scale_f64": (c_int, [c_void_p, c_int, c_double]),
     "lps_row_axpy_f64": (c_int, [c_void_p, c_int, c_int, c_double]),
     "lps_find_pivot": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_int)]),
+    "lps_find_pivot_max_increase": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "lps_find_pivot_all": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, POINTER(c_longlong)]),
     "lps_is_canonical": (c_int, [c_void_p, c_void_p, POINTER(c_int)]),
     "lps_is_optimal": (c_int, [c_void_p, POINTER(c_int)]),
     "lps_solve": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, POINTER(c_longlong)]),

@@ -345,6 +345,70 @@ extern "C" int lps_is_optimal(lps_handle* h, int* optimal) {
     return LPS_OK;
 }
 
+// Simplex.findPivotMaxIncrease (simplex.py:286-328) on the device, fp64 mode.
+extern "C" int lps_find_pivot_max_increase(lps_handle* h, int* r, int* c) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (!r || !c) return fail(LPS_E_INVALID, "null output");
+    if (h->nranks != 1) return fail(LPS_E_STATE, "whole-tableau rules are not available on a sharded handle");
+    double* ratio = nullptr;
+    int* irow = nullptr;
+    CU(cudaMalloc(&ratio, (size_t)h->n * sizeof(double)));
+    CU(cudaMalloc(&irow, (2 * (size_t)h->n + 4) * sizeof(int)));
+    int* ties = irow + h->n;
+    int* out = ties + h->n;
+    k_col_ratio_f64<<<(h->n + 127) / 128, 128, 0, h->stream>>>(grid_of(h), ratio, irow, ties);
+    k_max_increase_f64<<<1, 1024, 0, h->stream>>>(grid_of(h), ratio, irow, out);
+    h->launches_all += 2;
+    int res[3] = {0, -1, -1};
+    CU(cudaMemcpyAsync(res, out, sizeof(res), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaFree(ratio)); CU(cudaFree(irow));
+    *r = res[1]; *c = res[2];
+    return res[0];
+}
+
+// Simplex.findPivotAll (simplex.py:330-360) on the device, fp64 mode: every (row, column) of minimum ratio, column by
+// column, rows ascending.  *count receives the number of pivots; at most `cap` of them are written.
+extern "C" int lps_find_pivot_all(lps_handle* h, int* rows, int* cols, long long cap, long long* count) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (!count || cap < 0 || (cap > 0 && (!rows || !cols))) return fail(LPS_E_INVALID, "bad arguments");
+    if (h->nranks != 1) return fail(LPS_E_STATE, "whole-tableau rules are not available on a sharded handle");
+    const int n = h->n;
+    double* ratio = nullptr;
+    int* irow = nullptr;
+    CU(cudaMalloc(&ratio, (size_t)n * sizeof(double)));
+    CU(cudaMalloc(&irow, 2 * (size_t)n * sizeof(int)));
+    int* ties = irow + n;
+    k_col_ratio_f64<<<(n + 127) / 128, 128, 0, h->stream>>>(grid_of(h), ratio, irow, ties);
+    h->launches_all++;
+    std::vector<int> hrow(n), hties(n);
+    CU(cudaMemcpyAsync(hrow.data(), irow, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(hties.data(), ties, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<long long> off(n);
+    long long total = 0;
+    for (int j = 0; j < n; ++j) { off[j] = total; if (hrow[j] >= 0) total += hties[j]; }
+    *count = total;
+    int rc = LPS_OK;
+    if (total > 0 && total <= cap) {
+        long long* d_off = nullptr;
+        int* d_out = nullptr;
+        CU(cudaMalloc(&d_off, (size_t)n * sizeof(long long)));
+        CU(cudaMalloc(&d_out, 2 * (size_t)total * sizeof(int)));
+        CU(cudaMemcpyAsync(d_off, off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+        k_col_ties_f64<<<(n + 127) / 128, 128, 0, h->stream>>>(grid_of(h), ratio, irow, d_off, d_out, d_out + total);
+        h->launches_all++;
+        CU(cudaMemcpyAsync(rows, d_out, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(cols, d_out + total, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaFree(d_off)); CU(cudaFree(d_out));
+    }
+    CU(cudaFree(ratio)); CU(cudaFree(irow));
+    return rc;
+}
+
 extern "C" int lps_is_canonical(lps_handle* h, int* bcols, int* canonical) {
     USE(h);
     if (!canonical) return fail(LPS_E_INVALID, "null result");

@@ -574,6 +574,68 @@ __global__ void k_gather_col_f64(F64Grid g, int j, double* out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= g.m; i += gridDim.x * blockDim.x) out[i] = g.T[(size_t)i * g.ld + j];
 }
 
+// ------------------------------------------------------------------------------------------------
+// whole-tableau pivot rules: Simplex.findPivotMaxIncrease simplex.py:286-328 and
+// Simplex.findPivotAll simplex.py:330-360.  Both run the ratio test of EVERY column: one thread per column walks
+// the rows (coalesced across the warp, the right-hand side is a broadcast load).
+// ------------------------------------------------------------------------------------------------
+// per column j: lowest ratio b_i / a_ij over a_ij > 0, its first row (strict "<": simplex.py:308), and how many
+// rows attain it (findPivotAll lists them all); minrow = -1 when no entry is positive
+__global__ void k_col_ratio_f64(F64Grid g, double* minratio, int* minrow, int* ties) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.n) return;
+    double best = 0.0;
+    int row = -1, cnt = 0;
+    for (int i = 0; i < g.m; ++i) {
+        const double a = g.T[(size_t)i * g.ld + j];
+        if (!(a > 0.0)) continue;
+        const double r = g.T[(size_t)i * g.ld + g.n] / a;
+        if (row < 0 || r < best) { best = r; row = i; cnt = 1; }
+        else if (r == best) ++cnt;
+    }
+    minratio[j] = best; minrow[j] = row; ties[j] = cnt;
+}
+// findPivotMaxIncrease: over the columns with c_j < 0, the pivot with the largest objective decrease -c_j * ratio,
+// first column among equals (strict ">": simplex.py:321); a negative column without a positive entry: unbounded.
+// out[0] = status (LPS_OK / LPS_OPTIMAL / LPS_UNBOUNDED), out[1] = row, out[2] = column.  One block.
+__global__ void __launch_bounds__(1024) k_max_increase_f64(F64Grid g, const double* minratio, const int* minrow, int* out) {
+    __shared__ ArgMinF64 s_arg[32];
+    __shared__ int s_int[32];
+    const double* cost = g.T + (size_t)g.m * g.ld;
+    ArgMinF64 best{0.0, INT_MAX};                                 // key = -(decrease): arg-min with lowest index on ties
+    int unb = INT_MAX;
+    for (int j = threadIdx.x; j < g.n; j += blockDim.x) {
+        const double cj = cost[j];
+        if (cj >= 0.0 || cj != cj) continue;                      // "if cj >= ZERO: continue" (a NaN cost is never < 0)
+        if (minrow[j] < 0) { unb = min(unb, j); continue; }
+        const double dec = -cj * minratio[j];
+        if (best.idx == INT_MAX || -dec < best.key) { best.key = -dec; best.idx = j; }
+    }
+    // any negative column at all?  encode "seen" through unb / best
+    int seen = (best.idx != INT_MAX || unb != INT_MAX) ? 1 : 0;
+    best = block_argmin(best, s_arg);
+    unb = block_min_int(unb, s_int);
+    seen = __syncthreads_or(seen);
+    if (threadIdx.x == 0) {
+        if (unb != INT_MAX) { out[0] = LPS_UNBOUNDED; out[1] = -1; out[2] = unb; }
+        else if (!seen) { out[0] = LPS_OPTIMAL; out[1] = -1; out[2] = -1; }
+        else { out[0] = LPS_OK; out[1] = minrow[best.idx]; out[2] = best.idx; }
+    }
+}
+// findPivotAll, second pass: the rows of column j whose ratio equals the column's minimum, in row order, written at
+// offset[j] (exclusive prefix sum of `ties` over the columns with minrow >= 0)
+__global__ void k_col_ties_f64(F64Grid g, const double* minratio, const int* minrow, const long long* offset, int* rows, int* cols) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.n || minrow[j] < 0) return;
+    const double best = minratio[j];
+    long long at = offset[j];
+    for (int i = minrow[j]; i < g.m; ++i) {
+        const double a = g.T[(size_t)i * g.ld + j];
+        if (!(a > 0.0)) continue;
+        if (g.T[(size_t)i * g.ld + g.n] / a == best) { rows[at] = i; cols[at] = j; ++at; }
+    }
+}
+
 // Tableau.isCanonical (tableau.py:466-496), column scan over a (column block) x (row slab) grid.  A column is basic
 // when its cost is exactly 0 and it holds one exact 1 and zeros elsewhere.  colrow[j] = row of the 1 (claimed with a
 // compare-and-swap, a second claim spoils the column), bad[j] != 0 once the column is known not to be basic -- the

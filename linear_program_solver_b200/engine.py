@@ -153,6 +153,28 @@ class F64Engine:
             return "unbounded"
         return r.value, c.value
 
+    def find_pivot_max_increase(self):
+        """Simplex.findPivotMaxIncrease (simplex.py:286-328) over the device tableau."""
+        r, c = c_int(-1), c_int(-1)
+        rc = N.check(self.L.lps_find_pivot_max_increase(self.h, byref(r), byref(c)))
+        if rc == N.OPTIMAL:
+            return "optimal"
+        if rc == N.UNBOUNDED:
+            return "unbounded"
+        return r.value, c.value
+
+    def find_pivot_all(self):
+        """Simplex.findPivotAll (simplex.py:330-360) over the device tableau: list of (row, column)."""
+        cap = self.n + self.m
+        while True:
+            rows, cols = np.empty(cap, dtype=np.int32), np.empty(cap, dtype=np.int32)
+            count = c_longlong(0)
+            N.check(self.L.lps_find_pivot_all(self.h, rows.ctypes.data, cols.ctypes.data, cap, byref(count)))
+            if count.value <= cap:
+                k = count.value
+                return list(zip(rows[:k].tolist(), cols[:k].tolist()))
+            cap = count.value
+
     def is_canonical(self, want_cols: bool = True, cols: Optional[np.ndarray] = None):
         """(canonical?, bcols).  The library leaves bcols untouched when some b_i < 0 (tableau.py:476-477): pass
         `cols` pre-filled to tell."""

@@ -53,9 +53,11 @@ class ShardedF64Solver:
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         self.exchange = exchange
         if nranks > 1:
-            if exchange == "p2p":
-                self._attach_peers()
-            else:
+            if exchange == "p2p" and not self._attach_peers():
+                # some rank could not map a peer's exchange block (no peer access / IPC between these GPUs): every
+                # rank falls back to the collective exchange together
+                self.exchange = "nccl"
+            if self.exchange == "nccl":
                 self.eng.set_shard(self.row0, self.m_total, rank, nranks)
         # pivots enqueued between two host checks: ~2 ms of device work, between 4 and 256
         est_us = max(4.0, (self.m_local + 1) * (self.n + 1) * 16.0 / 5.0e6)
@@ -66,14 +68,21 @@ class ShardedF64Solver:
         self.eng.close()
 
     def _attach_peers(self):
-        """All-gather the 64-byte CUDA IPC handles of the exchange blocks, map the peers' blocks."""
+        """All-gather the 64-byte CUDA IPC handles of the exchange blocks, map the peers' blocks.  True when every
+        rank succeeded."""
         import torch
         import torch.distributed as dist
         mine = torch.from_numpy(self.eng.p2p_export()).to(f"cuda:{self.eng.device}")
         everyone = torch.empty(64 * self.nranks, dtype=torch.uint8, device=mine.device)
         dist.all_gather_into_tensor(everyone, mine, group=self.group)
-        self.eng.p2p_attach(self.row0, self.m_total, self.rank, self.nranks, everyone.cpu().numpy())
-        dist.barrier(group=self.group)            # every rank has mapped every block before the first peer store
+        ok = 1
+        try:
+            self.eng.p2p_attach(self.row0, self.m_total, self.rank, self.nranks, everyone.cpu().numpy())
+        except N.NativeError:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=mine.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)   # also: every rank has mapped every block
+        return bool(flag.item())
 
     # -- one pivot: select, exchange, update -------------------------------------------------------
     def _exchange(self):

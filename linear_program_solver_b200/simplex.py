@@ -185,8 +185,20 @@ class Simplex:
         return self._find(N.RULE_DANTZIG, do_pivot)
 
     def findPivotMaxIncrease(self, do_pivot: bool = False) -> PivotResult:
-        """pivot of maximum objective decrease (simplex.py:286-328).  Not on the solve path
-        (SURVEY.md section 8f rank 3): evaluated over a snapshot of the tableau."""
+        """pivot of maximum objective decrease (simplex.py:286-328).  Not on the solve path (SURVEY.md section 8f
+        rank 3).  fp64 mode: one pass over the device tableau (`lps_find_pivot_max_increase`); exact mode: evaluated
+        over a snapshot of the tableau with the reference's Fraction arithmetic."""
+        tab = self._tab
+        if tab.mode == "fp64":
+            found = tab._need_dev().find_pivot_max_increase()
+            if isinstance(found, str):
+                return found
+            if do_pivot:
+                self._pivot(*found)
+            return found
+        return self._max_increase_host(do_pivot)
+
+    def _max_increase_host(self, do_pivot: bool = False) -> PivotResult:
         tab = self._tab
         m, n = tab.getTableauSize()
         cost, b = tab._row(m), tab._col(n)
@@ -221,7 +233,14 @@ class Simplex:
         return si, sj
 
     def findPivotAll(self) -> List[Tuple[int, int]]:
-        """every pivot that keeps canonical form (simplex.py:330-360); snapshot evaluation"""
+        """every pivot that keeps canonical form (simplex.py:330-360).  fp64 mode: on the device
+        (`lps_find_pivot_all`); exact mode: snapshot evaluation."""
+        tab = self._tab
+        if tab.mode == "fp64":
+            return tab._need_dev().find_pivot_all()
+        return self._find_all_host()
+
+    def _find_all_host(self) -> List[Tuple[int, int]]:
         tab = self._tab
         m, n = tab.getTableauSize()
         b = tab._col(n)

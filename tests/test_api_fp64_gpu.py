@@ -168,3 +168,37 @@ def test_stepping_api_equals_solve():
     assert (st, k) == (1, ok) and trace.tolist() == otrace.tolist() and basis.tolist() == ob.tolist()
     assert sv.eng.download().tobytes() == T.tobytes()
     sv.close()
+
+
+@pytest.mark.parametrize("m,seed,hi", [(12, 5, 9), (40, 1, 3), (150, 2, 9)])
+def test_whole_tableau_rules_on_the_device_match_the_snapshot_evaluation(m, seed, hi):
+    """findPivotMaxIncrease / findPivotAll (simplex.py:286-360): the device pass against the host evaluation that
+    follows the reference line by line, at every state along a solve (small integer data: many ratio ties)."""
+    from linear_program_solver_b200 import Simplex
+    c, A, b = problems.dense_lp(m, seed, 1, hi)
+    s = Simplex(_tab(c, A, b))
+    for step in range(3 * m):
+        t = s._tab
+        t._need_host()                                            # the host evaluation reads a snapshot
+        want_max, want_all = s._max_increase_host(), s._find_all_host()
+        t._need_dev()
+        assert s.findPivotMaxIncrease() == want_max, step
+        assert s.findPivotAll() == want_all, step
+        if isinstance(want_max, str):
+            assert want_max == "optimal"
+            break
+        nxt = s.findPivotMaxIncrease(True) if step % 2 else s.findPivotStandard(True)
+        assert not isinstance(nxt, str)
+    else:
+        raise AssertionError("did not reach the optimum")
+
+
+def test_max_increase_reports_unbounded_and_optimal():
+    from linear_program_solver_b200 import Simplex
+    unb = _tab([-1, -2, 0], [[1, -1, 1]], [1])                  # column 1 is attractive and has no positive entry
+    s = Simplex(unb)
+    assert s.findPivotMaxIncrease() == "unbounded" == s._max_increase_host()
+    opt = _tab([1, 2, 0], [[1, 1, 1]], [1])
+    s = Simplex(opt)
+    assert s.findPivotMaxIncrease() == "optimal" == s._max_increase_host()
+    assert s.findPivotAll() == s._find_all_host()
