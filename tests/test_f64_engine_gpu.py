@@ -195,3 +195,48 @@ def test_large_prefix_matches_oracle(eng_mod):
     assert st == 4 and npiv == 12 and basis.tolist() == ob.tolist()
     assert e.download().tobytes() == T.tobytes()
     e.close()
+
+
+def _mem_available() -> int:
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
+def _same_bits(a: np.ndarray, b: np.ndarray, rows: int = 1024) -> bool:
+    """byte equality of two large float64 arrays without copying them (`tobytes` would)"""
+    ua, ub = a.view(np.uint64), b.view(np.uint64)
+    return a.shape == b.shape and all(np.array_equal(ua[i:i + rows], ub[i:i + rows]) for i in range(0, a.shape[0], rows))
+
+
+def test_c4_full_size_prefix_bit_identical_to_oracle(eng_mod):
+    """BASELINE.json config 4 at its full size, 32768 x 65536 (17.2 GB): the seeded family generated on the device
+    equals the oracle's, and after a 3-pivot prefix of the solve loop the whole tableau, the pivot trace and the
+    basis are byte-identical to the C oracle's (about 15 s: one download and three CPU pivots)."""
+    import torch
+    from oracle import c_oracle as C
+    m = 32768
+    need = (m + 1) * (2 * m + 1) * 8
+    if _mem_available() < 2.4 * need or torch.cuda.mem_get_info()[0] < 1.1 * need:
+        pytest.skip("needs about 40 GB of host memory and 19 GB of device memory")
+    e = eng_mod.F64Engine(m, 2 * m)
+    e.fill_dense(0, 1, 9)
+    T = np.empty((m + 1, 2 * m + 1), dtype=np.float64)
+    C.fill_dense(T, m, 0, 0, 1, 9)
+    got = e.download()
+    assert _same_bits(got, T)                                     # same input on both sides
+    del got
+    basis = np.arange(m, 2 * m, dtype=np.int32)
+    st, npiv, trace = e.solve(basis, None, max_pivots=3, trace_cap=3)
+    ob = np.arange(m, 2 * m, dtype=np.int32)
+    ost, ok, otrace = C.solve(T, ob, max_pivots=3)
+    assert (st, npiv) == (4, 3) and ok == 3
+    assert trace.tolist() == otrace.tolist() and basis.tolist() == ob.tolist()
+    got = e.download()
+    assert _same_bits(got, T)
+    e.close()
