@@ -59,8 +59,14 @@ static void plan(lps_handle* h) {
     if (tiles_wide >= 148 * 8) { h->chunk = kWideChunk; h->rows_per_cta = 64; }
     else { h->chunk = kNarrowChunk; h->rows_per_cta = ((size_t)(h->m + 1) * h->ld >= (1u << 20)) ? 16 : 8; }
     h->nchunks = (int)((h->ld + h->chunk - 1) / h->chunk);
-    // k_select_f64 spins on an in-kernel flag: never more CTAs than SMs, so all of them are resident
-    h->sel_blocks = std::max(1, std::min(std::max((h->m + kThreads - 1) / kThreads, (int)(h->ld / (8 * kThreads))), 148));
+    // k_select_f64 spins on an in-kernel flag: never more CTAs than SMs, so all of them are resident.  Small
+    // tableaux take ONE CTA of 1024 threads instead: no ticket, no flag, no fences -- the launch is a plain
+    // dependent chain of a few memory round trips.
+    if (h->m <= 8 * kSelMaxThreads && h->ld <= 16 * kSelMaxThreads) { h->sel_blocks = 1; h->sel_threads = kSelMaxThreads; }
+    else {
+        h->sel_threads = kThreads;
+        h->sel_blocks = std::max(1, std::min(std::max((h->m + kThreads - 1) / kThreads, (int)(h->ld / (8 * kThreads))), 148));
+    }
 }
 
 extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* stream, lps_handle** out) {
@@ -149,6 +155,7 @@ extern "C" int lps_destroy(lps_handle* h) {
     if (h->own_T) cudaFree(h->T);
     cudaFree(h->ucol);
     if (h->own_cand) cudaFree(h->cand_send);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
     for (void* p : h->ipc_open) cudaIpcCloseMemHandle(p);
     cudaFree(h->xchg); cudaFree(h->d_peers);
     cudaFree(h->pd_val); cudaFree(h->pd_idx); cudaFree(h->pb_idx);
@@ -234,7 +241,7 @@ static int launch_select(lps_handle* h) {
     a.g = grid_of(h); a.pp = partials_of(h); a.nchunks = h->nchunks; a.st = h->st; a.ucol = h->ucol;
     a.blk = h->sel_blk; a.cand = (CandHeader*)h->cand_send;
     a.xchg = h->use_xchg ? h->xchg : nullptr; a.peers = h->d_peers; a.rank = h->rank; a.nranks = h->nranks;
-    k_select_f64<<<h->sel_blocks, kThreads, 0, h->stream>>>(a);
+    k_select_f64<<<h->sel_blocks, h->sel_threads, 0, h->stream>>>(a);
     h->launches_all++;
     CU(cudaGetLastError());
     return LPS_OK;
@@ -512,6 +519,36 @@ extern "C" int lps_solve_end(lps_handle* h, int* basis, int* marks, int* trace, 
     return h->st_host->status;
 }
 
+// (select, update) x burst on the handle's stream as one executable graph; re-captured when an argument baked into
+// the nodes changed (trace buffer, marks, exchange mode, launch plan)
+static int ensure_burst_graph(lps_handle* h, long long burst) {
+    unsigned long long sig = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
+    mix((unsigned long long)(uintptr_t)h->trace); mix((unsigned long long)h->trace_cap); mix(h->use_marks ? 1 : 0);
+    mix((unsigned long long)(uintptr_t)h->basis); mix(h->use_xchg ? 1 : 0); mix((unsigned long long)h->chunk);
+    mix((unsigned long long)h->rows_per_cta); mix((unsigned long long)h->sel_blocks); mix((unsigned long long)h->sel_threads);
+    mix((unsigned long long)(uintptr_t)h->cand_send); mix((unsigned long long)(uintptr_t)h->cand_all); mix((unsigned long long)burst);
+    if (h->gexec && h->gsig == sig && h->gburst == burst) return LPS_OK;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    const long long la = h->launches_all, lu = h->launches_update;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = LPS_OK;
+    for (long long k = 0; k < burst && rc == LPS_OK; ++k) {
+        rc = launch_select(h);
+        if (rc == LPS_OK) rc = launch_update(h, 1);
+    }
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    h->launches_all = la; h->launches_update = lu;               // counted when the graph is launched
+    if (rc != LPS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(LPS_E_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { h->gexec = nullptr; return fail(LPS_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    h->gsig = sig; h->gburst = burst;
+    return LPS_OK;
+}
+
 extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int* trace, long long trace_cap, long long* npiv) {
     USE(h);
     if (h->nranks != 1) return fail(LPS_E_STATE, "lps_solve on a sharded handle: drive it with the stepping calls");
@@ -523,15 +560,28 @@ extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* m
     const double est_us = std::max(4.0, (double)(h->m + 1) * (double)h->ld * 16.0 / 5.0e6);
     const long long burst = (long long)std::max(4.0, std::min(256.0, 2000.0 / est_us));
     long long enqueued = 0;
+    // Launch-bound sizes (a pivot is tens of microseconds of device work, two launches cost about as much on the
+    // host): the burst is captured once as a CUDA graph and replayed.  Pairs enqueued past optimality or past the
+    // pivot prefix are no-ops on the device (k_select_f64 / k_update_f64 test the state first), so whole bursts
+    // are always safe.  Per-launch profiling events need the plain launches.
+    const bool graphed = !h->prof && est_us < 200.0;
+    if (graphed) TRY(ensure_burst_graph(h, burst));
     for (;;) {
-        const long long room = max_pivots >= 0 ? max_pivots - enqueued : burst;
-        const long long now = std::min(burst, room);
-        for (long long k = 0; k < now; ++k) {
-            TRY(launch_select(h));
-            TRY(launch_update(h, 1));
+        if (graphed) {
+            CU(cudaGraphLaunch(h->gexec, h->stream));
+            h->launches_all += 2 * burst;
+            h->launches_update += burst;
+            enqueued += burst;
+        } else {
+            const long long room = max_pivots >= 0 ? max_pivots - enqueued : burst;
+            const long long now = std::min(burst, room);
+            for (long long k = 0; k < now; ++k) {
+                TRY(launch_select(h));
+                TRY(launch_update(h, 1));
+            }
+            enqueued += now;
+            if (now == 0) TRY(launch_select(h));   // lets the device report LPS_MAX_PIVOTS (or optimality)
         }
-        enqueued += now;
-        if (now == 0) TRY(launch_select(h));   // lets the device report LPS_MAX_PIVOTS (or optimality)
         TRY(read_state(h));
         if (h->st_host->status != LPS_OK) break;
     }

@@ -21,6 +21,7 @@
 namespace lps {
 
 constexpr int kThreads = 256;
+constexpr int kSelMaxThreads = 1024;  // k_select_f64 runs as one CTA of 1024 threads on small tableaux
 constexpr int kMaxRowBlock = 128;     // rows of u staged per CTA
 constexpr int kMaxRanks = 64;
 
@@ -213,13 +214,14 @@ __device__ __forceinline__ int pick_winner(const XchgBlock* x, int par, int nran
 //      reciprocal of the pivot, tableau.py:262-267) and stores it where the update reads it -- the local candidate
 //      slot, or straight into EVERY rank's exchange block over NVLink (the pivot-row broadcast); the other ranks
 //      wait for the row's sequence flag.  When the kernel ends on a rank, that rank holds all its update needs.
-__global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
+__global__ void __launch_bounds__(kSelMaxThreads, 1) k_select_f64(SelectArgs a) {
     __shared__ ArgMinF64 s_arg[32];
     __shared__ int s_int[32];
     __shared__ int s_last, s_w;
     __shared__ long long s_row;
     SolveState* st = a.st;
     const F64Grid& g = a.g;
+    const int nt = (int)blockDim.x;
     if (st->status != LPS_OK) return;
     if (st->max_pivots >= 0 && st->npiv >= st->max_pivots) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && !st->dry_run) st->status = LPS_MAX_PIVOTS;
@@ -238,12 +240,12 @@ __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
     int c;
     if (rule == LPS_RULE_DANTZIG) {
         ArgMinF64 best{0.0, INT_MAX};
-        for (int k = threadIdx.x; k < a.nchunks; k += kThreads) best = argmin_pick(best, ArgMinF64{a.pp.d_val[k], a.pp.d_idx[k]});
+        for (int k = threadIdx.x; k < a.nchunks; k += nt) best = argmin_pick(best, ArgMinF64{a.pp.d_val[k], a.pp.d_idx[k]});
         best = block_argmin(best, s_arg);
         c = best.idx;
     } else {
         int first = INT_MAX;
-        for (int k = threadIdx.x; k < a.nchunks; k += kThreads) first = min(first, a.pp.b_idx[k]);
+        for (int k = threadIdx.x; k < a.nchunks; k += nt) first = min(first, a.pp.b_idx[k]);
         c = block_min_int(first, s_int);
     }
     if (c == INT_MAX) {
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
 
     // ---- A: ratio test over this block's rows; column c is gathered into ucol on the way ----
     ArgMinF64 best{0.0, INT_MAX};
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < g.m; i += gridDim.x * kThreads) {
+    for (int i = blockIdx.x * nt + threadIdx.x; i < g.m; i += gridDim.x * nt) {
         const double aic = g.T[(size_t)i * g.ld + c];
         a.ucol[i] = aic;
         if (aic > 0.0) {
@@ -265,25 +267,31 @@ __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
         }
     }
     best = block_argmin(best, s_arg);
+    const bool solo = (gridDim.x == 1);                        // small tableaux: one CTA, no cross-CTA handshake at all
     if (threadIdx.x == 0) {
-        a.blk[blockIdx.x] = best;
-        __threadfence();
-        const unsigned int t = atomicAdd(&st->ticket, 1u);
-        s_last = (t == gridDim.x - 1);
+        if (solo) s_last = 1;
+        else {
+            a.blk[blockIdx.x] = best;
+            __threadfence();
+            const unsigned int t = atomicAdd(&st->ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
     }
     __syncthreads();
 
     if (s_last) {
         // ---- B: reduce the per-block partials, exchange, publish the decision ----
-        __threadfence();
-        best = ArgMinF64{0.0, INT_MAX};
-        for (int k = threadIdx.x; k < (int)gridDim.x; k += kThreads) {
-            ArgMinF64 o;
-            o.key = __ldcg(&a.blk[k].key);
-            o.idx = __ldcg(&a.blk[k].idx);
-            best = argmin_pick(best, o);
+        if (!solo) {
+            __threadfence();
+            best = ArgMinF64{0.0, INT_MAX};
+            for (int k = threadIdx.x; k < (int)gridDim.x; k += nt) {
+                ArgMinF64 o;
+                o.key = __ldcg(&a.blk[k].key);
+                o.idx = __ldcg(&a.blk[k].idx);
+                best = argmin_pick(best, o);
+            }
+            best = block_argmin(best, s_arg);
         }
-        best = block_argmin(best, s_arg);
         const int r = best.idx;
         CandHeader h{};
         h.ratio = best.key; h.row = (r == INT_MAX) ? -1 : g.row0 + r; h.c = c; h.rule = rule; h.stuck = stuck;
@@ -308,13 +316,16 @@ __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
             if (w == -2) st->status = LPS_E_PEER;
             st->sel_w = w;
             st->sel_row = w_row;
-            __threadfence();
-            st_release_gpu(&st->xseq, seq);
+            if (solo) { s_w = w; s_row = w_row; st->xseq = seq; }
+            else {
+                __threadfence();
+                st_release_gpu(&st->xseq, seq);
+            }
         }
     }
 
     // ---- C: the decision, then the normalised pivot row ----
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !solo) {
         int w = -3;
         if (wait_seq_gpu(&st->xseq, seq)) { w = st->sel_w; s_row = st->sel_row; }
         s_w = w;
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) k_select_f64(SelectArgs a) {
     const double inv = 1.0 / src[c];
     const bool spread = (a.xchg != nullptr);
     double* local = spread ? nullptr : reinterpret_cast<double*>(a.cand + 1);
-    for (int j = 2 * (blockIdx.x * kThreads + threadIdx.x); j < (int)g.ld; j += 2 * gridDim.x * kThreads) {
+    for (int j = 2 * (blockIdx.x * nt + threadIdx.x); j < (int)g.ld; j += 2 * gridDim.x * nt) {
         double2 x = *reinterpret_cast<const double2*>(src + j);
         if (inv != 1.0) { x.x = x.x * inv; x.y = x.y * inv; }
         if (spread) {

@@ -52,7 +52,7 @@ struct lps_handle {
     std::vector<void*> ipc_open;
     bool use_xchg = false;   // set by lps_p2p_attach with more than one rank
 
-    int chunk = kWideChunk, nchunks = 0, rows_per_cta = 64, sel_blocks = 1;
+    int chunk = kWideChunk, nchunks = 0, rows_per_cta = 64, sel_blocks = 1, sel_threads = 256;
     bool stream_hint = false;
     double* pd_val = nullptr;
     int* pd_idx = nullptr;
@@ -67,6 +67,11 @@ struct lps_handle {
     long long trace_cap = 0;
     int* scratch_i = nullptr;        // n + 8 ints (isCanonical)
     bool solving = false;
+
+    // a burst of (select, update) pairs captured once as a CUDA graph: small tableaux are launch bound on the host
+    cudaGraphExec_t gexec = nullptr;
+    unsigned long long gsig = 0;     // the launch arguments the graph was captured with
+    long long gburst = 0;
 
     // profiling of the update kernel
     bool prof = false;

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="variables (default 2m); wider than 2m = the shape of one shard")
     ap.add_argument("--pivots", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-prof", action="store_true", help="no per-launch events: lps_solve replays a CUDA graph on small sizes")
     a = ap.parse_args()
     import torch
     from linear_program_solver_b200.engine import F64Engine
@@ -46,13 +47,14 @@ def main():
     fill_dense(eng)
     basis = np.arange(n - m, n, dtype=np.int32)
     st, k, _ = eng.solve(basis, None, max_pivots=a.warmup)
-    eng.prof_reset()
+    if not a.no_prof:
+        eng.prof_reset()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     st, k, _ = eng.solve(basis, None, max_pivots=a.pivots)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    ms, nu, na = eng.prof_read()
+    ms, nu, na = eng.prof_read() if not a.no_prof else (0.0, 0, 0)
     bytes_per = 16 * (m + 1) * (n + 1) + 8 * (m + 1) + 8 * (n + 1)
     out = {"m": m, "n": n, "status": st, "pivots": k, "wall_s": wall, "pivots_per_s": k / wall,
            "update_ms_avg": ms / max(nu, 1), "update_launches_timed": nu, "launches": na,
