@@ -565,13 +565,15 @@ extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* m
     // pivot prefix are no-ops on the device (k_select_f64 / k_update_f64 test the state first), so whole bursts
     // are always safe.  Per-launch profiling events need the plain launches.
     const bool graphed = !h->prof && est_us < 200.0;
-    if (graphed) TRY(ensure_burst_graph(h, burst));
+    const long long gburst = std::min<long long>(burst, 32);   // short graphs: capture stays cheap next to a short solve
+    if (graphed) TRY(ensure_burst_graph(h, gburst));
     for (;;) {
         if (graphed) {
-            CU(cudaGraphLaunch(h->gexec, h->stream));
-            h->launches_all += 2 * burst;
-            h->launches_update += burst;
-            enqueued += burst;
+            for (long long k = 0; k < burst; k += gburst) CU(cudaGraphLaunch(h->gexec, h->stream));
+            const long long done = (burst + gburst - 1) / gburst * gburst;
+            h->launches_all += 2 * done;
+            h->launches_update += done;
+            enqueued += done;
         } else {
             const long long room = max_pivots >= 0 ? max_pivots - enqueued : burst;
             const long long now = std::min(burst, room);

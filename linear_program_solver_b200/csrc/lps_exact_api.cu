@@ -207,6 +207,7 @@ int lpsx_destroy(lps_handle* h) {
         if (x->st_host) cudaFreeHost(x->st_host);
         delete x;
     }
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     cudaFree(h->basis); cudaFree(h->marks); cudaFree(h->trace); cudaFree(h->scratch_i);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -582,6 +583,35 @@ int lpsx_is_canonical(lps_handle* h, int* bcols, int* canonical) {
     return LPS_OK;
 }
 
+static int xensure_burst_graph(lps_handle* h, long long burst) {
+    ExactData* x = h->x;
+    unsigned long long sig = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
+    mix((unsigned long long)(uintptr_t)h->trace); mix((unsigned long long)h->trace_cap); mix(h->use_marks ? 1 : 0);
+    mix((unsigned long long)x->P); mix((unsigned long long)x->lane_threads); mix((unsigned long long)x->spt);
+    mix((unsigned long long)x->chunk); mix((unsigned long long)x->rows_per_cta); mix(x->stream_hint ? 1 : 0);
+    mix(x->adaptive ? 1 : 0); mix((unsigned long long)burst);
+    if (h->gexec && h->gsig == sig && h->gburst == burst) return LPS_OK;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    const long long la = h->launches_all, lu = h->launches_update;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = LPS_OK;
+    for (long long k = 0; k < burst && rc == LPS_OK; ++k) {
+        rc = xlaunch_select(h);
+        if (rc == LPS_OK) rc = xlaunch_apply(h, 1);
+    }
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    h->launches_all = la; h->launches_update = lu;               // counted when the graph is launched
+    if (rc != LPS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(LPS_E_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { h->gexec = nullptr; return fail(LPS_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    h->gsig = sig; h->gburst = burst;
+    return LPS_OK;
+}
+
 int lpsx_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int* trace, long long trace_cap, long long* npiv) {
     ExactData* x = h->x;
     CU(cudaMemcpyAsync(h->basis, basis, (size_t)h->m * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -603,15 +633,29 @@ int lpsx_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int*
     const double est_us = std::max(20.0, (double)x->plane * x->P * 8.0 / 5.0e6);
     const long long burst = (long long)std::max(2.0, std::min(128.0, 2000.0 / est_us));
     long long enqueued = 0;
+    // Six launches per pivot: below a few hundred microseconds of device work per pivot the host is the limit, so
+    // the burst is captured once as a CUDA graph (again after every change of the working prime set) and replayed;
+    // pairs behind optimality, the pivot prefix or LPS_NEED_PRIMES are no-ops on the device.
+    const bool graphed = !h->prof && est_us < 400.0;
+    const long long gburst = std::min<long long>(burst, 16);   // short graphs: capture stays cheap next to a 30-pivot solve
     for (;;) {
-        const long long room = max_pivots >= 0 ? max_pivots - enqueued : burst;
-        const long long now = std::min(burst, room);
-        for (long long k = 0; k < now; ++k) {
-            TRY(xlaunch_select(h));
-            TRY(xlaunch_apply(h, 1));
+        if (graphed) {
+            TRY(xensure_burst_graph(h, gburst));
+            for (long long k = 0; k < burst; k += gburst) CU(cudaGraphLaunch(h->gexec, h->stream));
+            const long long done = (burst + gburst - 1) / gburst * gburst;
+            h->launches_all += 6 * done;
+            h->launches_update += done;
+            enqueued += done;
+        } else {
+            const long long room = max_pivots >= 0 ? max_pivots - enqueued : burst;
+            const long long now = std::min(burst, room);
+            for (long long k = 0; k < now; ++k) {
+                TRY(xlaunch_select(h));
+                TRY(xlaunch_apply(h, 1));
+            }
+            enqueued += now;
+            if (now == 0) TRY(xlaunch_select(h));
         }
-        enqueued += now;
-        if (now == 0) TRY(xlaunch_select(h));
         TRY(xread_state(h));
         if (x->st_host->status == LPS_NEED_PRIMES) {     // the pending pivot needs a larger working prime set
             enqueued = x->st_host->npiv;                 // the launches behind it were no-ops

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--pivots", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-prof", action="store_true", help="no per-launch events: the solve replays a CUDA graph on small sizes")
     a = ap.parse_args()
     import torch
     from linear_program_solver_b200 import problems
@@ -38,13 +39,14 @@ def main():
     info = eng.info()
     basis = np.arange(m, 2 * m, dtype=np.int32)
     st, k0, _ = eng.solve(basis, None, max_pivots=a.warmup)
-    eng.prof_reset()
+    if not a.no_prof:
+        eng.prof_reset()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     st, k, trace = eng.solve(basis, None, max_pivots=a.pivots, trace_cap=a.pivots)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    ms, nu, na = eng.prof_read()
+    ms, nu, na = eng.prof_read() if not a.no_prof else (0.0, 0, 0)
     info_end = eng.info()
     P = info_end["primes"]
     bytes_per = 8 * P * (m + 1) * (n + 1)
