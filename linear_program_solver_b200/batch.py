@@ -122,6 +122,24 @@ class BatchResult:
         """`Simplex.getObjValue` (simplex.py:188-190): minus the corner cell."""
         return Fraction(-self._one(k, self.m), self._one(k, self.m + 1))
 
+    def objectives(self) -> List[Fraction]:
+        """`objective(k)` of every LP at once: Horner over the digit planes with numpy object arrays (one big-integer
+        multiply-add per LP and digit inside numpy instead of a Python loop per LP)."""
+        primes = self._codec.primes
+        out = []
+        for idx in (self.m, self.m + 1):
+            dig = self._digits[:, :, idx]                         # [count, P]
+            nz = np.nonzero(dig.any(axis=0))[0]
+            acc = np.zeros(dig.shape[0], dtype=object)
+            if nz.size:
+                for j in range(int(nz[-1]), -1, -1):
+                    acc = acc * primes[j] + dig[:, j].astype(object)
+            neg = self._sign[:, idx] < 0
+            acc[neg] = -acc[neg]
+            out.append(acc)
+        num, den = out
+        return [Fraction(-int(a), int(b)) if b else Fraction(0) for a, b in zip(num, den)]
+
     def bfs(self, k: int) -> Dict[int, Fraction]:
         """`Simplex.getBFS` (simplex.py:165-172)."""
         b = self.rhs(k)
@@ -277,3 +295,21 @@ def solve_batch(grids, trace_cap: int = 0, cluster: int = 0, device: Optional[in
         return solver.solve(G32, max_pivots)
     finally:
         solver.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# several GPUs: node LPs are independent, so they shard by LP with no data-path collective (SURVEY.md section 8e)
+# ------------------------------------------------------------------------------------------------
+def shard_lps(count: int, rank: int, nranks: int) -> tuple:
+    """[lo, hi) of the LPs rank `rank` of `nranks` solves: contiguous, balanced to within one LP."""
+    return count * rank // nranks, count * (rank + 1) // nranks
+
+
+def solve_batch_sharded(grids, rank: int, nranks: int, device: Optional[int] = None, **kw):
+    """This rank's share of `solve_batch(grids)`: returns (lo, hi, BatchResult of LPs lo..hi-1).  One process per GPU;
+    the caller gathers whatever it needs of the results (statuses, objectives) with its own transport."""
+    G = np.asarray(grids)
+    lo, hi = shard_lps(G.shape[0], rank, nranks)
+    if hi <= lo:
+        return lo, hi, None
+    return lo, hi, solve_batch(G[lo:hi], device=device, **kw)

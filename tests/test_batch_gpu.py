@@ -213,6 +213,8 @@ def test_c5_batch_of_64x128_nodes():
     assert fixtures
     for seed, r in fixtures.items():
         _check_fixture(res, seed, r)
+    allobj = res.objectives()                                    # vectorised decode == per-LP decode
+    assert all(allobj[k] == res.objective(k) for k in range(0, count, 5))
     for k in range(0, count, 7):
         c, A, b = lps[k]
         assert int(res.status[k]) == N.OPTIMAL

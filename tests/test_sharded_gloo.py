@@ -155,3 +155,15 @@ def test_sharded_protocol_equals_single_process_oracle(world, m, seed, max_pivot
         ml = shard.shape[0] - 1
         assert shard[:ml].tobytes() == T[row0:row0 + ml].tobytes()       # the rank's rows
         assert shard[ml].tobytes() == T[m].tobytes()                      # its replica of the objective row
+
+
+def test_node_lps_shard_by_lp_without_overlap():
+    """C5 over several GPUs: contiguous, balanced, exhaustive shares."""
+    from linear_program_solver_b200.batch import shard_lps
+    for count in (0, 1, 7, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            parts = [shard_lps(count, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == count
+            assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1

@@ -33,7 +33,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--family", choices=["hashed", "seeded"], default="hashed")
     ap.add_argument("--timing", action="store_true", help="print the kernel's per-phase cycle shares (profiling aid)")
+    ap.add_argument("--gpus", type=int, default=1, help="under torchrun: every rank solves its own --count LPs (weak scaling)")
     a = ap.parse_args()
+    if a.gpus > 1:
+        return main_multi(a)
 
     import torch
     from linear_program_solver_b200 import problems
@@ -92,7 +95,7 @@ def main():
         # end to end with host buffers through the public call
         t0 = time.perf_counter()
         r2 = solve_batch(grids, cluster=cl)
-        objs = [r2.objective(k) for k in range(count)]
+        objs = r2.objectives()
         e2e_s = time.perf_counter() - t0
         smem_bytes = 8.0 * P * (m + 1) * (n + 1) * pivots
         line = {
@@ -107,12 +110,56 @@ def main():
                               "bytes_per_pivot": 8 * P * (m + 1) * (n + 1)},
             "e2e": {"node_lps_per_s": count / e2e_s, "seconds": e2e_s, "h2d_bytes": int(grids.nbytes),
                     "d2h_bytes": int(count * (4 + 16 + 4 * m + (m + 2) * (1 + 4 * P))),
-                    "api": "batch.solve_batch + objective(k) for every LP"},
+                    "api": "batch.solve_batch + objectives()"},
             "gen_seconds": gen_s,
         }
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+
+
+def main_multi(a):
+    """Weak scaling over the GPUs of one box: rank g solves LPs with seeds g*count .. (g+1)*count-1, no collective on
+    the data path; device-timed kernel (max over ranks) and the end-to-end call, both summed over ranks."""
+    import torch
+    import torch.distributed as dist
+    from linear_program_solver_b200 import problems
+    from linear_program_solver_b200.batch import BatchExactSolver, plan_batch, solve_batch
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    assert world == a.gpus
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    m, n, count = a.m, 2 * a.m, a.count
+    grids = np.stack([problems.hashed_dense_grid(m, rank * count + s) for s in range(count)]).astype(np.int32)
+    art_cap, primes, bits = plan_batch(grids, device=local)
+    solver = BatchExactSolver(count, m, n, primes, art_cap=art_cap, cluster=int(a.cluster.split(",")[0]), trace_cap=0, device=local)
+    solver.upload(grids)
+    solver.run(64 * (m + n))
+    solver.sync()
+    times = []
+    for _ in range(a.reps):
+        dist.barrier()
+        solver.run(64 * (m + n))
+        solver.sync()
+        times.append(solver.info()["last_run_ms"])
+    ok = int((solver.download(want_numbers=False).status == 1).sum())
+    solver.close()
+    dist.barrier()
+    t0 = time.perf_counter()
+    r2 = solve_batch(grids, device=local)
+    objs = r2.objectives()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([float(np.median(times)), e2e_s, float(ok)], dtype=torch.float64, device="cuda")
+    mx = t.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = t.clone()
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({"workload": f"C5 x {world} GPUs: {count} independent {m}x{n} exact node LPs per GPU", "n_gpus": world,
+                          "scaling": "weak", "primes": len(primes), "ms_max_over_ranks": float(mx[0]),
+                          "node_lps_per_s": world * count / (float(mx[0]) * 1e-3), "optimal": int(sm[2]),
+                          "e2e": {"node_lps_per_s": world * count / float(mx[1]), "seconds_max_over_ranks": float(mx[1])}}), flush=True)
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
