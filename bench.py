@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--m", type=int, default=32768, help="constraint rows (n = 2m); default is config C4")
-    ap.add_argument("--pivots-per-step", type=int, default=256,
+    ap.add_argument("--pivots-per-step", type=int, default=512,
                     help="consecutive simplex pivots per step (a solve of this size runs tens of thousands)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=0)

@@ -678,7 +678,7 @@ extern "C" int lps_p2p_attach_local(lps_handle* h, long long row0, long long m_t
 extern "C" int lps_prof_reset(lps_handle* h) {
     USE(h);
     if (h->ev.empty()) {
-        h->ev.resize(2 * 4096);
+        h->ev.resize(2 * 8192);
         for (auto& e : h->ev) CU(cudaEventCreate(&e));
     }
     h->ev_used = 0;
