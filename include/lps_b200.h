@@ -228,7 +228,8 @@ int lps_exact_loop_state(lps_handle *h, int set, int *rule, long long *stuck, in
 typedef struct lps_batch lps_batch;
 size_t lps_batch_smem_bytes(int m, int n, int art_cap, int nprimes, int cluster);
 /* Sizing on the device (bookkeeping, no pivot arithmetic): the largest number of artificial columns any LP of
- * the batch needs and log2 of a Hadamard bound on every minor of every LP (phase-1 objective included). */
+ * the batch needs and log2 of a Hadamard bound on every minor of every LP (phase-1 objective included).
+ * `grids` of lps_batch_plan and lps_batch_upload may be host or device memory (unified addressing). */
 int lps_batch_plan(int count, int m, int n, const int32_t *grids, int device, int *art_cap, double *bound_bits);
 int lps_batch_create(int count, int m, int n, int art_cap, int nprimes, const uint32_t *primes, int cluster,
                      int trace_cap, int device, void *stream, lps_batch **out);
@@ -240,6 +241,11 @@ int lps_batch_sync(lps_batch *b);
 /* Number of consecutive Dantzig pivots at the entry objective after which solve() switches to Bland's rule.
  * Negative (default): the reference's m + n (simplex.py:123).  Parity tests lower it to reach loop B. */
 int lps_batch_set_stuck_limit(lps_batch *b, long long limit);
+/* A batch may be created with FEWER primes than the static bound of lps_batch_plan asks for (half of them holds a
+ * 64 x 128 LP in one CTA instead of a cluster of two).  With the capacity check on, every LP tracks the Hadamard
+ * product of its current basis columns' norms and ends with LPS_NEED_PRIMES -- before the pivot that might not fit is
+ * applied -- when the short set could overflow; the caller re-runs those LPs in a batch with the full set. */
+int lps_batch_set_capacity_check(lps_batch *b, int on);
 /* Results (any pointer may be NULL): status[count]; npiv[count][4] = phase-1, drive-out, phase-2 pivots and
  * the number of artificial columns; basis[count][m] (Simplex._bfs); sign[count][m+2] / digits[count][P][m+2]:
  * b_0..b_{m-1}, the `_z` cell and the common denominator D as sign + mixed-radix digits (see

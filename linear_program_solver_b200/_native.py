@@ -83,6 +83,7 @@ SIGNATURES = {
     "lps_batch_run": (c_int, [c_void_p, c_longlong]),
     "lps_batch_sync": (c_int, [c_void_p]),
     "lps_batch_set_stuck_limit": (c_int, [c_void_p, c_longlong]),
+    "lps_batch_set_capacity_check": (c_int, [c_void_p, c_int]),
     "lps_batch_download": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lps_batch_timing": (c_int, [c_void_p, c_void_p]),
     "lps_batch_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t), POINTER(c_int), POINTER(c_double),

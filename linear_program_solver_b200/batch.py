@@ -203,9 +203,15 @@ class BatchExactSolver:
         return {"cluster": c.value, "primes": len(self.primes), "rows_per_cta": pl.value, "smem_bytes": sm.value,
                 "resident_clusters": rc.value, "last_run_ms": ms.value, "launches": nl.value}
 
-    def upload(self, grids: np.ndarray):
-        assert grids.dtype == np.int32 and grids.shape == (self.count, self.m + 1, self.n + 1) and grids.flags.c_contiguous
-        N.check(self.L.lps_batch_upload(self.h, grids.ctypes.data))
+    def upload(self, grids):
+        """grids: int32 [count, m+1, n+1], a C-contiguous numpy array or a torch tensor already on the device."""
+        assert tuple(grids.shape) == (self.count, self.m + 1, self.n + 1)
+        if isinstance(grids, np.ndarray):
+            assert grids.dtype == np.int32 and grids.flags.c_contiguous
+            N.check(self.L.lps_batch_upload(self.h, grids.ctypes.data))
+        else:
+            assert grids.is_contiguous() and grids.element_size() == 4
+            N.check(self.L.lps_batch_upload(self.h, grids.data_ptr()))
         self._keep = grids                    # the copy is asynchronous
 
     def run(self, max_pivots: int = -1):
@@ -225,6 +231,11 @@ class BatchExactSolver:
         out = np.zeros((self.count, 16), dtype=np.int64)
         N.check(self.L.lps_batch_timing(self.h, out.ctypes.data))
         return out
+
+    def set_capacity_check(self, on: bool = True):
+        """The batch holds fewer primes than the static bound asks for: LPs whose basis grows too heavy for them end
+        with NEED_PRIMES before the pivot that might not fit (include/lps_b200.h)."""
+        N.check(self.L.lps_batch_set_capacity_check(self.h, 1 if on else 0))
 
     def set_stuck_limit(self, limit: int = -1):
         """Degenerate Dantzig pivots before the switch to Bland; -1 = the reference's m + n (simplex.py:123)."""
@@ -250,7 +261,8 @@ class BatchExactSolver:
         return self.download()
 
 
-def plan_batch(grids: np.ndarray, banned: Sequence[int] = (), device: Optional[int] = None, on_device: bool = True):
+def plan_batch(grids: np.ndarray, banned: Sequence[int] = (), device: Optional[int] = None, on_device: bool = True,
+               dev_ptr: Optional[int] = None):
     """(art_cap, primes, bound bits) for a batch of integer tableaux, or raises ValueError when the Hadamard bound
     needs more primes than the batched kernel holds (solve those LPs one at a time).  The counting runs on
     the device (`lps_batch_plan`); `on_device=False` uses the numpy statement of the same rule (tests compare them)."""
@@ -260,7 +272,9 @@ def plan_batch(grids: np.ndarray, banned: Sequence[int] = (), device: Optional[i
         L = N.lib()
         dev = int(torch.cuda.current_device() if device is None else device)
         k, b = c_int(0), c_double(0.0)
-        N.check(L.lps_batch_plan(G.shape[0], G.shape[1] - 1, G.shape[2] - 1, G.ctypes.data, dev, byref(k), byref(b)))
+        # dev_ptr: the same grids already on the device (solve_batch uploads them once for planning and solving)
+        N.check(L.lps_batch_plan(G.shape[0], G.shape[1] - 1, G.shape[2] - 1, dev_ptr if dev_ptr else G.ctypes.data, dev,
+                                 byref(k), byref(b)))
         art_cap, bits = k.value, int(math.ceil(b.value * (1 + 1e-9))) + 3
     else:
         missing = missing_basic_rows(G)
@@ -275,7 +289,7 @@ def plan_batch(grids: np.ndarray, banned: Sequence[int] = (), device: Optional[i
 
 
 def solve_batch(grids, trace_cap: int = 0, cluster: int = 0, device: Optional[int] = None, max_pivots: int = -1,
-                stuck_limit: int = -1) -> BatchResult:
+                stuck_limit: int = -1, two_tier: bool = True) -> BatchResult:
     """`Simplex(tab); solve()` of the reference for every integer tableau of `grids`
     ([count, m+1, n+1], device layout: row m = costs, column n = rhs, cell (m, n) = minus the objective)."""
     G = np.asarray(grids)
@@ -285,17 +299,60 @@ def solve_batch(grids, trace_cap: int = 0, cluster: int = 0, device: Optional[in
         if G.size and (G.max() >= 2 ** 31 or G.min() < -(2 ** 31)):
             raise ValueError("batched tableaux take 32-bit integer coefficients")
     G32 = np.ascontiguousarray(G, dtype=np.int32)
-    art_cap, primes, _ = plan_batch(G32, device=device)
-    solver = BatchExactSolver(G.shape[0], G.shape[1] - 1, G.shape[2] - 1, primes, art_cap=art_cap, cluster=cluster,
-                              trace_cap=trace_cap, device=device)
+    import torch
+    dev = torch.device("cuda", int(torch.cuda.current_device() if device is None else device))
+    Gd = torch.from_numpy(G32).to(dev)       # ONE host-to-device copy serves the planner and every tier
+    torch.cuda.current_stream(dev).synchronize()          # the library works on its own streams
+    art_cap, primes, _ = plan_batch(G32, device=device, dev_ptr=Gd.data_ptr())
+    primes = sorted(primes)
     if max_pivots < 0:                       # Bland's rule terminates; the cap only bounds a run gone wrong
         max_pivots = 64 * (G.shape[1] + G.shape[2]) + 256
-    try:
-        solver.set_stuck_limit(stuck_limit)
-        return solver.solve(G32, max_pivots)
-    finally:
-        solver.close()
+    m, n = G.shape[1] - 1, G.shape[2] - 1
 
+    def run(grids32, prime_set, check):
+        solver = BatchExactSolver(grids32.shape[0], m, n, prime_set, art_cap=art_cap, cluster=cluster,
+                                  trace_cap=trace_cap, device=device)
+        try:
+            solver.set_stuck_limit(stuck_limit)
+            solver.set_capacity_check(check)
+            return solver.solve(grids32, max_pivots)
+        finally:
+            solver.close()
+
+    # Two tiers.  The static bound covers a basis made of the heaviest columns; node LPs rarely get there.  A first
+    # pass on HALF the primes (a 64 x 128 LP then sits in one CTA instead of a cluster of two, twice as many LPs are
+    # resident) solves every LP whose basis stays light -- each LP checks that rigorously before every pivot -- and
+    # the few that end with NEED_PRIMES are solved again on the full set.
+    short = len(primes) // 2
+    short += short & 1                       # the kernel takes an even number of primes
+    if two_tier and short >= 2 and short < len(primes) and G.shape[0] >= 2:
+        first = run(Gd, primes[:short], True)
+        redo = np.nonzero(first.status == N.NEED_PRIMES)[0]
+        second = None
+        if redo.size:
+            Gr = Gd[torch.from_numpy(redo).to(dev)].contiguous()
+            torch.cuda.current_stream(dev).synchronize()
+            second = run(Gr, primes, False)
+        return _merge_tiers(first, second, redo, MixedRadix(primes))
+    return run(Gd, primes, False)
+
+
+def _merge_tiers(first: "BatchResult", second: Optional["BatchResult"], redo: np.ndarray, codec: MixedRadix) -> "BatchResult":
+    """Results of the short-prime pass with the re-run LPs patched in; digits padded to the full prime set (the short
+    set is a prefix of the ascending prime list, so the mixed-radix digits agree and the upper ones are 0)."""
+    P = len(codec.primes)
+    digits = np.zeros((first._digits.shape[0], P, first._digits.shape[2]), dtype=np.uint32)
+    digits[:, : first._digits.shape[1]] = first._digits
+    status, npiv, basis, sign = first.status.copy(), first.npiv.copy(), first.basis.copy(), first._sign.copy()
+    trace = None if first.trace is None else first.trace.copy()
+    if second is not None:
+        status[redo], npiv[redo], basis[redo], sign[redo] = second.status, second.npiv, second.basis, second._sign
+        digits[redo] = second._digits
+        if trace is not None:
+            trace[redo] = second.trace
+    out = BatchResult(first.m, first.n, status, npiv, basis, sign, digits, trace, codec)
+    out.tiers = (int(first.status.shape[0]), int(redo.size))     # LPs in the first pass, LPs solved again
+    return out
 
 # ------------------------------------------------------------------------------------------------
 # several GPUs: node LPs are independent, so they shard by LP with no data-path collective (SURVEY.md section 8e)

@@ -358,10 +358,11 @@ extern "C" int lps_find_pivot_max_increase(lps_handle* h, int* r, int* c) {
     NEED_MODE(h, 0);
     if (!r || !c) return fail(LPS_E_INVALID, "null output");
     if (h->nranks != 1) return fail(LPS_E_STATE, "whole-tableau rules are not available on a sharded handle");
-    double* ratio = nullptr;
-    int* irow = nullptr;
-    CU(cudaMalloc(&ratio, (size_t)h->n * sizeof(double)));
-    CU(cudaMalloc(&irow, (2 * (size_t)h->n + 4) * sizeof(int)));
+    DevBuf b_ratio, b_int;
+    CU(b_ratio.alloc((size_t)h->n * sizeof(double)));
+    CU(b_int.alloc((2 * (size_t)h->n + 4) * sizeof(int)));
+    double* ratio = b_ratio.as<double>();
+    int* irow = b_int.as<int>();
     int* ties = irow + h->n;
     int* out = ties + h->n;
     k_col_ratio_f64<<<(h->n + 127) / 128, 128, 0, h->stream>>>(grid_of(h), ratio, irow, ties);
@@ -370,7 +371,6 @@ extern "C" int lps_find_pivot_max_increase(lps_handle* h, int* r, int* c) {
     int res[3] = {0, -1, -1};
     CU(cudaMemcpyAsync(res, out, sizeof(res), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaFree(ratio)); CU(cudaFree(irow));
     *r = res[1]; *c = res[2];
     return res[0];
 }
@@ -383,10 +383,11 @@ extern "C" int lps_find_pivot_all(lps_handle* h, int* rows, int* cols, long long
     if (!count || cap < 0 || (cap > 0 && (!rows || !cols))) return fail(LPS_E_INVALID, "bad arguments");
     if (h->nranks != 1) return fail(LPS_E_STATE, "whole-tableau rules are not available on a sharded handle");
     const int n = h->n;
-    double* ratio = nullptr;
-    int* irow = nullptr;
-    CU(cudaMalloc(&ratio, (size_t)n * sizeof(double)));
-    CU(cudaMalloc(&irow, 2 * (size_t)n * sizeof(int)));
+    DevBuf b_ratio, b_int, b_off, b_out;
+    CU(b_ratio.alloc((size_t)n * sizeof(double)));
+    CU(b_int.alloc(2 * (size_t)n * sizeof(int)));
+    double* ratio = b_ratio.as<double>();
+    int* irow = b_int.as<int>();
     int* ties = irow + n;
     k_col_ratio_f64<<<(n + 127) / 128, 128, 0, h->stream>>>(grid_of(h), ratio, irow, ties);
     h->launches_all++;
@@ -400,19 +401,17 @@ extern "C" int lps_find_pivot_all(lps_handle* h, int* rows, int* cols, long long
     *count = total;
     int rc = LPS_OK;
     if (total > 0 && total <= cap) {
-        long long* d_off = nullptr;
-        int* d_out = nullptr;
-        CU(cudaMalloc(&d_off, (size_t)n * sizeof(long long)));
-        CU(cudaMalloc(&d_out, 2 * (size_t)total * sizeof(int)));
+        CU(b_off.alloc((size_t)n * sizeof(long long)));
+        CU(b_out.alloc(2 * (size_t)total * sizeof(int)));
+        long long* d_off = b_off.as<long long>();
+        int* d_out = b_out.as<int>();
         CU(cudaMemcpyAsync(d_off, off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
         k_col_ties_f64<<<(n + 127) / 128, 128, 0, h->stream>>>(grid_of(h), ratio, irow, d_off, d_out, d_out + total);
         h->launches_all++;
         CU(cudaMemcpyAsync(rows, d_out, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(cols, d_out + total, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        CU(cudaFree(d_off)); CU(cudaFree(d_out));
     }
-    CU(cudaFree(ratio)); CU(cudaFree(irow));
     return rc;
 }
 
@@ -434,15 +433,15 @@ extern "C" int lps_is_canonical(lps_handle* h, int* bcols, int* canonical) {
     const int rows_per_slab = (h->m + slabs - 1) / slabs;
     k_canon_init_f64<<<(h->n + 255) / 256, 256, 0, h->stream>>>(grid_of(h), h->scratch_i, bad);
     k_canon_cols_f64<<<dim3((h->n + 127) / 128, slabs), 128, 0, h->stream>>>(grid_of(h), rows_per_slab, h->scratch_i, bad);
-    int* d_bcols = nullptr;
-    CU(cudaMalloc(&d_bcols, (size_t)h->m * sizeof(int)));
+    DevBuf b_bcols;
+    CU(b_bcols.alloc((size_t)h->m * sizeof(int)));
+    int* d_bcols = b_bcols.as<int>();
     CU(cudaMemsetAsync(d_bcols, 0x7f, (size_t)h->m * sizeof(int), h->stream));
     k_canon_rows<<<std::max(1, std::min((h->n + 255) / 256, 592)), 256, 0, h->stream>>>(h->scratch_i, bad, h->n, d_bcols);
     h->launches_all += 3;
     std::vector<int> tmp(h->m);
     CU(cudaMemcpyAsync(tmp.data(), d_bcols, (size_t)h->m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaFree(d_bcols));
     int all = 1;
     for (int i = 0; i < h->m; ++i) {
         const int j = (tmp[i] == 0x7f7f7f7f) ? -1 : tmp[i];

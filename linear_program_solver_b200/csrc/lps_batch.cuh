@@ -57,12 +57,14 @@ struct BatchParams {
     int* trace;                      // [count][trace_cap][3] or NULL
     int trace_cap;
     long long* timing;               // NULL, or [count][16] cycles of CTA 0 per phase (profiling aid, see b_tick)
+    int wcheck;                      // 1: the prime set is shorter than the static bound asks for -- refuse (LPS_NEED_PRIMES)
+                                     // any pivot after which the Hadamard product of the basis columns might not fit
 };
 
 // Shared-memory carve-up, identical on host (sizing) and device.
 struct BatchLayout {
     size_t planes, prow, objdig, nbeta, tbc, tbb, inv, half, dres, dinv, alpha, piv, cand_price, cand_ratio, obj_top,
-        col_top, rhs_top, tb_row, cand, basis, rowsign, wexp, wmant, rcp, col_mant, rhs_mant, pr, obj_sign, col_sign, rhs_sign,
+        col_top, rhs_top, tb_row, cand, basis, rowsign, wcol, wexp, wmant, rcp, col_mant, rhs_mant, pr, obj_sign, col_sign, rhs_sign,
         total;
 };
 __host__ __device__ inline int batch_price_words(int P) { return P + 2; }          // idx, top, digits[P]
@@ -93,6 +95,7 @@ __host__ __device__ inline BatchLayout batch_layout(int m, int P, int C, int mlo
     L.cand = take((size_t)(mr > tb ? mr : tb) * 4, 4);
     L.basis = take((size_t)m * 4, 4);
     L.rowsign = take((size_t)m * 4, 4);
+    L.wcol = take((size_t)ld * 4, 4);
     L.wexp = take((size_t)(P + 1) * 4, 4);
     L.wmant = take((size_t)(P + 1) * 8, 8);
     L.rcp = take((size_t)(P + 1) * 8, 8);
@@ -185,6 +188,10 @@ struct BState {                  // one copy per CTA, kept identical across the 
     int npiv[3];
     int sgnD;
     int flag, count, low, low2;  // scratch
+    // capacity of a prime set shorter than the static bound (BatchParams::wcheck): every entry is, up to sign, a minor
+    // of the LP's extended matrix over the basis columns plus at most two more, so log2|entry| <= wsum + 2 wmax in
+    // 1/256 bits, wsum = sum of wcol[basis[i]], wcol[j] >= 256 log2 of column j's 2-norm (cost rows of both phases)
+    long long wsum, wlimit;
 };
 
 // Everything a device function of the kernel needs, built once per CTA in shared memory.
@@ -196,7 +203,7 @@ struct BCtx {
     // byte offsets into the dynamic shared memory; the accessors rebuild pointers the compiler knows to be
     // in the shared window (LDS/STS with 32-bit addresses instead of generic loads)
     unsigned o_planes, o_prow, o_objdig, o_nbeta, o_tbc, o_tbb, o_inv, o_half, o_Dres, o_dinv_m, o_alpha_m, o_piv;
-    unsigned o_cand_price, o_cand_ratio, o_obj_top, o_col_top, o_rhs_top, o_tb_row, o_cand, o_basis, o_rowsign, o_wexp;
+    unsigned o_cand_price, o_cand_ratio, o_obj_top, o_col_top, o_rhs_top, o_tb_row, o_cand, o_basis, o_rowsign, o_wcol, o_wexp;
     unsigned o_wmant, o_rcp, o_col_mant, o_rhs_mant;
     unsigned o_pr;
     unsigned o_obj_sign, o_col_sign, o_rhs_sign;
@@ -221,6 +228,7 @@ struct BCtx {
     __device__ __forceinline__ int* cand() const { return reinterpret_cast<int*>(lps_bsmem + o_cand); }
     __device__ __forceinline__ int* basis() const { return reinterpret_cast<int*>(lps_bsmem + o_basis); }
     __device__ __forceinline__ int* rowsign() const { return reinterpret_cast<int*>(lps_bsmem + o_rowsign); }
+    __device__ __forceinline__ int* wcol() const { return reinterpret_cast<int*>(lps_bsmem + o_wcol); }
     __device__ __forceinline__ int* wexp() const { return reinterpret_cast<int*>(lps_bsmem + o_wexp); }
     __device__ __forceinline__ double* wmant() const { return reinterpret_cast<double*>(lps_bsmem + o_wmant); }
     __device__ __forceinline__ double* rcp() const { return reinterpret_cast<double*>(lps_bsmem + o_rcp); }
@@ -760,10 +768,19 @@ __device__ __noinline__ bool b_apply(int slot) {
     return true;
 }
 
+// would the tableau after pivot (r, c) still fit the prime set?  (block- and cluster-uniform: replicated state)
+__device__ __forceinline__ bool b_fits(int r, int c) {
+    const BCtx& x = b_ctx();
+    if (!x.a.wcheck) return true;
+    const int old = x.basis()[r];
+    return x.S.wsum + x.wcol()[c] - x.wcol()[old] <= x.S.wlimit;
+}
+
 __device__ __forceinline__ void b_commit(int r, int c, int rule) {
     BCtx& x = b_ctx();   // Simplex._pivot simplex.py:192-197
     if (threadIdx.x == 0) {
         BState& S = x.S;
+        S.wsum += x.wcol()[c] - x.wcol()[x.basis()[r]];
         if (x.qr == 0 && x.a.trace && S.npiv_total < x.a.trace_cap) {
             int* tr = x.a.trace + ((size_t)x.lp * x.a.trace_cap + S.npiv_total) * 3;
             tr[0] = r; tr[1] = c; tr[2] = rule;
@@ -814,6 +831,12 @@ __device__ __noinline__ void b_solve() {
         const int r = rec[0];
         const int sgn_br = rec[7] * S.sgnD;
         __syncthreads();
+        if (!b_fits(r, c)) {                                   // nothing modified: the host re-runs this LP on the full prime set
+            __syncthreads();
+            if (tid == 0) S.status = LPS_NEED_PRIMES;
+            __syncthreads();
+            return;
+        }
         if (!b_apply<P>(slot)) {
             if (tid == 0) S.status = LPS_BAD_PRIME;
             __syncthreads();
@@ -867,6 +890,7 @@ __global__ void __launch_bounds__(kBMaxThreads, LPS_BATCH_MINB) k_bnb_nodes(Batc
         x.o_cand = (unsigned)(base + L.cand);
         x.o_basis = (unsigned)(base + L.basis);
         x.o_rowsign = (unsigned)(base + L.rowsign);
+        x.o_wcol = (unsigned)(base + L.wcol);
         x.o_wexp = (unsigned)(base + L.wexp);
         x.o_wmant = (unsigned)(base + L.wmant);
         x.o_rcp = (unsigned)(base + L.rcp);
@@ -936,6 +960,27 @@ __global__ void __launch_bounds__(kBMaxThreads, LPS_BATCH_MINB) k_bnb_nodes(Batc
     }
     __syncthreads();
     const int K = S.K;
+    if (a.wcheck) {
+        // column weights of the extended matrix [A | artificial units | b ; c | 1 | 0] (the cost row of either phase)
+        int* wcol = x.wcol();
+        for (int j = tid; j <= n + K; j += (int)blockDim.x) {
+            double sq = 0.0;
+            if (j < n || j == n + K) {
+                const int js = j < n ? j : n;
+                for (int i = 0; i <= m; ++i) { const double v = (double)G[(size_t)i * (n + 1) + js]; sq += v * v; }
+            } else sq = 2.0;                                  // an artificial column: one 1 and cost 1
+            wcol[j] = sq <= 1.0 ? 0 : (int)ceil(128.0 * log2(sq * (1.0 + 1e-9))) + 1;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            long long wmax = 0, wsum = 0;
+            for (int j = 0; j <= n + K; ++j) wmax = max(wmax, (long long)wcol[j]);
+            for (int i = 0; i < m; ++i) wsum += wcol[basis[i]];
+            S.wsum = wsum;
+            S.wlimit = 256LL * (a.wexp[P] - 2) - 2 * wmax - 256LL * 3;   // bits of the prime set, two extra columns, guard
+        }
+        __syncthreads();
+    }
 
     // ---- encode the local rows and the objective replica into residues --------------------------------
     // phase-1 tableau when K > 0: costs 0, z 0, artificial unit columns with cost 1, then
@@ -1032,6 +1077,12 @@ __global__ void __launch_bounds__(kBMaxThreads, LPS_BATCH_MINB) k_bnb_nodes(Batc
                 const int* rec = x.cand_ratio() + owner * words;
                 if (rec[0] < 0) { redundant = true; b_csync(); continue; }   // dependent row: marked for deletion (simplex.py:82-84)
                 const int j1 = rec[1];
+                if (!b_fits(i, j1)) {
+                    __syncthreads();
+                    if (tid == 0) S.status = LPS_NEED_PRIMES;
+                    __syncthreads();
+                    break;
+                }
                 if (!b_apply<P>(owner)) {
                     if (tid == 0) S.status = LPS_BAD_PRIME;
                     __syncthreads();

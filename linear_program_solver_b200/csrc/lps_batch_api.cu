@@ -31,6 +31,7 @@ struct lps_batch {
     long long launches = 0;
     long long stuck_limit = -1;
     int threads = 256;
+    int wcheck = 0;
 };
 
 static const size_t kBatchSmemMax = 227 * 1024 - 64;       // opt-in maximum (the kernel has no static shared memory)
@@ -209,7 +210,7 @@ extern "C" int lps_batch_plan(int count, int m, int n, const int32_t* grids, int
     if (e == cudaSuccess) e = cudaMalloc(&d_b, (size_t)count * sizeof(double));
     std::vector<int> hk(count);
     std::vector<double> hb(count);
-    if (e == cudaSuccess) e = cudaMemcpy(d_g, grids, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_g, grids, bytes, cudaMemcpyDefault);   // host or device memory (UVA)
     if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(k_batch_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
         k_batch_plan<<<count, 256, smem>>>(d_g, m, n, d_k, d_b);
@@ -241,7 +242,7 @@ extern "C" int lps_batch_upload(lps_batch* b, const int32_t* grids) {
     USEB(b);
     if (!grids) return fail(LPS_E_INVALID, "null grids");
     const size_t bytes = (size_t)b->count * (b->m + 1) * (b->n + 1) * sizeof(int32_t);
-    CU(cudaMemcpyAsync(b->grids, grids, bytes, cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->grids, grids, bytes, cudaMemcpyDefault, b->stream));    // host or device memory (UVA)
     return LPS_OK;
 }
 
@@ -252,7 +253,7 @@ extern "C" int lps_batch_run(lps_batch* b, long long max_pivots) {
     a.ld = b->ld; a.tb = b->tb; a.max_pivots = max_pivots; a.stuck_limit = b->stuck_limit;
     a.pr = b->pr; a.invtab = b->invtab; a.half = b->half; a.wmant = b->wmant; a.wexp = b->wexp;
     a.grids = b->grids; a.status = b->status; a.npiv = b->npiv; a.basis = b->basis; a.sign = b->sign; a.digits = b->digits;
-    a.trace = b->trace; a.trace_cap = b->trace_cap; a.timing = b->timing;
+    a.trace = b->trace; a.trace_cap = b->trace_cap; a.timing = b->timing; a.wcheck = b->wcheck;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)b->count * b->C, 1, 1);
     cfg.blockDim = dim3(b->threads, 1, 1);
@@ -292,6 +293,11 @@ extern "C" int lps_batch_download(lps_batch* b, int* status, int* npiv, int* bas
 
 /* Degenerate-pivot count after which Simplex.solve switches from Dantzig to Bland pricing; negative (the
  * default) is the reference's m + n (simplex.py:123).  A lower limit lets tests reach the Bland loop. */
+extern "C" int lps_batch_set_capacity_check(lps_batch* b, int on) {
+    USEB(b);
+    b->wcheck = on ? 1 : 0;
+    return LPS_OK;
+}
 extern "C" int lps_batch_set_stuck_limit(lps_batch* b, long long limit) {
     USEB(b);
     b->stuck_limit = limit;

@@ -342,12 +342,13 @@ extern "C" int lps_upload_exact(lps_handle* h, const uint32_t* limbs, int nlimbs
     x->adaptive = false;
     TRY(set_working(h, x->Pcap));                        // encode for every allocated prime
     const size_t entries = (size_t)(h->m + 1) * ld_host;
-    uint32_t* d_limbs = nullptr;
-    unsigned char* d_neg = nullptr;
-    uint32_t* d_sig = nullptr;
-    CU(cudaMalloc(&d_limbs, entries * nlimbs * sizeof(uint32_t)));
-    CU(cudaMalloc(&d_neg, entries));
-    CU(cudaMalloc(&d_sig, ((size_t)h->m + 1) * sigma_nlimbs * sizeof(uint32_t)));
+    DevBuf b_limbs, b_neg, b_sig;
+    CU(b_limbs.alloc(entries * nlimbs * sizeof(uint32_t)));
+    CU(b_neg.alloc(entries));
+    CU(b_sig.alloc(((size_t)h->m + 1) * sigma_nlimbs * sizeof(uint32_t)));
+    uint32_t* d_limbs = b_limbs.as<uint32_t>();
+    unsigned char* d_neg = b_neg.as<unsigned char>();
+    uint32_t* d_sig = b_sig.as<uint32_t>();
     CU(cudaMemcpyAsync(d_limbs, limbs, entries * nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_neg, neg, entries, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_sig, sigma_limbs, ((size_t)h->m + 1) * sigma_nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
@@ -367,7 +368,6 @@ extern "C" int lps_upload_exact(lps_handle* h, const uint32_t* limbs, int nlimbs
     *x->st_host = s;
     CU(cudaMemcpyAsync(x->st, x->st_host, sizeof(XState), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaFree(d_limbs)); CU(cudaFree(d_neg)); CU(cudaFree(d_sig));
     return LPS_OK;
 }
 
@@ -564,15 +564,15 @@ int lpsx_is_canonical(lps_handle* h, int* bcols, int* canonical) {
     k_xone<<<dim3(std::max(1, std::min((h->m + 256) / 256, 64)), x->P), 256, 0, h->stream>>>(g, x->Dres, x->sigma, x->sstride, x->alive, x->one);
     k_xcanon_a<<<(h->n + 127) / 128, 128, 0, h->stream>>>(g, x->one, h->scratch_i);
     if (x->P > 1) k_xcanon_b<<<dim3((h->n + 127) / 128, x->P - 1), 128, 0, h->stream>>>(g, x->one, x->sstride, h->scratch_i);
-    int* d_bcols = nullptr;
-    CU(cudaMalloc(&d_bcols, (size_t)h->m * sizeof(int)));
+    DevBuf b_bcols;
+    CU(b_bcols.alloc((size_t)h->m * sizeof(int)));
+    int* d_bcols = b_bcols.as<int>();
     CU(cudaMemsetAsync(d_bcols, 0x7f, (size_t)h->m * sizeof(int), h->stream));
     k_canon_rows<<<std::max(1, std::min((h->n + 255) / 256, 592)), 256, 0, h->stream>>>(h->scratch_i, nullptr, h->n, d_bcols);
     h->launches_all += 4;
     std::vector<int> tmp(h->m);
     CU(cudaMemcpyAsync(tmp.data(), d_bcols, (size_t)h->m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaFree(d_bcols));
     int all = 1;
     for (int i = 0; i < h->m; ++i) {
         const int j = (tmp[i] == 0x7f7f7f7f) ? -1 : tmp[i];

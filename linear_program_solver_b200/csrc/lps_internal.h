@@ -81,6 +81,17 @@ struct lps_handle {
 };
 
 
+// scratch device buffer of one call: freed on every return path
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
 int lps_use(const lps_handle* h);
 #define USE(h)                         \
     do {                               \

@@ -240,3 +240,22 @@ def test_device_planner_agrees_with_the_numpy_statement():
         k2, p2, b2 = plan_batch(grids, on_device=False)
         assert k1 == k2
         assert abs(b1 - b2) <= 1 and abs(len(p1) - len(p2)) <= 2
+
+
+@pytest.mark.parametrize("m,hi,count", [(24, 9, 48), (40, 127, 32), (64, 9, 96)])
+def test_two_tier_batches_give_the_single_tier_answers(m, hi, count):
+    """solve_batch first runs every LP on half the primes with the per-LP capacity check and re-runs the LPs that
+    asked for more; pivots, bases, statuses and rational results must equal the run on the full prime set."""
+    from linear_program_solver_b200.batch import solve_batch
+    grids = np.stack([_grid(*problems.dense_lp(m, seed, 1, hi)) for seed in range(count)])
+    one = solve_batch(grids, trace_cap=8 * m, two_tier=False)
+    two = solve_batch(grids, trace_cap=8 * m, two_tier=True)
+    assert not hasattr(one, "tiers")
+    if hasattr(two, "tiers"):                                     # (a 2-prime plan has no shorter tier)
+        assert two.tiers[0] == count and 0 <= two.tiers[1] <= count
+    assert one.status.tolist() == two.status.tolist()
+    assert one.npiv.tolist() == two.npiv.tolist() and one.basis.tolist() == two.basis.tolist()
+    for k in range(count):
+        assert one.pivots(k) == two.pivots(k)
+        assert one.integers(k) == two.integers(k)
+    assert one.objectives() == two.objectives()
