@@ -259,3 +259,32 @@ def test_two_tier_batches_give_the_single_tier_answers(m, hi, count):
         assert one.pivots(k) == two.pivots(k)
         assert one.integers(k) == two.integers(k)
     assert one.objectives() == two.objectives()
+
+
+def test_capacity_check_stops_an_lp_before_a_short_prime_set_overflows():
+    """Two primes (about 60 bits) cannot hold a 24 x 48 solve: with the check on, every LP either finishes with the
+    answers of the full prime set or ends with NEED_PRIMES -- never with a wrong number; merging the re-run LPs
+    reproduces the single-tier batch."""
+    from linear_program_solver_b200 import _native as N
+    from linear_program_solver_b200.batch import BatchExactSolver, MixedRadix, _merge_tiers, plan_batch, solve_batch
+    m, count = 24, 40
+    grids = np.stack([_grid(*problems.dense_lp(m, seed)) for seed in range(count)]).astype(np.int32)
+    art_cap, primes, _ = plan_batch(grids)
+    primes = sorted(primes)
+    full = solve_batch(grids, trace_cap=8 * m, two_tier=False)
+    s = BatchExactSolver(count, m, 2 * m, primes[:2], art_cap=art_cap, trace_cap=8 * m)
+    s.set_capacity_check(True)
+    first = s.solve(grids, 64 * 3 * m)
+    s.close()
+    redo = np.nonzero(first.status == N.NEED_PRIMES)[0]
+    assert 0 < redo.size                                          # the short set is too small for some LPs at least
+    assert set(first.status.tolist()) <= {N.OPTIMAL, N.NEED_PRIMES}
+    for k in np.nonzero(first.status == N.OPTIMAL)[0]:            # finished LPs carry the exact answers
+        assert first.pivots(int(k)) == full.pivots(int(k)) and first.basis[k].tolist() == full.basis[k].tolist()
+    s2 = BatchExactSolver(int(redo.size), m, 2 * m, primes, art_cap=art_cap, trace_cap=8 * m)
+    second = s2.solve(np.ascontiguousarray(grids[redo]), 64 * 3 * m)
+    s2.close()
+    merged = _merge_tiers(first, second, redo, MixedRadix(primes))
+    assert merged.status.tolist() == full.status.tolist() and merged.basis.tolist() == full.basis.tolist()
+    assert merged.objectives() == full.objectives()
+    assert all(merged.integers(k) == full.integers(k) for k in range(count))

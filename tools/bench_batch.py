@@ -24,6 +24,47 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def time_two_tier(grids, primes, art_cap, cl, reps, m, n, device=None, barrier=None):
+    """Device time of solve_batch's two launches: half the primes with the per-LP capacity check, then the LPs that
+    asked for more primes on the full set.  None when the plan has no shorter tier."""
+    from linear_program_solver_b200 import _native as NN
+    from linear_program_solver_b200.batch import BatchExactSolver
+    count = grids.shape[0]
+    short = len(primes) // 2
+    short += short & 1
+    if not (2 <= short < len(primes)):
+        return None
+    ps = sorted(primes)
+    s1 = BatchExactSolver(count, m, n, ps[:short], art_cap=art_cap, cluster=cl, trace_cap=0, device=device)
+    s1.set_capacity_check(True)
+    s1.upload(grids)
+    s1.run(64 * (m + n)); s1.sync()
+    t1 = []
+    for _ in range(reps):
+        if barrier:
+            barrier()
+        s1.run(64 * (m + n)); s1.sync()
+        t1.append(s1.info()["last_run_ms"])
+    i1 = s1.info()
+    st1 = s1.download(want_numbers=False).status
+    s1.close()
+    redo = np.nonzero(st1 == NN.NEED_PRIMES)[0]
+    t2 = [0.0]
+    if redo.size:
+        s2 = BatchExactSolver(int(redo.size), m, n, ps, art_cap=art_cap, cluster=cl, trace_cap=0, device=device)
+        s2.upload(np.ascontiguousarray(grids[redo]))
+        s2.run(64 * (m + n)); s2.sync()
+        t2 = []
+        for _ in range(reps):
+            s2.run(64 * (m + n)); s2.sync()
+            t2.append(s2.info()["last_run_ms"])
+        s2.close()
+    ms = float(np.median(t1)) + float(np.median(t2))
+    return {"primes_first": short, "cluster_first": i1["cluster"], "resident_first": i1["resident_clusters"],
+            "ms_first": float(np.median(t1)), "solved_again": int(redo.size), "ms_second": float(np.median(t2)),
+            "ms": ms, "node_lps_per_s": count / (ms * 1e-3), "optimal_first": int((st1 == 1).sum())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--count", type=int, default=4096)
@@ -94,40 +135,7 @@ def main():
         solver.close()
         # two tiers (what solve_batch does): half the primes with the per-LP capacity check, then the LPs that
         # asked for more primes again on the full set; device time of both launches
-        tier = None
-        short = len(primes) // 2
-        short += short & 1
-        if 2 <= short < len(primes):
-            from linear_program_solver_b200 import _native as NN
-            ps = sorted(primes)
-            s1 = BatchExactSolver(count, m, n, ps[:short], art_cap=art_cap, cluster=cl, trace_cap=0)
-            s1.set_capacity_check(True)
-            s1.upload(grids)
-            s1.run(64 * (m + n)); s1.sync()
-            t1 = []
-            for _ in range(a.reps):
-                s1.run(64 * (m + n)); s1.sync()
-                t1.append(s1.info()["last_run_ms"])
-            i1 = s1.info()
-            st1 = s1.download(want_numbers=False).status
-            s1.close()
-            redo = np.nonzero(st1 == NN.NEED_PRIMES)[0]
-            t2, i2 = [0.0], None
-            if redo.size:
-                s2 = BatchExactSolver(int(redo.size), m, n, ps, art_cap=art_cap, cluster=cl, trace_cap=0)
-                s2.upload(np.ascontiguousarray(grids[redo]))
-                s2.run(64 * (m + n)); s2.sync()
-                t2 = []
-                for _ in range(a.reps):
-                    s2.run(64 * (m + n)); s2.sync()
-                    t2.append(s2.info()["last_run_ms"])
-                i2 = s2.info()
-                s2.close()
-            ms2t = float(np.median(t1)) + float(np.median(t2))
-            tier = {"primes_first": short, "cluster_first": i1["cluster"], "resident_first": i1["resident_clusters"],
-                    "ms_first": float(np.median(t1)), "solved_again": int(redo.size), "ms_second": float(np.median(t2)),
-                    "ms": ms2t, "node_lps_per_s": count / (ms2t * 1e-3),
-                    "optimal_first": int((st1 == 1).sum())}
+        tier = time_two_tier(grids, primes, art_cap, cl, a.reps, m, n)
         # end to end with host buffers through the public call
         t0 = time.perf_counter()
         r2 = solve_batch(grids, cluster=cl)
@@ -172,18 +180,22 @@ def main_multi(a):
     m, n, count = a.m, 2 * a.m, a.count
     grids = np.stack([problems.hashed_dense_grid(m, rank * count + s) for s in range(count)]).astype(np.int32)
     art_cap, primes, bits = plan_batch(grids, device=local)
-    solver = BatchExactSolver(count, m, n, primes, art_cap=art_cap, cluster=int(a.cluster.split(",")[0]), trace_cap=0, device=local)
-    solver.upload(grids)
-    solver.run(64 * (m + n))
-    solver.sync()
-    times = []
-    for _ in range(a.reps):
-        dist.barrier()
+    tier = time_two_tier(grids, primes, art_cap, int(a.cluster.split(",")[0]), a.reps, m, n, device=local, barrier=dist.barrier)
+    if tier is None:
+        solver = BatchExactSolver(count, m, n, primes, art_cap=art_cap, cluster=int(a.cluster.split(",")[0]), trace_cap=0, device=local)
+        solver.upload(grids)
         solver.run(64 * (m + n))
         solver.sync()
-        times.append(solver.info()["last_run_ms"])
-    ok = int((solver.download(want_numbers=False).status == 1).sum())
-    solver.close()
+        times = []
+        for _ in range(a.reps):
+            dist.barrier()
+            solver.run(64 * (m + n))
+            solver.sync()
+            times.append(solver.info()["last_run_ms"])
+        ok = int((solver.download(want_numbers=False).status == 1).sum())
+        solver.close()
+    else:
+        times, ok = [tier["ms"]], tier["optimal_first"]
     dist.barrier()
     t0 = time.perf_counter()
     r2 = solve_batch(grids, device=local)
