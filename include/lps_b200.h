@@ -205,6 +205,11 @@ int lps_exact_info(lps_handle *h, int *nprimes, int *bad_prime, size_t *residue_
  * allocated primes and the number of extensions so far.  lps_exact_info's nprimes / residue_bytes describe the
  * working set. */
 int lps_exact_set_weights(lps_handle *h, const int *wcol, int guard_bits);
+/* lps_upload_exact and lps_exact_set_weights in one call: only the residue planes of the working set are allocated
+ * and encoded (the handle's other planes appear when an extension needs them). */
+int lps_upload_exact_weighted(lps_handle *h, const uint32_t *limbs, int nlimbs, const unsigned char *neg,
+                              size_t ld_host, const uint32_t *sigma_limbs, int sigma_nlimbs, const int *wcol,
+                              int guard_bits);
 int lps_exact_working(lps_handle *h, int *working, int *allocated, int *extensions);
 /* Loop state of Simplex.solve (simplex.py:117-137: rule in force, stuck counter, whether the
  * objective has moved since entry, pending objective check).  set == 0 reads it; set != 0 writes it

@@ -68,6 +68,7 @@ SIGNATURES = {
     "lps_exact_ld": (c_size_t, [c_int]),
     "lps_create_exact": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, POINTER(c_void_p)]),
     "lps_upload_exact": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_int]),
+    "lps_upload_exact_weighted": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_int, c_void_p, c_int]),
     "lps_read_exact": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lps_read_alive": (c_int, [c_void_p, c_void_p]),
     "lps_exact_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),

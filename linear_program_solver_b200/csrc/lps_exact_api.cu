@@ -12,7 +12,8 @@
 
 struct ExactData {
     int P = 0, spt = 1, lane_threads = 1024;   // P: primes of the working set (all kernels run on these)
-    int Pcap = 0;                               // allocated primes (sized by the caller's static bound)
+    int Pcap = 0;                               // primes of the handle (sized by the caller's static bound): tables cover all
+    int Palloc = 0;                             // residue planes actually allocated (grown with the working set)
     std::vector<uint32_t> primes_h;             // host copies for the working-set arithmetic
     std::vector<int> wexp_h;
     int* wcol = nullptr;                        // device [n+1] column weights (NULL until lps_exact_set_weights)
@@ -146,18 +147,8 @@ extern "C" int lps_create_exact(int m, int n, int nprimes, const uint32_t* prime
     k_xinvtab<<<dim3((P + 127) / 128, P), 128, 0, h->stream>>>(x->pr, P, x->invtab);
     CUX(cudaGetLastError());
 
-    const size_t bytes = (size_t)P * x->plane * sizeof(uint32_t);
-    {
-        cudaError_t e = cudaMalloc(&x->R, bytes);
-        if (e != cudaSuccess) { lpsx_destroy(h); return fail(LPS_E_NOMEM, "cudaMalloc of %zu bytes (%d primes) failed: %s", bytes, P, cudaGetErrorString(e)); }
-    }
-    CUX(cudaMemsetAsync(x->R, 0, bytes, h->stream));
-    x->stream_hint = bytes > kL2Bytes;
-    // column chunks of 2048 / 1024 residues, row blocks sized so that small tableaux still fill the SMs
-    const size_t cells = x->plane * P;
-    if (cells >= (size_t)148 * 8 * 2048 * 64) { x->chunk = 2048; x->rows_per_cta = 64; }
-    else if (cells >= (size_t)148 * 4 * 1024 * 16) { x->chunk = 1024; x->rows_per_cta = 16; }
-    else { x->chunk = 1024; x->rows_per_cta = 8; }
+    // the residue planes are allocated by the upload: all of them, or -- with column weights -- the working set only
+    x->R = nullptr; x->Palloc = 0;
     x->nbeta_ld = ((size_t)m + 1 + kXMaxRowBlock - 1) / kXMaxRowBlock * kXMaxRowBlock + kXMaxRowBlock;
     CUX(cudaMalloc(&x->nbeta, (size_t)P * x->nbeta_ld * sizeof(uint32_t)));
     CUX(cudaMemsetAsync(x->nbeta, 0, (size_t)P * x->nbeta_ld * sizeof(uint32_t), h->stream));
@@ -235,6 +226,24 @@ static int xwrite_state(lps_handle* h) {
 // bits (x 256) a number may have under the first P primes: |x| <= (M - 1) / 2, log2 M >= wexp[P] - 1
 static long long cap256(const ExactData* x, int P) { return 256LL * ((long long)x->wexp_h[P] - 2); }
 
+// at least `want` residue planes; the first `keep` planes survive a reallocation, new planes are zero
+static int ensure_planes(lps_handle* h, int want, int keep) {
+    ExactData* x = h->x;
+    if (want <= x->Palloc) return LPS_OK;
+    int np = std::min(x->Pcap, std::max(want, 2 * x->Palloc));
+    uint32_t* nr = nullptr;
+    cudaError_t e = cudaMalloc(&nr, (size_t)np * x->plane * sizeof(uint32_t));
+    if (e != cudaSuccess && np > want) { cudaGetLastError(); np = want; e = cudaMalloc(&nr, (size_t)np * x->plane * sizeof(uint32_t)); }
+    if (e != cudaSuccess) return fail(LPS_E_NOMEM, "cudaMalloc of %zu bytes (%d residue planes) failed: %s", (size_t)np * x->plane * sizeof(uint32_t), np, cudaGetErrorString(e));
+    keep = (x->R && keep > 0) ? std::min(keep, x->Palloc) : 0;
+    if (keep > 0) CU(cudaMemcpyAsync(nr, x->R, (size_t)keep * x->plane * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemsetAsync(nr + (size_t)keep * x->plane, 0, (size_t)(np - keep) * x->plane * sizeof(uint32_t), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (x->R) CU(cudaFree(x->R));
+    x->R = nr; x->Palloc = np;
+    return LPS_OK;
+}
+
 static int set_working(lps_handle* h, int P) {
     ExactData* x = h->x;
     x->P = P;
@@ -259,7 +268,7 @@ static int set_working(lps_handle* h, int P) {
 
 // smallest working set that leaves `head` (x 256 bits) of room above `need`
 static int pick_working(const ExactData* x, long long need, int at_least) {
-    const long long target = need + std::max(need / 2, 256LL * 96);
+    const long long target = need + std::max(need / 4, 256LL * 96);
     for (int P = std::max(1, at_least); P <= x->Pcap; ++P)
         if (cap256(x, P) >= target) return P;
     return x->Pcap;
@@ -294,6 +303,7 @@ static int grow_working(lps_handle* h) {
     const long long need = s.wnext + 2 * x->wmax256 + x->guard256;
     const int Pnew = pick_working(x, need, x->P + 1);
     if (Pnew > x->P) {
+        TRY(ensure_planes(h, Pnew, x->P));
         TRY(launch_extend<4>(h, Pnew, nullptr, (long long)(h->m + 1) * (h->n + 1)));
         TRY(launch_extend<4>(h, Pnew, x->Dres, 1));
         TRY(set_working(h, Pnew));
@@ -314,6 +324,7 @@ extern "C" int lps_exact_set_weights(lps_handle* h, const int* wcol, int guard_b
     NEED_MODE(h, 1);
     ExactData* x = h->x;
     if (!wcol || guard_bits < 0) return fail(LPS_E_INVALID, "bad weights");
+    if (!x->R) return fail(LPS_E_STATE, "upload first");
     long long wmax = 0;
     for (int j = 0; j <= h->n; ++j) {
         if (wcol[j] < 0) return fail(LPS_E_INVALID, "negative weight");
@@ -332,15 +343,27 @@ extern "C" int lps_exact_set_weights(lps_handle* h, const int* wcol, int guard_b
 // ------------------------------------------------------------------------------------------------
 // upload / read-out
 // ------------------------------------------------------------------------------------------------
-extern "C" int lps_upload_exact(lps_handle* h, const uint32_t* limbs, int nlimbs, const unsigned char* neg, size_t ld_host,
-                                const uint32_t* sigma_limbs, int sigma_nlimbs) {
-    USE(h);
-    NEED_MODE(h, 1);
+static int upload_common(lps_handle* h, const uint32_t* limbs, int nlimbs, const unsigned char* neg, size_t ld_host,
+                         const uint32_t* sigma_limbs, int sigma_nlimbs, const int* wcol, int guard_bits) {
     ExactData* x = h->x;
     if (!limbs || !neg || nlimbs <= 0 || ld_host < (size_t)h->n + 1) return fail(LPS_E_INVALID, "bad host grid");
     if (!sigma_limbs || sigma_nlimbs <= 0) return fail(LPS_E_INVALID, "bad row scales");
+    // which primes carry the tableau from the start: all of them, or the working set the weights ask for
+    int P0 = x->Pcap;
     x->adaptive = false;
-    TRY(set_working(h, x->Pcap));                        // encode for every allocated prime
+    if (wcol) {
+        if (guard_bits < 0) return fail(LPS_E_INVALID, "bad guard");
+        long long wmax = 0;
+        for (int j = 0; j <= h->n; ++j) {
+            if (wcol[j] < 0) return fail(LPS_E_INVALID, "negative weight");
+            wmax = std::max<long long>(wmax, wcol[j]);
+        }
+        x->wmax256 = wmax; x->guard256 = 256LL * guard_bits; x->adaptive = true; x->grows = 0;
+        P0 = pick_working(x, 2 * wmax + x->guard256, 1);
+    }
+    if (!x->adaptive) TRY(ensure_planes(h, x->Pcap, 0));
+    else if (x->Palloc < P0) TRY(ensure_planes(h, std::min(x->Pcap, std::max(2 * P0, 8)), 0));
+    TRY(set_working(h, P0));
     const size_t entries = (size_t)(h->m + 1) * ld_host;
     DevBuf b_limbs, b_neg, b_sig;
     CU(b_limbs.alloc(entries * nlimbs * sizeof(uint32_t)));
@@ -354,21 +377,44 @@ extern "C" int lps_upload_exact(lps_handle* h, const uint32_t* limbs, int nlimbs
     CU(cudaMemcpyAsync(d_sig, sigma_limbs, ((size_t)h->m + 1) * sigma_nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     const XGrid g = xgrid_of(h);
     const unsigned bx = (unsigned)std::min<size_t>((x->plane + 255) / 256, 148 * 8);
+    if (x->Palloc > x->P)                                    // planes beyond the working set: zero until an extension fills them
+        CU(cudaMemsetAsync(x->R + (size_t)x->P * x->plane, 0, (size_t)(x->Palloc - x->P) * x->plane * sizeof(uint32_t), h->stream));
     k_xencode<<<dim3(bx, x->P), 256, 0, h->stream>>>(g, d_limbs, nlimbs, d_neg, ld_host);
-    k_xencode_vec<<<dim3((h->m + 256) / 256, x->P), 256, 0, h->stream>>>(g, d_sig, sigma_nlimbs, h->m + 1, x->sigma, x->sstride);
+    k_xencode_vec<<<dim3((h->m + 256) / 256, x->Pcap), 256, 0, h->stream>>>(g, d_sig, sigma_nlimbs, h->m + 1, x->sigma, x->sstride);   // row scales: every prime
     h->launches_all += 2;
     CU(cudaGetLastError());
-    std::vector<uint32_t> ones(x->P, 1u);
-    CU(cudaMemcpyAsync(x->Dres, ones.data(), x->P * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    std::vector<uint32_t> ones(x->Pcap, 1u);
+    CU(cudaMemcpyAsync(x->Dres, ones.data(), x->Pcap * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     std::vector<int> alive(h->m + 1, 1);
     CU(cudaMemcpyAsync(x->alive, alive.data(), alive.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (x->adaptive) {
+        CU(cudaMemcpyAsync(x->wcol, wcol, ((size_t)h->n + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(x->xbasis, 0xff, (size_t)h->m * sizeof(int), h->stream));
+    }
     XState s{};
     s.status = LPS_OK; s.max_pivots = -1; s.sgnD = 1; s.c = s.r = s.last_r = s.last_c = -1; s.bad_prime = -1;
-    s.wlimit = 1LL << 62;
+    s.wsum = 0; s.wnext = 0; s.wlimit = x->adaptive ? wlimit_of(x, x->P) : (1LL << 62);
     *x->st_host = s;
     CU(cudaMemcpyAsync(x->st, x->st_host, sizeof(XState), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return LPS_OK;
+}
+
+extern "C" int lps_upload_exact(lps_handle* h, const uint32_t* limbs, int nlimbs, const unsigned char* neg, size_t ld_host,
+                                const uint32_t* sigma_limbs, int sigma_nlimbs) {
+    USE(h);
+    NEED_MODE(h, 1);
+    return upload_common(h, limbs, nlimbs, neg, ld_host, sigma_limbs, sigma_nlimbs, nullptr, 0);
+}
+
+// Upload with the column weights of lps_exact_set_weights in the same call: only the working set of residue planes
+// is allocated and encoded (C3: 5 planes of 8 MB instead of 362); the rest appears when an extension needs it.
+extern "C" int lps_upload_exact_weighted(lps_handle* h, const uint32_t* limbs, int nlimbs, const unsigned char* neg, size_t ld_host,
+                                         const uint32_t* sigma_limbs, int sigma_nlimbs, const int* wcol, int guard_bits) {
+    USE(h);
+    NEED_MODE(h, 1);
+    if (!wcol) return fail(LPS_E_INVALID, "null weights");
+    return upload_common(h, limbs, nlimbs, neg, ld_host, sigma_limbs, sigma_nlimbs, wcol, guard_bits);
 }
 
 template <int NB>
@@ -588,7 +634,7 @@ static int xensure_burst_graph(lps_handle* h, long long burst) {
     unsigned long long sig = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
     mix((unsigned long long)(uintptr_t)h->trace); mix((unsigned long long)h->trace_cap); mix(h->use_marks ? 1 : 0);
-    mix((unsigned long long)x->P); mix((unsigned long long)x->lane_threads); mix((unsigned long long)x->spt);
+    mix((unsigned long long)(uintptr_t)x->R); mix((unsigned long long)x->P); mix((unsigned long long)x->lane_threads); mix((unsigned long long)x->spt);
     mix((unsigned long long)x->chunk); mix((unsigned long long)x->rows_per_cta); mix(x->stream_hint ? 1 : 0);
     mix(x->adaptive ? 1 : 0); mix((unsigned long long)burst);
     if (h->gexec && h->gsig == sig && h->gburst == burst) return LPS_OK;

@@ -256,13 +256,16 @@ class ExactEngine:
             self._create(primes)
         sl, _, snl = to_limbs(sigma)
         limbs = np.ascontiguousarray(limbs)
-        N.check(self.L.lps_upload_exact(self.h, limbs.ctypes.data, nl, np.ascontiguousarray(neg).ctypes.data, self.n + 1,
-                                        sl.ctypes.data, snl))
+        neg = np.ascontiguousarray(neg)
         self.sigma = sigma
         if self.adaptive and self.forced_primes is None:
-            # working prime set: sized by the norms of the current basis columns, extended on the device on demand
+            # working prime set: sized by the norms of the current basis columns, extended on the device on demand;
+            # only its residue planes are allocated and encoded now
             wcol = np.ascontiguousarray(column_weights(G if G is not None else ints), dtype=np.int32)
-            N.check(self.L.lps_exact_set_weights(self.h, wcol.ctypes.data, sigma_bits + 3))
+            N.check(self.L.lps_upload_exact_weighted(self.h, limbs.ctypes.data, nl, neg.ctypes.data, self.n + 1,
+                                                     sl.ctypes.data, snl, wcol.ctypes.data, sigma_bits + 3))
+        else:
+            N.check(self.L.lps_upload_exact(self.h, limbs.ctypes.data, nl, neg.ctypes.data, self.n + 1, sl.ctypes.data, snl))
 
     def _read(self, what: int, index: int, count: int) -> List[int]:
         sign = np.empty(count, dtype=np.int8)
