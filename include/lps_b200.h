@@ -108,6 +108,15 @@ int lps_pivot(lps_handle *h, int r, int c);
 int lps_row_scale_f64(lps_handle *h, int r, double mult);
 int lps_row_axpy_f64(lps_handle *h, int rd, int rs, double mult);
 
+/* Leaving phase 1 on the device: Simplex._find_bfs simplex.py:95-105 when no constraint row is dropped
+ * (private-field surgery `_c = _c[:n]`, `_a[i] = _a[i][:n]` :95-100, then setZ / setC :101-102 and
+ * rowSubFromObj(i, c_{B_i}) for every row :104-105).  The trailing columns n_new..n-1 (the artificial
+ * variables) are cut -- the right-hand side moves to column n_new, the handle's n becomes n_new, ld and
+ * all buffers keep their sizes -- and the objective row becomes `cost` (n_new reduced costs followed by
+ * the _z cell) priced out against `basis` (m columns below n_new) in the reference's row order and
+ * rounding.  No host round trip of the tableau. */
+int lps_phase2_f64(lps_handle *h, int n_new, const double *cost, const int *basis);
+
 /* Simplex.findPivotStandard / findPivotMinIndex with do_pivot=False
  * (simplex.py:251-284, :218-249).  Returns LPS_OK with (*r,*c) set, or
  * LPS_OPTIMAL / LPS_UNBOUNDED. */
@@ -211,6 +220,18 @@ int lps_upload_exact_weighted(lps_handle *h, const uint32_t *limbs, int nlimbs, 
                               size_t ld_host, const uint32_t *sigma_limbs, int sigma_nlimbs, const int *wcol,
                               int guard_bits);
 int lps_exact_working(lps_handle *h, int *working, int *allocated, int *extensions);
+/* lps_phase2_f64 for the exact mode.  cost: n_new + 1 signed integers C_j = sigma_m c_j (limbs as in
+ * lps_upload_exact; C_n: the _z cell), sigma_m the new scale of the objective row (a multiple of every
+ * row scale and of the cost denominators); mult: m signed integers G_i = C_{basis[i]} / s_i with s_i
+ * the scale row i still carries (lps_read_alive) or 1.  The device computes N_mj = D C_j - sum_i G_i N_ij.
+ * From here on the tableau's numbers are minors of [constraint rows as uploaded ; C] over the basis
+ * columns of every row: wcol / guard_bits are that matrix's column weights (as for
+ * lps_exact_set_weights; ignored on a handle without a working prime set), and the prime set given to
+ * lps_create_exact must cover its Hadamard bound as well. */
+int lps_phase2_exact(lps_handle *h, int n_new, const uint32_t *cost_limbs, int cost_nlimbs,
+                     const unsigned char *cost_neg, const uint32_t *mult_limbs, int mult_nlimbs,
+                     const unsigned char *mult_neg, const uint32_t *sigma_m_limbs, int sigma_m_nlimbs,
+                     const int *basis, const int *wcol, int guard_bits);
 /* Loop state of Simplex.solve (simplex.py:117-137: rule in force, stuck counter, whether the
  * objective has moved since entry, pending objective check).  set == 0 reads it; set != 0 writes it
  * and makes the next lps_solve continue from it (resuming after LPS_BAD_PRIME on a re-encoded

@@ -50,6 +50,7 @@ SIGNATURES = {
     "lps_pivot": (c_int, [c_void_p, c_int, c_int]),
     "lps_row_scale_f64": (c_int, [c_void_p, c_int, c_double]),
     "lps_row_axpy_f64": (c_int, [c_void_p, c_int, c_int, c_double]),
+    "lps_phase2_f64": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "lps_find_pivot": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_int)]),
     "lps_find_pivot_max_increase": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
     "lps_find_pivot_all": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, POINTER(c_longlong)]),
@@ -74,6 +75,8 @@ SIGNATURES = {
     "lps_exact_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     "lps_exact_set_weights": (c_int, [c_void_p, c_void_p, c_int]),
     "lps_exact_working": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "lps_phase2_exact": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_int]),
     "lps_exact_loop_state": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_longlong), POINTER(c_int), POINTER(c_int)]),
     "lps_batch_smem_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "lps_batch_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_int, POINTER(c_int), POINTER(c_double)]),

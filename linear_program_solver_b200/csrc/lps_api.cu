@@ -325,6 +325,43 @@ extern "C" int lps_row_axpy_f64(lps_handle* h, int rd, int rs, double mult) {
     return LPS_OK;
 }
 
+// Leaving phase 1 without a host round trip of the tableau (Simplex._find_bfs simplex.py:95-105 when no row is
+// dropped): the artificial columns n_new..n-1 are cut, the objective row becomes `cost` (n_new reduced costs, then
+// the _z cell) priced out against the basis by the m rowSubFromObj steps of the reference, in its order and rounding.
+extern "C" int lps_phase2_f64(lps_handle* h, int n_new, const double* cost, const int* basis) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (h->nranks != 1) return fail(LPS_E_STATE, "lps_phase2_f64 on a sharded handle");
+    if (h->solving) return fail(LPS_E_STATE, "solve in progress");
+    if (!cost || !basis || n_new <= 0 || n_new > h->n) return fail(LPS_E_INVALID, "bad arguments (n_new = %d, n = %d)", n_new, h->n);
+    std::vector<double> mult(h->m);
+    for (int i = 0; i < h->m; ++i) {
+        if (basis[i] < 0 || basis[i] >= n_new) return fail(LPS_E_INVALID, "basis[%d] = %d is not a column below %d", i, basis[i], n_new);
+        mult[i] = -cost[basis[i]];
+    }
+    DevBuf b_vec;
+    const size_t nv = (size_t)h->m + 1 + (size_t)n_new + 1 + (size_t)h->m;
+    CU(b_vec.alloc(nv * sizeof(double)));
+    double* d_rhs = b_vec.as<double>();
+    double* d_cost = d_rhs + h->m + 1;
+    double* d_mult = d_cost + n_new + 1;
+    CU(cudaMemcpyAsync(d_cost, cost, ((size_t)n_new + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_mult, mult.data(), (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (n_new < h->n) {
+        k_gather_col_f64<<<std::max(1, std::min((h->m + 256) / 256, 592)), 256, 0, h->stream>>>(grid_of(h), h->n, d_rhs);
+        const long long cells = (long long)(h->m + 1) * (h->n - n_new + 1);
+        k_cut_cols_f64<<<(unsigned)std::max<long long>(1, std::min<long long>((cells + 255) / 256, 148 * 16)), 256, 0, h->stream>>>(grid_of(h), n_new, d_rhs);
+        h->launches_all += 2;
+        h->n = n_new;                                   // ld, launch plan and buffers keep their (larger) sizes
+        if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }   // the captured launches carry the old n
+    }
+    k_restore_obj_f64<<<(n_new + 1 + 127) / 128, 128, 0, h->stream>>>(grid_of(h), d_cost, d_mult);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));               // host vectors and the scratch buffer go out of scope
+    return LPS_OK;
+}
+
 extern "C" int lps_find_pivot(lps_handle* h, int rule, int* r, int* c) {
     USE(h);
     if (!r || !c || (rule != LPS_RULE_DANTZIG && rule != LPS_RULE_BLAND)) return fail(LPS_E_INVALID, "bad arguments");

@@ -857,8 +857,9 @@ __global__ void __launch_bounds__(256) k_xencode(XGrid g, const uint32_t* limbs,
         plane[x] = res;
     }
 }
-// same for a vector (the row scales): out[k*ostride + e]
-__global__ void __launch_bounds__(256) k_xencode_vec(XGrid g, const uint32_t* limbs, int nlimbs, int count, uint32_t* out, size_t ostride) {
+// same for a vector (the row scales; signed when `neg` is given): out[k*ostride + e]
+__global__ void __launch_bounds__(256) k_xencode_vec(XGrid g, const uint32_t* limbs, int nlimbs, int count, uint32_t* out, size_t ostride,
+                                                     const unsigned char* neg = nullptr) {
     const int k = blockIdx.y;
     const PrimeQ p = g.pr[k];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
@@ -871,8 +872,52 @@ __global__ void __launch_bounds__(256) k_xencode_vec(XGrid g, const uint32_t* li
             res += w;
             if (res >= p.q) res -= p.q;
         }
+        if (neg && neg[e] && res) res = p.q - res;
         out[(size_t)k * ostride + e] = res;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// leaving phase 1 on the device (Simplex._find_bfs simplex.py:95-105, every row kept)
+// ------------------------------------------------------------------------------------------------
+// rhs[k][i] <- N_i,n (the right-hand side column of every plane, before the columns are cut)
+__global__ void __launch_bounds__(256) k_xgather_rhs(XGrid g, uint32_t* rhs, size_t rstride) {
+    const int k = blockIdx.y;
+    const uint32_t* pl = g.R + (size_t)k * g.plane;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= g.m; i += gridDim.x * blockDim.x) rhs[(size_t)k * rstride + i] = pl[(size_t)i * g.ld + g.n];
+}
+// cut the trailing columns n_new..g.n-1 (the artificial variables): the right-hand side lands in column n_new, the
+// columns behind it become padding (zero)
+__global__ void __launch_bounds__(256) k_xcut_cols(XGrid g, int n_new, const uint32_t* rhs, size_t rstride) {
+    const int k = blockIdx.y, width = g.n - n_new + 1;
+    uint32_t* pl = g.R + (size_t)k * g.plane;
+    const long long total = (long long)(g.m + 1) * width;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+        const long long i = x / width;
+        const int jj = (int)(x - i * width);
+        pl[(size_t)i * g.ld + n_new + jj] = jj == 0 ? rhs[(size_t)k * rstride + i] : 0u;
+    }
+}
+// The original objective priced out against the current basis (setZ / setC, then rowSubFromObj(i, c_{B_i}) for every
+// row: simplex.py:101-105) in the fraction-free form: with C_j = sigma_m c_j (integers; C_n the _z cell) and
+// G_i = C_{B_i} / s_i (s_i: the scale row i still carries, or 1)
+//     N_mj <- D C_j - sum_i G_i N_ij      so that  N_mj / (D sigma_m) = c_j - sum_i c_{B_i} T_ij.
+// One thread per column and plane walks the rows (coalesced across the warp); rows with G_i = 0 are skipped.
+__global__ void __launch_bounds__(128) k_xrestore_obj(XGrid g, const uint32_t* Dres, const uint32_t* C, size_t cstride,
+                                                      const uint32_t* G, size_t gstride) {
+    const int k = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > g.n) return;
+    const PrimeQ p = g.pr[k];
+    uint32_t* pl = g.R + (size_t)k * g.plane;
+    const uint32_t* Gk = G + (size_t)k * gstride;
+    uint64_t sum = 0;                                            // plain residues: m < 2^31 terms below 2^31 each
+    for (int i = 0; i < g.m; ++i) {
+        const uint32_t gi = Gk[i];
+        if (gi == 0u) continue;
+        sum += mmul(mmul(gi, p.r2, p.q, p.qinv), pl[(size_t)i * g.ld + j], p.q, p.qinv);
+    }
+    const uint32_t dc = mmul(mmul(Dres[k], p.r2, p.q, p.qinv), C[(size_t)k * cstride + j], p.q, p.qinv);
+    pl[(size_t)g.m * g.ld + j] = msub(dc, (uint32_t)(sum % p.q), p.q);
 }
 
 // invtab[j*P+k] = Montgomery form of p_j^-1 mod p_k for j < k (0 elsewhere)

@@ -417,6 +417,95 @@ extern "C" int lps_upload_exact_weighted(lps_handle* h, const uint32_t* limbs, i
     return upload_common(h, limbs, nlimbs, neg, ld_host, sigma_limbs, sigma_nlimbs, wcol, guard_bits);
 }
 
+// Leaving phase 1 without a host round trip of the tableau (Simplex._find_bfs simplex.py:95-105 when no row is
+// dropped).  The artificial columns n_new..n-1 are cut and the objective row becomes the original objective priced
+// out against the basis (k_xrestore_obj).  cost: n_new + 1 signed integers C_j = sigma_m c_j (C_n: the _z cell);
+// mult: m signed integers G_i = C_{basis[i]} / s_i; sigma_m: the new scale of the objective row.  From here on the
+// numbers of the tableau are minors of the matrix [constraint rows as uploaded ; C] over the basis columns of ALL
+// rows: wcol holds that matrix's column weights (lps_exact_set_weights), every row's basis column counts, and the
+// working prime set is extended first if it must.  The caller sized the handle's prime set for that matrix too.
+extern "C" int lps_phase2_exact(lps_handle* h, int n_new, const uint32_t* cost_limbs, int cost_nlimbs, const unsigned char* cost_neg,
+                                const uint32_t* mult_limbs, int mult_nlimbs, const unsigned char* mult_neg,
+                                const uint32_t* sigma_m_limbs, int sigma_m_nlimbs, const int* basis, const int* wcol, int guard_bits) {
+    USE(h);
+    NEED_MODE(h, 1);
+    ExactData* x = h->x;
+    if (!x->R) return fail(LPS_E_STATE, "upload first");
+    if (n_new <= 0 || n_new > h->n) return fail(LPS_E_INVALID, "n_new = %d outside 1..%d", n_new, h->n);
+    if (!cost_limbs || !cost_neg || cost_nlimbs <= 0 || !mult_limbs || !mult_neg || mult_nlimbs <= 0 || !sigma_m_limbs ||
+        sigma_m_nlimbs <= 0 || !basis)
+        return fail(LPS_E_INVALID, "null argument");
+    for (int i = 0; i < h->m; ++i)
+        if (basis[i] < 0 || basis[i] >= n_new) return fail(LPS_E_INVALID, "basis[%d] = %d is not a column below %d", i, basis[i], n_new);
+    if (x->adaptive && (!wcol || guard_bits < 0)) return fail(LPS_E_INVALID, "the working prime set needs the new column weights");
+    TRY(xread_state(h));
+    if (x->st_host->status == LPS_NEED_PRIMES || x->st_host->status == LPS_BAD_PRIME) return fail(LPS_E_STATE, "a pivot is pending");
+
+    // 1. cut the artificial columns (nbeta is free between pivots: scratch for the right-hand side)
+    if (n_new < h->n) {
+        const XGrid g = xgrid_of(h);
+        k_xgather_rhs<<<dim3(std::max(1, std::min((h->m + 256) / 256, 64)), x->P), 256, 0, h->stream>>>(g, x->nbeta, x->nbeta_ld);
+        const long long cells = (long long)(h->m + 1) * (h->n - n_new + 1);
+        k_xcut_cols<<<dim3((unsigned)std::max<long long>(1, std::min<long long>((cells + 255) / 256, 148 * 4)), x->P), 256, 0, h->stream>>>(g, n_new, x->nbeta, x->nbeta_ld);
+        h->launches_all += 2;
+        CU(cudaGetLastError());
+        h->n = n_new;                                    // ld, planes and buffers keep their (larger) sizes
+        if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }   // the captured launches carry the old n
+    }
+
+    // 2. weights of the new matrix; every row's basis column counts from now on
+    if (x->adaptive) {
+        long long wmax = 0, wsum = 0;
+        for (int j = 0; j <= n_new; ++j) {
+            if (wcol[j] < 0) return fail(LPS_E_INVALID, "negative weight");
+            wmax = std::max<long long>(wmax, wcol[j]);
+        }
+        for (int i = 0; i < h->m; ++i) wsum += wcol[basis[i]];
+        x->wmax256 = wmax; x->guard256 = 256LL * guard_bits;
+        CU(cudaMemcpyAsync(x->wcol, wcol, ((size_t)n_new + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(x->xbasis, basis, (size_t)h->m * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        if (wsum > wlimit_of(x, x->P)) {                 // the restored objective row may not fit the working set
+            const int Pnew = pick_working(x, wsum + 2 * wmax + x->guard256, x->P + 1);
+            if (Pnew > x->P) {
+                TRY(ensure_planes(h, Pnew, x->P));
+                TRY(launch_extend<4>(h, Pnew, nullptr, (long long)(h->m + 1) * (h->n + 1)));
+                TRY(launch_extend<4>(h, Pnew, x->Dres, 1));
+                TRY(set_working(h, Pnew));
+                x->grows++;
+            }
+        }
+        XState& s = *x->st_host;
+        s.wsum = wsum; s.wnext = wsum; s.wlimit = wlimit_of(x, x->P);
+    }
+    x->st_host->status = LPS_OK;
+    TRY(xwrite_state(h));
+
+    // 3. residues of C and G on the working planes, of sigma_m on every prime; the new objective row
+    const XGrid g = xgrid_of(h);
+    const size_t cs = ((size_t)n_new + 1 + 3) / 4 * 4, gs = ((size_t)h->m + 3) / 4 * 4;
+    DevBuf b_cl, b_cn, b_ml, b_mn, b_sl, b_c, b_g;
+    CU(b_cl.alloc(((size_t)n_new + 1) * cost_nlimbs * sizeof(uint32_t)));
+    CU(b_cn.alloc((size_t)n_new + 1));
+    CU(b_ml.alloc((size_t)h->m * mult_nlimbs * sizeof(uint32_t)));
+    CU(b_mn.alloc((size_t)h->m));
+    CU(b_sl.alloc((size_t)sigma_m_nlimbs * sizeof(uint32_t)));
+    CU(b_c.alloc((size_t)x->P * cs * sizeof(uint32_t)));
+    CU(b_g.alloc((size_t)x->P * gs * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(b_cl.p, cost_limbs, ((size_t)n_new + 1) * cost_nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(b_cn.p, cost_neg, (size_t)n_new + 1, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(b_ml.p, mult_limbs, (size_t)h->m * mult_nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(b_mn.p, mult_neg, (size_t)h->m, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(b_sl.p, sigma_m_limbs, (size_t)sigma_m_nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    k_xencode_vec<<<dim3((n_new + 256) / 256, x->P), 256, 0, h->stream>>>(g, b_cl.as<uint32_t>(), cost_nlimbs, n_new + 1, b_c.as<uint32_t>(), cs, b_cn.as<unsigned char>());
+    k_xencode_vec<<<dim3((h->m + 255) / 256, x->P), 256, 0, h->stream>>>(g, b_ml.as<uint32_t>(), mult_nlimbs, h->m, b_g.as<uint32_t>(), gs, b_mn.as<unsigned char>());
+    k_xencode_vec<<<dim3(1, x->Pcap), 256, 0, h->stream>>>(g, b_sl.as<uint32_t>(), sigma_m_nlimbs, 1, x->sigma + h->m, x->sstride);
+    k_xrestore_obj<<<dim3((n_new + 1 + 127) / 128, x->P), 128, 0, h->stream>>>(g, x->Dres, b_c.as<uint32_t>(), cs, b_g.as<uint32_t>(), gs);
+    h->launches_all += 4;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));                // the scratch buffers go out of scope
+    return LPS_OK;
+}
+
 template <int NB>
 static int launch_garner(lps_handle* h, const GarnerJob& job) {
     const ExactData* x = h->x;

@@ -586,6 +586,37 @@ __global__ void k_gather_col_f64(F64Grid g, int j, double* out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// leaving phase 1 on the device (Simplex._find_bfs simplex.py:95-105, every row kept)
+// ------------------------------------------------------------------------------------------------
+// cut the trailing columns n_new..g.n-1 (the artificial variables): the right-hand side `rhs` (column g.n, gathered
+// before this launch) lands in column n_new, the columns behind it become padding (zero)
+__global__ void k_cut_cols_f64(F64Grid g, int n_new, const double* rhs) {
+    const int width = g.n - n_new + 1;
+    const long long total = (long long)(g.m + 1) * width;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+        const long long i = x / width;
+        const int jj = (int)(x - i * width);
+        g.T[(size_t)i * g.ld + n_new + jj] = jj == 0 ? rhs[i] : 0.0;
+    }
+}
+// setZ / setC followed by rowSubFromObj(i, c_{B_i}) for i = 0..m-1 (simplex.py:101-105 -> tableau.py:282-293): every
+// column adds mult_i * a_ij in row order, product and sum rounded separately like the reference's `c_j += m*a_rj`;
+// rows with a zero multiplier are skipped (tableau.py:285).  mult_i = -cost[B_i]: the basis columns are unit
+// vectors, so the objective row at B_i still holds cost[B_i] when row i's turn comes.
+__global__ void k_restore_obj_f64(F64Grid g, const double* cost, const double* mult) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > g.n) return;
+    double acc = cost[j];
+    const double* col = g.T + j;
+    for (int i = 0; i < g.m; ++i) {
+        const double ml = mult[i];
+        if (ml == 0.0) continue;
+        acc = __dadd_rn(acc, __dmul_rn(ml, col[(size_t)i * g.ld]));
+    }
+    g.T[(size_t)g.m * g.ld + j] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // whole-tableau pivot rules: Simplex.findPivotMaxIncrease simplex.py:286-328 and
 // Simplex.findPivotAll simplex.py:330-360.  Both run the ratio test of EVERY column: one thread per column walks
 // the rows (coalesced across the warp, the right-hand side is a broadcast load).

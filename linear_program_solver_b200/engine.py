@@ -144,6 +144,15 @@ class F64Engine:
     def row_axpy(self, rd: int, rs: int, mult: float):
         N.check(self.L.lps_row_axpy_f64(self.h, rd, rs, float(mult)))
 
+    def phase2(self, n_new: int, cost: np.ndarray, basis):
+        """Simplex._find_bfs simplex.py:95-105 on the device (`lps_phase2_f64`): cut the columns from n_new on, install
+        `cost` (n_new reduced costs, then the _z cell) priced out against `basis`."""
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        bas = np.ascontiguousarray(basis, dtype=np.int32)
+        assert cost.size == n_new + 1 and bas.size == self.m
+        N.check(self.L.lps_phase2_f64(self.h, n_new, cost.ctypes.data, bas.ctypes.data))
+        self.n = int(n_new)
+
     def find_pivot(self, rule: int):
         r, c = c_int(-1), c_int(-1)
         rc = N.check(self.L.lps_find_pivot(self.h, rule, byref(r), byref(c)))

@@ -116,6 +116,19 @@ def column_weights(G) -> List[int]:
     return [0 if s == 0 else max(0, math.ceil(128.0 * math.log2(s) * (1.0 + 1e-12)) + 1) for s in sums]
 
 
+def weights_from_squares(sq: Sequence[int]) -> List[int]:
+    """w >= 256 * log2(sqrt(s)) for exact squared column norms s (Python ints), 0 for s = 0."""
+    return [0 if s == 0 else max(0, math.ceil(128.0 * math.log2(s) * (1.0 + 1e-12)) + 1) for s in sq]
+
+
+def bound_bits_from_squares(row_sq: Sequence[float], col_sq: Sequence[float]) -> int:
+    """`hadamard_bits` from squared row and column norms (floats; one more guard bit for their rounding)."""
+    order = min(len(row_sq), len(col_sq))
+    by_rows = sum(math.log2(max(1.0, v)) for v in sorted(row_sq, reverse=True)[:order]) / 2
+    by_cols = sum(math.log2(max(1.0, v)) for v in sorted(col_sq, reverse=True)[:order]) / 2
+    return int(math.ceil(min(by_rows, by_cols))) + 3
+
+
 def primes_for_bits(bits: int, skip: Sequence[int] = ()) -> List[int]:
     """Enough primes that their product exceeds 2^(bits+2): symmetric range plus one guard bit."""
     need = bits + 2
@@ -227,8 +240,13 @@ class ExactEngine:
         N.check(self.L.lps_sync(self.h))
 
     # -- transfers -----------------------------------------------------------------------------
-    def upload(self, grid):
-        """grid: (m+1) x (n+1) Fractions / ints in device layout, or an int64 numpy array."""
+    def upload(self, grid, cost_hint=None):
+        """grid: (m+1) x (n+1) Fractions / ints in device layout, or an int64 numpy array.
+
+        cost_hint (phase 1, simplex.py:50-51): the original objective -- n0 <= n reduced costs followed by the _z
+        cell -- that `phase2` will install on the device once the artificial problem is solved.  The prime set is
+        then sized for the matrix [constraint rows ; that objective] as well."""
+        self.phase2_info = None
         if isinstance(grid, np.ndarray) and grid.dtype.kind in "iu":
             G = np.ascontiguousarray(grid, dtype=np.int64)
             ints = None
@@ -249,6 +267,10 @@ class ExactEngine:
             flat = [v for row in ints for v in row]
             limbs, neg, nl = to_limbs(flat)
         sigma_bits = max(s.bit_length() for s in sigma)
+        if cost_hint is not None:
+            hint_bits, self.phase2_info = self._prepare_phase2(cost_hint, G if G is not None else ints, sigma)
+            bits = max(bits, hint_bits)
+            sigma_bits = max(sigma_bits, self.phase2_info["sigma_m"].bit_length())
         bits += sigma_bits                               # "== 1" tests compare with D * sigma_i
         self.last_bits = bits
         primes = self.forced_primes if self.forced_primes is not None else primes_for_bits(bits, self.banned)
@@ -266,6 +288,75 @@ class ExactEngine:
                                                      sl.ctypes.data, snl, wcol.ctypes.data, sigma_bits + 3))
         else:
             N.check(self.L.lps_upload_exact(self.h, limbs.ctypes.data, nl, neg.ctypes.data, self.n + 1, sl.ctypes.data, snl))
+
+    # -- leaving phase 1 on the device ----------------------------------------------------------------
+    def _prepare_phase2(self, cost_hint, ints, sigma):
+        """The integer objective row C = sigma_m * cost that `phase2` installs, the squared column norms of the
+        uploaded constraint rows, and the bits of the Hadamard bound of the uploaded matrix with its objective row
+        replaced, entry by entry, by the larger of the two objective rows in magnitude (covers both phases)."""
+        m, n = self.m, self.n
+        n0 = len(cost_hint) - 1
+        assert 0 < n0 <= n
+        cq = [v if isinstance(v, Fraction) else Fraction(v) for v in cost_hint]
+        sigma_m = math.lcm(*[v.denominator for v in cq], *[int(s) for s in sigma[:m]])
+        C = [int(v * sigma_m) for v in cq]
+        wide = [0] * (n + 1)                              # C in the uploaded layout: artificial columns cost 0
+        wide[:n0] = C[:n0]
+        wide[n] = C[n0]
+        if isinstance(ints, np.ndarray):
+            A = ints[:m].astype(np.float64)
+            col_sq_a = [int(v) for v in (ints[:m].astype(object) ** 2).sum(axis=0)] if m * (n + 1) <= 1 << 16 else \
+                [int(math.ceil(v * (1.0 + 1e-9))) for v in (A * A).sum(axis=0)]
+            row_sq = [float(v) for v in (A * A).sum(axis=1)]
+            obj = [int(v) for v in ints[m]]
+        else:
+            col_sq_a = [0] * (n + 1)
+            row_sq = []
+            for row in ints[:m]:
+                acc = 0
+                for j, v in enumerate(row):
+                    if v:
+                        vv = v * v
+                        col_sq_a[j] += vv
+                        acc += vv
+                row_sq.append(float(acc))
+            obj = ints[m]
+        both = [max(abs(a), abs(b)) for a, b in zip(obj, wide)]
+        row_sq.append(float(sum(v * v for v in both)))
+        col_sq = [float(col_sq_a[j] + both[j] * both[j]) for j in range(n + 1)]
+        info = {"n0": n0, "C": C, "sigma_m": sigma_m, "col_sq_a": col_sq_a, "n_up": n}
+        return bound_bits_from_squares(row_sq, col_sq), info
+
+    def phase2(self, n_new: int, basis: Sequence[int]) -> bool:
+        """Simplex._find_bfs simplex.py:95-105 on the device (`lps_phase2_exact`): cut the artificial columns, install
+        the original objective priced out against `basis`.  False (nothing done) when the upload carried no cost hint
+        for this shape or the tableau has been re-encoded since."""
+        info = getattr(self, "phase2_info", None)
+        if info is None or self.h is None or info["n0"] != n_new or info["n_up"] != self.n or len(basis) != self.m:
+            return False
+        m = self.m
+        C, sigma_m = info["C"], info["sigma_m"]
+        alive = self._alive()
+        G = []
+        for i in range(m):
+            q, rem = divmod(C[basis[i]], self.sigma[i] if alive[i] else 1)
+            assert rem == 0
+            G.append(q)
+        sq = [info["col_sq_a"][j] + C[j] * C[j] for j in range(n_new)] + [info["col_sq_a"][self.n] + C[n_new] * C[n_new]]
+        wcol = np.ascontiguousarray(weights_from_squares(sq), dtype=np.int32)
+        sig = self.sigma[:m] + [sigma_m]
+        guard = max(s.bit_length() for s in sig) + 3
+        cl, cn, cnl = to_limbs(C)
+        gl, gn, gnl = to_limbs(G)
+        sl, _, snl = to_limbs([sigma_m])
+        cl, cn, gl, gn = (np.ascontiguousarray(a) for a in (cl, cn, gl, gn))
+        bas = np.ascontiguousarray(basis, dtype=np.int32)
+        N.check(self.L.lps_phase2_exact(self.h, n_new, cl.ctypes.data, cnl, cn.ctypes.data, gl.ctypes.data, gnl, gn.ctypes.data,
+                                        sl.ctypes.data, snl, bas.ctypes.data, wcol.ctypes.data, guard))
+        self.n = n_new
+        self.sigma = sig
+        self.phase2_info = None
+        return True
 
     def _read(self, what: int, index: int, count: int) -> List[int]:
         sign = np.empty(count, dtype=np.int8)

@@ -58,9 +58,11 @@ class Simplex:
             tab.setAij(i, n + ind, 1)
             tab.rowSubFromObj(i, 1)
             self._bfs[i] = n + ind
+        tab._expect_phase2(orig_c, orig_z)
         self.solve()
         z = tab.getZ()
         if z != 0:
+            tab._cost_hint = None
             raise ValueError(f"infeasible problem, artificial opt = {z}")
         rowkeep = [True] * m
         for i in range(m):
@@ -75,11 +77,14 @@ class Simplex:
                 self._pivot(i, j1)
         self._bfs = [j for i, j in enumerate(self._bfs) if rowkeep[i]]
         assert all(0 <= j < n for j in self._bfs), "invalid basic feasible solution (internal error)"
-        tab._delete(rowkeep, n)
-        tab.setZ(orig_z)
-        tab.setC(orig_c)
-        for i, j in enumerate(self._bfs):
-            tab.rowSubFromObj(i, tab.getCj(j))
+        # simplex.py:95-105.  With every row kept this is one device call (the tableau stays on the GPU); dropping a
+        # dependent row goes through the host-side re-layout, like the reference's private-field surgery.
+        if not (all(rowkeep) and tab._leave_phase1(n, orig_c, orig_z, self._bfs)):
+            tab._delete(rowkeep, n)
+            tab.setZ(orig_z)
+            tab.setC(orig_c)
+            for i, j in enumerate(self._bfs):
+                tab.rowSubFromObj(i, tab.getCj(j))
         if not all(rowkeep):
             # the reference leaves its row count stale after dropping a dependent row
             # (simplex.py:93) and fails on the next row scan; same exception, sane tableau

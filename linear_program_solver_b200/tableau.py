@@ -57,6 +57,8 @@ class Tableau:
         self._host_ok, self._dev_ok = True, False
         self._peek: dict = {}
         self._int_grid = None        # exact mode, from_grid(integer ndarray): uploaded as is, Fractions only on demand
+        self._cost_hint = None       # exact mode, phase 1: the objective `_leave_phase1` will install (sizes the prime set)
+        self.phase2_on_device = 0    # how many times `_leave_phase1` ran as a device call (tests look at it)
 
     # -- number handling -----------------------------------------------------------------
     def _num(self, x):
@@ -112,7 +114,11 @@ class Tableau:
     def _need_dev(self):
         eng = self._engine()
         if not self._dev_ok:
-            eng.upload(self._grid if self._host_ok else self._int_grid)
+            src = self._grid if self._host_ok else self._int_grid
+            if self._mode == "exact" and self._cost_hint is not None:
+                eng.upload(src, cost_hint=self._cost_hint)
+            else:
+                eng.upload(src)
             self._dev_ok = True
         return eng
 
@@ -324,6 +330,7 @@ class Tableau:
     # resizing / permutation / copy (tableau.py:184-250): host-side re-layout
     # ------------------------------------------------------------------------------------
     def _reshape_host(self, new_grid, m: int, n: int):
+        self._cost_hint = None
         self._grid = new_grid
         self._m, self._n = m, n
         self._drop_engine()
@@ -394,6 +401,32 @@ class Tableau:
         dup._cl = self._cl[:]
         dup._cm = self._cm[:]
         return dup
+
+    def _expect_phase2(self, cost: List[Any], z):
+        """Phase 1 is about to run on this tableau (simplex.py:50-61): remember the objective that `_leave_phase1`
+        installs afterwards, so that the exact mode sizes its prime set for it at the upload."""
+        self._cost_hint = [self._num(v) for v in cost] + [-self._num(z)] if self._mode == "exact" else None
+
+    def _leave_phase1(self, ncols: int, cost: List[Any], z, basis: List[int]) -> bool:
+        """What simplex.py:95-105 does when no row is dropped -- cut the columns from `ncols` on, setZ(z), setC(cost),
+        rowSubFromObj(i, c_{basis[i]}) for every row -- as one device call, without moving the tableau through the
+        host.  False (nothing done) when the device copy is not the valid one or the engine cannot do it."""
+        hint, self._cost_hint = self._cost_hint, None
+        if not self._dev_ok or self._eng is None or len(cost) != ncols:
+            return False
+        if self._mode == "fp64":
+            vec = np.array([self._num(v) for v in cost] + [-self._num(z)], dtype=np.float64)
+            self._eng.phase2(ncols, vec, basis)
+        elif hint is None or not self._eng.phase2(ncols, basis):
+            return False
+        self._n = ncols
+        self._cl = self._cl[:ncols]
+        self._cm = self._cm[:ncols]
+        self._host_ok = False
+        self._int_grid = None
+        self._peek.clear()
+        self.phase2_on_device += 1
+        return True
 
     def _delete(self, keep_rows: List[bool], ncols: int):
         """Drop constraint rows / trailing columns (what simplex.py:88-100 does through private fields)."""

@@ -83,6 +83,7 @@ def test_phase1_matches_float_oracle(m, n, seed):
         return
     t = _tab(c, A, b)
     s = Simplex(t)
+    assert t.phase2_on_device == 1                       # simplex.py:95-105 ran as `lps_phase2_f64`, not through the host
     n1 = len(want["phase1_pivots"])
     assert [list(p) for p in s.pivot_log] == [list(p) for p in want["phase1_pivots"]]
     assert s.getBasicSequence() == want["initial_basis"]
@@ -91,6 +92,48 @@ def test_phase1_matches_float_oracle(m, n, seed):
     assert s.getBasicSequence() == want["basis"]
     assert float(s.getObjValue()).hex() == float(want["objective"]).hex()
     assert t.getTableauSize() == (m, n)
+
+
+@pytest.mark.parametrize("m,n,k,seed", [(6, 10, 3, 0), (150, 260, 90, 1), (700, 1500, 400, 2)])
+def test_leave_phase1_kernels_match_the_row_operations(m, n, k, seed):
+    """`lps_phase2_f64` (cut of the trailing columns + objective restore) against the oracle's restatement of
+    simplex.py:95-105 -- `_c = _c[:n]`, setZ / setC, rowSubFromObj per basic row -- bit for bit, on a tableau that a
+    few pivots brought to a basis inside the first n columns.  (The float-rebound reference itself leaves phase 1 only
+    on tiny inputs: its `z != 0` test is exact.)"""
+    from linear_program_solver_b200 import Tableau
+    from oracle import lpsol_oracle as O
+    rng = np.random.default_rng(seed)
+    grid = rng.integers(-9, 10, size=(m + 1, n + k + 1)).astype(np.float64)
+    grid[:m, n - m:n] = np.eye(m)                          # a unit basis inside the first n columns
+    grid[m, n - m:n] = 0.0
+    t = Tableau.from_grid(grid.copy(), mode="fp64")
+    ref = [[float(x) for x in row] for row in grid]
+    basis = list(range(n - m, n))
+    for step in range(min(m, 5)):                          # pivots: the basis columns stay exact unit vectors
+        r, c = (step * 7) % m, step
+        if ref[r][c] == 0.0:
+            continue
+        t.pivot(r, c)
+        O.pivot(ref, r, c)
+        basis[r] = c
+    cost = [float(v) for v in rng.integers(-20, 21, size=n)]
+    cost[basis[0]] = 0.0                                   # a zero multiplier: the row is skipped (tableau.py:285)
+    z = 12.5
+    assert t._leave_phase1(n, cost, z, basis) and t.phase2_on_device == 1
+    want = [row[:n] + [row[n + k]] for row in ref]
+    want[m] = cost + [-z]
+    for i, j in enumerate(basis):
+        O.row_axpy(want, m, i, -want[m][j])
+    got = t._eng.download()
+    assert t.getTableauSize() == (m, n) and got.shape == (m + 1, n + 1)
+    assert got.tobytes() == np.array(want, dtype=np.float64).tobytes()
+    # the handle keeps working at its new width: one more pivot, compared again
+    r = 1 % m
+    c = next(j for j in range(n) if want[r][j] != 0.0 and j not in basis)
+    t.pivot(r, c)
+    O.pivot(want, r, c)
+    assert t._eng.download().tobytes() == np.array(want, dtype=np.float64).tobytes()
+    assert t.getZ() == -want[m][n]
 
 
 def test_special_cases_error_behaviour():

@@ -2,6 +2,7 @@
 
 Exact mode must reproduce the reference's pivot sequence, basis and rational results bit-for-bit, so
 every comparison here is `==` on ints / Fractions / pivot lists."""
+import math
 import random
 from fractions import Fraction
 
@@ -137,6 +138,7 @@ def test_phase1_matches_reference_exactly(rec):
             assert str(ei.value) == rec["ctor_error"][1]
         return
     s = Simplex(t)
+    assert t.phase2_on_device == 1                       # simplex.py:95-105 ran as `lps_phase2_exact`, not through the host
     n1 = len(rec["phase1_pivots"])
     assert [list(p) for p in s.pivot_log] == rec["phase1_pivots"]
     assert s.getBasicSequence() == rec["initial_basis"]
@@ -147,6 +149,41 @@ def test_phase1_matches_reference_exactly(rec):
     assert {str(j): str(v) for j, v in s.getBFS().items()} == rec["bfs"]
     assert [bool(x) for x in t.getVarMarks()] == rec["marks"]
     assert list(t.getTableauSize()) == rec["m_n"]
+
+
+@pytest.mark.parametrize("m,n,seed,rational", [(40, 72, 0, False), (60, 100, 1, False), (9, 16, 2, True), (14, 24, 3, True)])
+def test_phase1_leaves_on_the_device(m, n, seed, rational):
+    """Larger equality-form LPs (and rational data, whose rows carry scales): the whole constructor -- artificial
+    problem, drive-out pivots, cut of the artificial columns, objective restore (`lps_phase2_exact`) -- and the
+    phase-2 solve against the oracle; the tableau after the constructor is the oracle's, entry by entry; the prime
+    set stays the working set of the ORIGINAL matrix (no re-encoding of the pivoted tableau)."""
+    from linear_program_solver_b200 import Simplex
+    from oracle import lpsol_oracle as O
+    c, A, b = problems.equality_lp(m, n, seed)
+    if rational:
+        rng = random.Random(seed)
+        A = [[Fraction(v, rng.choice([1, 2, 3])) for v in row] for row in A]
+        c = [Fraction(v, rng.choice([1, 5])) for v in c]
+        b = [sum(A[i][j] * ((j * 7 + seed) % 5) for j in range(n)) for i in range(m)]
+    want = O.simplex(c, A, b)
+    t = _tab(c, A, b)
+    s = Simplex(t)
+    assert t.phase2_on_device == 1 and t.getTableauSize() == (m, n)
+    info = t._eng.info()
+    assert info["primes"] <= info["allocated_primes"] and t._eng.reencodes == 0
+    assert [tuple(p) for p in s.pivot_log] == [tuple(p) for p in want["phase1_pivots"]]
+    assert s.getBasicSequence() == want["initial_basis"]
+    if m <= 20:                                          # the tableau phase 2 starts from, entry by entry
+        g0 = O.make_grid(c, A, b)
+        g0, _ = O.find_bfs(g0)
+        assert t._eng.download() == g0
+    n1 = len(s.pivot_log)
+    s.solve()
+    assert [tuple(p) for p in s.pivot_log[n1:]] == [tuple(p) for p in want["pivots"]]
+    assert s.getBasicSequence() == want["basis"]
+    assert s.getObjValue() == want["objective"]
+    assert s.getBFS() == want["bfs"]
+    assert t._eng.reencodes == 0
 
 
 def test_special_cases():
@@ -263,3 +300,52 @@ def test_working_prime_set_covers_every_integer_of_a_solve():
         cap = sum(w[j] for j in xbasis if j >= 0) + max(w)
         big = max(max(abs(v) for row in N for v in row), abs(D))
         assert 256 * math.log2(big) <= cap
+
+
+# ---- full-size property check (BASELINE.json config 3): an exact optimality certificate -------------------------
+def test_c3_full_solve_carries_an_exact_optimality_certificate():
+    """C3 (exact 1000 x 2000, 8-bit coefficients) solved to optimality through the public API.  The reference needs
+    hours for this size, so instead of a recorded answer the result is proved on the CPU with Python integers,
+    independently of the device arithmetic: the reported basic solution satisfies A x = b, x >= 0 exactly; the
+    multipliers y read off the slack columns of the device's objective row reproduce EVERY reduced cost
+    d_j = c_j - y^T A_j exactly, all d_j >= 0, d_j = 0 on the basis; and c^T x = y^T b = the reported objective
+    (strong duality).  Together: the device's final tableau row, basis and rational objective are the exact optimum.
+    The pivot sequence's first six pivots are pinned by the reference fixture (dense_exact.json)."""
+    from linear_program_solver_b200 import Simplex, Tableau
+    m = 1000
+    c, A, b = problems.dense_lp(m, 0, 1, 127)
+    n = 2 * m
+    grid = np.array([A[i] + [b[i]] for i in range(m)] + [c + [0]], dtype=np.int64)
+    t = Tableau.from_grid(grid, mode="exact")
+    s = Simplex(t)
+    npiv = s.solve()
+    rec = next(r for r in load_golden("dense_exact") if r["m"] == m and r["hi"] == 127)
+    assert [list(p) for p in s.pivot_log[:len(rec["pivots"])]] == rec["pivots"]
+    assert npiv == len(s.pivot_log) > m // 2 and t.isOptimal()
+    basis = s.getBasicSequence()
+    assert len(set(basis)) == m
+    bfs, z = s.getBFS(), s.getObjValue()
+    d = t.getC()                                           # reduced costs, n Fractions (one Garner pass on the device)
+    assert z.denominator.bit_length() > 300                # a genuinely big rational, not a float-sized answer
+    # primal: A x = b, x >= 0, with one common denominator so that the products are integer
+    den = 1
+    for v in bfs.values():
+        den = den * v.denominator // math.gcd(den, v.denominator)
+    X = np.zeros(n, dtype=object)
+    for j, v in bfs.items():
+        assert v >= 0
+        X[j] = int(v * den)
+    Aobj = np.array(A, dtype=object)
+    assert ((Aobj @ X) == np.array(b, dtype=object) * den).all()
+    assert Fraction(int(np.dot(np.array(c, dtype=object), X)), den) == z
+    # dual: y_i = -d_(m+i) (slack columns are unit vectors with zero cost)
+    dd = 1
+    for v in d:
+        dd = dd * v.denominator // math.gcd(dd, v.denominator)
+    Dint = np.array([int(v * dd) for v in d], dtype=object)
+    assert all(v >= 0 for v in Dint) and all(Dint[j] == 0 for j in basis)
+    Y = -Dint[m:]
+    assert ((np.array(c, dtype=object) * dd - (Y @ Aobj)) == Dint).all()
+    assert Fraction(int(np.dot(Y, np.array(b, dtype=object))), dd) == z
+    info = t._eng.info()
+    assert info["primes"] < info["allocated_primes"]       # solved on the working prime set

@@ -78,3 +78,98 @@ def test_mixed_radix_decode():
             digits[k, e] = a % p
             a //= p
     assert codec.decode(sign, digits) == vals
+
+
+def _phase1_state(c, A, b):
+    """Run the oracle's phase 1 (simplex.py:36-94) up to, but not including, the cut of the artificial columns, keeping
+    the fraction-free integer state (N, D, alive) the device would hold next to the oracle's Fraction grid."""
+    grid = O.make_grid(c, A, b)
+    m, n = O.shape(grid)
+    for i in range(m):
+        if grid[i][n] < 0:
+            O.row_scale(grid, i, Fraction(-1))
+    basis = [-1] * m
+    assert not O.is_canonical(grid, basis)
+    cost, zcell = grid[m][:n], grid[m][n]
+    missing = [i for i in range(m) if basis[i] == -1]
+    k = len(missing)
+    for i in range(m + 1):
+        row = grid[i]
+        row[n:] = [Fraction(0)] * k + [row[n]]
+    for j in range(n):
+        grid[m][j] = Fraction(0)
+    grid[m][n + k] = Fraction(0)
+    for idx, i in enumerate(missing):
+        grid[m][n + idx] = Fraction(1)
+        grid[i][n + idx] = Fraction(1)
+        O.row_axpy(grid, m, i, Fraction(-1))
+        basis[i] = n + idx
+    ints, sigma = X.clear_denominators(grid)
+    N, D, alive = [row[:] for row in ints], 1, [1] * (m + 1)
+    trace = []
+    O.solve(grid, basis, trace)
+    assert O.objective(grid) == 0
+    for i in range(m):
+        if basis[i] >= n:
+            col = next(j for j in range(n) if grid[i][j] != 0)
+            O.pivot(grid, i, col)
+            basis[i] = col
+            trace.append((i, col, 2))
+    for r, cc, _ in trace:
+        D = O.bareiss_pivot(N, D, r, cc)
+        alive[r] = 0
+    den = lambda i: D * sigma[i] if alive[i] else D
+    assert all(Fraction(N[i][j], den(i)) == grid[i][j] for i in range(m + 1) for j in range(n + k + 1))
+    return grid, ints, sigma, N, D, alive, basis, cost, zcell, n, k
+
+
+@pytest.mark.parametrize("m,n,seed,rational", [(5, 9, 0, False), (8, 14, 1, False), (12, 20, 2, False), (6, 11, 3, True), (10, 17, 4, True)])
+def test_phase2_objective_formula_and_bounds(m, n, seed, rational):
+    """What `lps_phase2_exact` computes -- N_mj = D C_j - sum_i G_i N_ij with the integers `ExactEngine.phase2`
+    prepares -- is the reference's restored objective row (simplex.py:101-105) in the fraction-free form, it fits the
+    column-weight bound handed to the device, and the following pivots stay integral."""
+    c, A, b = problems.equality_lp(m, n, seed)
+    if rational:
+        rng = random.Random(seed)
+        A = [[Fraction(v, rng.choice([1, 2, 3])) for v in row] for row in A]
+        c = [Fraction(v, rng.choice([1, 5])) for v in c]
+        b = [sum(A[i][j] * ((j * 7 + seed) % 5) for j in range(n)) for i in range(m)]
+    grid, ints, sigma, N, D, alive, basis, cost, zcell, n, k = _phase1_state(c, A, b)
+    eng = object.__new__(X.ExactEngine)
+    eng.m, eng.n = m, n + k
+    bits, info = eng._prepare_phase2(cost + [zcell], ints, sigma)
+    assert bits >= X.hadamard_bits(ints) - 1
+    C, sigma_m = info["C"], info["sigma_m"]
+    assert all(Fraction(C[j], sigma_m) == (cost + [zcell])[j] for j in range(n + 1))
+    G = []
+    for i in range(m):
+        q, rem = divmod(C[basis[i]], sigma[i] if alive[i] else 1)
+        assert rem == 0
+        G.append(q)
+    cols = list(range(n)) + [n + k]                       # the columns that survive the cut
+    new_obj = [D * C[jj] - sum(G[i] * N[i][j] for i in range(m)) for jj, j in enumerate(cols)]
+    # the reference: cut, setZ / setC, rowSubFromObj per basic row
+    want = [row[:n] + [row[n + k]] for row in grid]
+    want[m] = cost + [zcell]
+    for i, j in enumerate(basis):
+        O.row_axpy(want, m, i, -want[m][j])
+    assert all(Fraction(new_obj[jj], D * sigma_m) == want[m][jj] for jj in range(n + 1))
+    assert all(want[m][j] == 0 for j in basis)
+    # magnitude: below the product of the basis columns' norms times the entry's own column norm
+    sq = [info["col_sq_a"][j] + C[jj] * C[jj] for jj, j in enumerate(cols)]
+    w = X.weights_from_squares(sq)
+    wsum = sum(w[j] for j in basis)
+    Nc = [[row[j] for j in cols] for row in N[:m]] + [new_obj]
+    for i in range(m + 1):
+        for jj in range(n + 1):
+            assert abs(Nc[i][jj]).bit_length() * 256 <= wsum + w[jj] + 256
+    assert abs(D).bit_length() * 256 <= wsum + 256
+    # phase 2 keeps dividing exactly (bareiss_pivot asserts it) and stays the reference's tableau
+    sig2 = sigma[:m] + [sigma_m]
+    trace = []
+    O.solve(want, basis[:], trace)
+    for r, cc, _ in trace:
+        D = O.bareiss_pivot(Nc, D, r, cc)
+        alive[r] = 0
+    den = lambda i: D * sig2[i] if alive[i] else D
+    assert all(Fraction(Nc[i][j], den(i)) == want[i][j] for i in range(m + 1) for j in range(n + 1))

@@ -9,6 +9,7 @@ Cases (seeded dense family of SURVEY.md section 8d):
   X2  exact 200 x 400, seed 0          GPU vs the oracle when it fits the CPU budget
   C3  exact 1000 x 2000, 8-bit         GPU only (the oracle needs hours); objective digits reported
   C2  fp64 2000 x 4000                 GPU vs oracle/pivot_oracle.c (all host cores), bit-identical objective checked
+  P1  exact equality-form LPs          phase 1 + drive-out + phase switch on the device + phase 2; 60 x 100 vs the oracle
 One JSON line per case.  Upload, set-up, solve and read-back are all inside the timed region.
 """
 import argparse
@@ -44,6 +45,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cpu-seconds", type=float, default=60.0, help="skip an oracle run expected to take longer")
     ap.add_argument("--skip-c3", action="store_true")
+    ap.add_argument("--only-phase1", action="store_true", help="only the equality-form (phase 1 + phase 2) cases")
     a = ap.parse_args()
     from linear_program_solver_b200 import problems
     from oracle import c_oracle as C
@@ -51,6 +53,23 @@ def main():
 
     gpu_solve(problems.to_grid(*problems.dense_lp(8, 1)), "exact")          # warm-up: library load, contexts
     gpu_solve(np.array(problems.to_grid(*problems.dense_lp(8, 1)), dtype=np.float64), "fp64")
+
+    # ---- P1: equality-form LPs (no slack basis): artificial problem, drive-out pivots, phase switch on the device ----
+    for (m, n, with_oracle) in ((60, 100, True), (200, 340, False), (400, 680, False)):
+        c, A, b = problems.equality_lp(m, n, 0)
+        dt, z, basis, k = gpu_solve(np.array(problems.to_grid(c, A, b), dtype=np.int64), "exact")
+        z = Fraction(z)
+        line = {"case": f"P1 exact equality-form {m}x{n}, seed 0 (phase 1 + phase 2)", "gpu_seconds": dt, "pivots": k,
+                "objective_numerator_bits": z.numerator.bit_length(), "objective_denominator_bits": z.denominator.bit_length(),
+                "cpu_oracle_seconds": None}
+        if with_oracle:
+            t0 = time.perf_counter()
+            want = O.simplex(c, A, b, num=Fraction)
+            line.update(cpu_oracle_seconds=time.perf_counter() - t0, identical=bool(z == want["objective"] and basis == want["basis"]))
+            line["speedup"] = line["cpu_oracle_seconds"] / dt
+        print(json.dumps(line), flush=True)
+    if a.only_phase1:
+        return
 
     # ---- C1: exact 50 x 100, ten seeds -------------------------------------------------------------
     tg = tc = 0.0
