@@ -268,9 +268,9 @@ def run_ours(a):
             z = s.getObjValue()
             x = s.getBFS()
             d2h_box[0] = 8 * (n + 1) + 8 * (m + 1) + 4 * m + 4 * n + 12 * B
-            t._drop_engine()
             t3 = time.perf_counter()
-            parts.append((t1 - t0, t2 - t1, t3 - t2))
+            t._drop_engine()                    # device buffers released inside the timed step (not part of read_back)
+            parts.append((t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3))
             return z, len(x)
     else:
         def e2e_step():
@@ -330,7 +330,8 @@ def run_ours(a):
                     "d2h_bytes_per_step": d2h_box[0], "steps": e2e_steps, "pivots_per_step": B,
                     "seconds_per_step": {"upload_and_setup": float(np.mean([p[0] for p in parts])),
                                          "pivots": float(np.mean([p[1] for p in parts])),
-                                         "read_back": float(np.mean([p[2] for p in parts]))},
+                                         "read_back": float(np.mean([p[2] for p in parts])),
+                                         "release": float(np.mean([p[3] for p in parts if len(p) > 3] or [0.0]))},
                     "api": "Tableau.from_grid + Simplex + solve(max_pivots)" if world == 1 else
                            "ShardedF64Solver: lps_upload_f64 + solve + read-back per rank"},
             "gpu_launches": int(all_launches),

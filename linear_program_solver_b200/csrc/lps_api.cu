@@ -26,6 +26,26 @@ int lps_fail(int code, const char* fmt, ...) {
     return code;
 }
 
+// pinned state mirrors, recycled (see lps_internal.h)
+#include <mutex>
+static std::mutex g_pin_mu;
+static std::vector<void*> g_pin_free;
+void* lps_pinned_get(size_t bytes) {
+    if (bytes > 256) return nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (!g_pin_free.empty()) { void* p = g_pin_free.back(); g_pin_free.pop_back(); return p; }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, 256) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void lps_pinned_put(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_free.push_back(p);
+}
+
 static F64Grid grid_of(const lps_handle* h) {
     F64Grid g;
     g.T = h->T; g.ld = h->ld; g.m = h->m; g.n = h->n; g.row0 = h->row0; g.m_total = h->m_total;
@@ -97,32 +117,38 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
     }
     plan(h);
     const size_t ucol_n = ((size_t)m + 1 + kMaxRowBlock - 1) / kMaxRowBlock * kMaxRowBlock + kMaxRowBlock;
-    CU(cudaMalloc(&h->ucol, ucol_n * sizeof(double)));
+    const int maxchunks = (int)((h->ld + kNarrowChunk - 1) / kNarrowChunk);
+    {   // the small buffers: one allocation (lps_internal.h, Slab)
+        Slab sl;
+        sl.add(&h->ucol, ucol_n);
+        sl.add(&h->d_peers, (size_t)kMaxRanks);
+        sl.add(&h->pd_val, (size_t)maxchunks);
+        sl.add(&h->pd_idx, (size_t)maxchunks);
+        sl.add(&h->pb_idx, (size_t)maxchunks);
+        sl.add(&h->sel_blk, (size_t)148 * 4);
+        sl.add(&h->st, (size_t)1);
+        sl.add(&h->scratch_i, 2 * (size_t)n + 16);
+        sl.add(&h->marks, (size_t)n);
+        h->cand_stride = lps_cand_bytes(n);
+        sl.add(&h->cand_send, h->cand_stride);           // replaced, never freed, when lps_set_shard passes the caller's slots
+        CU(sl.commit(&h->slab));
+    }
     CU(cudaMemsetAsync(h->ucol, 0, ucol_n * sizeof(double), h->stream));
-    h->cand_stride = lps_cand_bytes(n);
-    CU(cudaMalloc(&h->cand_send, h->cand_stride));
     CU(cudaMemsetAsync(h->cand_send, 0, h->cand_stride, h->stream));
     h->cand_all = h->cand_send;
-    h->own_cand = true;
+    h->own_cand = false;
     {
         const size_t xb = sizeof(XchgBlock) + h->ld * sizeof(double);
         CU(cudaMalloc(&h->xchg, xb));
         CU(cudaMemsetAsync(h->xchg, 0, xb, h->stream));
-        CU(cudaMalloc(&h->d_peers, kMaxRanks * sizeof(XchgBlock*)));
         CU(cudaMemcpyAsync(h->d_peers, &h->xchg, sizeof(XchgBlock*), cudaMemcpyHostToDevice, h->stream));
     }
-    const int maxchunks = (int)((h->ld + kNarrowChunk - 1) / kNarrowChunk);
-    CU(cudaMalloc(&h->pd_val, maxchunks * sizeof(double)));
-    CU(cudaMalloc(&h->pd_idx, maxchunks * sizeof(int)));
-    CU(cudaMalloc(&h->pb_idx, maxchunks * sizeof(int)));
-    CU(cudaMalloc(&h->sel_blk, 148 * 4 * sizeof(ArgMinF64)));
-    CU(cudaMalloc(&h->st, sizeof(SolveState)));
     CU(cudaMemsetAsync(h->st, 0, sizeof(SolveState), h->stream));
-    CU(cudaMallocHost(&h->st_host, sizeof(SolveState)));
-    CU(cudaMalloc(&h->basis, (size_t)m * sizeof(int)));
+    static_assert(sizeof(SolveState) <= 256, "pinned state blocks are 256 bytes");
+    h->st_host = (SolveState*)lps_pinned_get(sizeof(SolveState));
+    if (!h->st_host) return fail(LPS_E_NOMEM, "no pinned host memory for the state mirror");
+    CU(cudaMalloc(&h->basis, (size_t)m * sizeof(int)));        // its own allocation: re-sized by lps_set_shard / lps_p2p_attach
     CU(cudaMemsetAsync(h->basis, 0xff, (size_t)m * sizeof(int), h->stream));
-    CU(cudaMalloc(&h->scratch_i, (2 * (size_t)n + 16) * sizeof(int)));
-    CU(cudaMalloc(&h->marks, (size_t)n * sizeof(int)));
     CU(cudaMemsetAsync(h->marks, 0, (size_t)n * sizeof(int), h->stream));
     *out = h;
     return LPS_OK;
@@ -155,14 +181,14 @@ extern "C" int lps_destroy(lps_handle* h) {
     cudaStreamSynchronize(h->stream);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_T) cudaFree(h->T);
-    cudaFree(h->ucol);
     if (h->own_cand) cudaFree(h->cand_send);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     for (void* p : h->ipc_open) cudaIpcCloseMemHandle(p);
-    cudaFree(h->xchg); cudaFree(h->d_peers);
-    cudaFree(h->pd_val); cudaFree(h->pd_idx); cudaFree(h->pb_idx);
-    cudaFree(h->sel_blk); cudaFree(h->st); cudaFreeHost(h->st_host);
-    cudaFree(h->basis); cudaFree(h->marks); cudaFree(h->trace); cudaFree(h->scratch_i);
+    cudaFree(h->xchg);
+    cudaFree(h->slab);
+    lps_pinned_put(h->st_host);
+    cudaFree(h->basis);
+    if (h->trace) cudaFree(h->trace);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return LPS_OK;
@@ -209,8 +235,13 @@ extern "C" int lps_read_col_f64(lps_handle* h, int j, double* host) {
     USE(h);
     NEED_MODE(h, 0);
     if (!host || j < 0 || j > h->n) return fail(LPS_E_INVALID, "column %d out of range", j);
-    CU(cudaMemcpy2DAsync(host, sizeof(double), h->T + j, h->ld * sizeof(double), sizeof(double), (size_t)h->m + 1,
-                         cudaMemcpyDeviceToHost, h->stream));
+    // gathered on the device, then ONE contiguous copy (a strided 2-D copy of 8-byte rows costs a DMA descriptor per row)
+    DevBuf b_col;
+    CU(b_col.alloc(((size_t)h->m + 1) * sizeof(double)));
+    k_gather_col_f64<<<std::max(1, std::min((h->m + 256) / 256, 592)), 256, 0, h->stream>>>(grid_of(h), j, b_col.as<double>());
+    h->launches_all++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, b_col.p, ((size_t)h->m + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return LPS_OK;
 }

@@ -69,6 +69,11 @@ static PrimeQ make_prime(uint32_t q) {
     return p;
 }
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 #define CUX(call)                                                                                   \
     do {                                                                                            \
         cudaError_t e_ = (call);                                                                    \
@@ -97,8 +102,11 @@ extern "C" int lps_create_exact(int m, int n, int nprimes, const uint32_t* prime
     ExactData* x = new (std::nothrow) ExactData();
     if (!h || !x) { delete h; delete x; return fail(LPS_E_NOMEM, "out of host memory"); }
     h->mode = 1; h->x = x; h->device = device; h->m = m; h->n = n; h->m_total = m;
+    static const bool trace_alloc = getenv("LPS_TRACE_ALLOC") != nullptr;
+    const double tc0 = now_ms();
     if (stream) h->stream = (cudaStream_t)stream;
     else { CUX(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    const double tc1 = now_ms();
     const int P = nprimes;
     x->P = P; x->Pcap = P;
     x->primes_h.assign(primes, primes + P);
@@ -134,74 +142,73 @@ extern "C" int lps_create_exact(int m, int n, int nprimes, const uint32_t* prime
         }
     }
     x->wexp_h = we;
-    CUX(cudaMalloc(&x->pr, P * sizeof(PrimeQ)));
-    CUX(cudaMemcpyAsync(x->pr, pr.data(), P * sizeof(PrimeQ), cudaMemcpyHostToDevice, h->stream));
-    CUX(cudaMalloc(&x->half, P * sizeof(uint32_t)));
-    CUX(cudaMemcpyAsync(x->half, half.data(), P * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-    CUX(cudaMalloc(&x->wmant, (P + 1) * sizeof(double)));
-    CUX(cudaMemcpyAsync(x->wmant, wm.data(), (P + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CUX(cudaMalloc(&x->wexp, (P + 1) * sizeof(int)));
-    CUX(cudaMemcpyAsync(x->wexp, we.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CUX(cudaStreamSynchronize(h->stream));                // the host vectors go out of scope below
-    CUX(cudaMalloc(&x->invtab, (size_t)P * P * sizeof(uint32_t)));
-    k_xinvtab<<<dim3((P + 127) / 128, P), 128, 0, h->stream>>>(x->pr, P, x->invtab);
-    CUX(cudaGetLastError());
-
-    // the residue planes are allocated by the upload: all of them, or -- with column weights -- the working set only
-    x->R = nullptr; x->Palloc = 0;
+    // every small device buffer of the handle: one allocation (lps_internal.h, Slab)
     x->nbeta_ld = ((size_t)m + 1 + kXMaxRowBlock - 1) / kXMaxRowBlock * kXMaxRowBlock + kXMaxRowBlock;
-    CUX(cudaMalloc(&x->nbeta, (size_t)P * x->nbeta_ld * sizeof(uint32_t)));
-    CUX(cudaMemsetAsync(x->nbeta, 0, (size_t)P * x->nbeta_ld * sizeof(uint32_t), h->stream));
-    CUX(cudaMalloc(&x->Dres, P * sizeof(uint32_t)));
-    CUX(cudaMalloc(&x->dinv_m, P * sizeof(uint32_t)));
-    CUX(cudaMalloc(&x->alpha_m, P * sizeof(uint32_t)));
     x->sstride = ((size_t)m + 1 + 3) / 4 * 4;
-    CUX(cudaMalloc(&x->sigma, (size_t)P * x->sstride * sizeof(uint32_t)));
-    CUX(cudaMalloc(&x->one, (size_t)P * x->sstride * sizeof(uint32_t)));
-    CUX(cudaMalloc(&x->alive, ((size_t)m + 1) * sizeof(int)));
     const size_t nobj = (size_t)n + 1, ncr = 2 * ((size_t)m + 1), nrd = std::max(nobj, (size_t)m + 1);
-    CUX(cudaMalloc(&x->obj_sign, nobj)); CUX(cudaMalloc(&x->obj_top, nobj * sizeof(int))); CUX(cudaMalloc(&x->obj_mant, nobj * sizeof(double)));
-    CUX(cudaMalloc(&x->cr_sign, ncr)); CUX(cudaMalloc(&x->cr_top, ncr * sizeof(int))); CUX(cudaMalloc(&x->cr_mant, ncr * sizeof(double)));
-    CUX(cudaMalloc(&x->rd_sign, nrd)); CUX(cudaMalloc(&x->rd_top, nrd * sizeof(int))); CUX(cudaMalloc(&x->rd_mant, nrd * sizeof(double)));
     x->obj_dstride = (nobj + 7) / 8 * 8;
     x->rd_stride = (nrd + 7) / 8 * 8;
-    CUX(cudaMalloc(&x->obj_dig, (size_t)P * x->obj_dstride * sizeof(uint32_t)));
-    CUX(cudaMalloc(&x->rd_dig, (size_t)P * x->rd_stride * sizeof(uint32_t)));
-    CUX(cudaMalloc(&x->cand, (size_t)m * sizeof(int)));
-    CUX(cudaMalloc(&x->wcol, ((size_t)n + 1) * sizeof(int)));
-    CUX(cudaMalloc(&x->xbasis, (size_t)m * sizeof(int)));
-    CUX(cudaMalloc(&x->st, sizeof(XState)));
-    CUX(cudaMallocHost(&x->st_host, sizeof(XState)));
-    CUX(cudaMalloc(&h->basis, (size_t)m * sizeof(int)));
+    {
+        Slab sl;
+        sl.add(&x->pr, (size_t)P); sl.add(&x->half, (size_t)P); sl.add(&x->wmant, (size_t)P + 1); sl.add(&x->wexp, (size_t)P + 1);
+        sl.add(&x->invtab, (size_t)P * P);
+        sl.add(&x->nbeta, (size_t)P * x->nbeta_ld);
+        sl.add(&x->Dres, (size_t)P); sl.add(&x->dinv_m, (size_t)P); sl.add(&x->alpha_m, (size_t)P);
+        sl.add(&x->sigma, (size_t)P * x->sstride); sl.add(&x->one, (size_t)P * x->sstride);
+        sl.add(&x->alive, (size_t)m + 1);
+        sl.add(&x->obj_sign, nobj); sl.add(&x->obj_top, nobj); sl.add(&x->obj_mant, nobj);
+        sl.add(&x->cr_sign, ncr); sl.add(&x->cr_top, ncr); sl.add(&x->cr_mant, ncr);
+        sl.add(&x->rd_sign, nrd); sl.add(&x->rd_top, nrd); sl.add(&x->rd_mant, nrd);
+        sl.add(&x->obj_dig, (size_t)P * x->obj_dstride); sl.add(&x->rd_dig, (size_t)P * x->rd_stride);
+        sl.add(&x->cand, (size_t)m); sl.add(&x->wcol, (size_t)n + 1); sl.add(&x->xbasis, (size_t)m);
+        sl.add(&x->st, (size_t)1);
+        sl.add(&h->basis, (size_t)m); sl.add(&h->marks, (size_t)n); sl.add(&h->scratch_i, (size_t)n + 8);
+        CUX(sl.commit(&h->slab));
+    }
+    const double tc2 = now_ms();
+    CUX(cudaMemcpyAsync(x->pr, pr.data(), P * sizeof(PrimeQ), cudaMemcpyHostToDevice, h->stream));
+    CUX(cudaMemcpyAsync(x->half, half.data(), P * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CUX(cudaMemcpyAsync(x->wmant, wm.data(), (P + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUX(cudaMemcpyAsync(x->wexp, we.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    k_xinvtab<<<dim3((P + 127) / 128, P), 128, 0, h->stream>>>(x->pr, P, x->invtab);
+    CUX(cudaGetLastError());
+    // the residue planes are allocated by the upload: all of them, or -- with column weights -- the working set only
+    x->R = nullptr; x->Palloc = 0;
+    CUX(cudaMemsetAsync(x->nbeta, 0, (size_t)P * x->nbeta_ld * sizeof(uint32_t), h->stream));
+    static_assert(sizeof(XState) <= 256, "pinned state blocks are 256 bytes");
+    x->st_host = (XState*)lps_pinned_get(sizeof(XState));
+    if (!x->st_host) { lpsx_destroy(h); return fail(LPS_E_NOMEM, "no pinned host memory for the state mirror"); }
     CUX(cudaMemsetAsync(h->basis, 0xff, (size_t)m * sizeof(int), h->stream));
-    CUX(cudaMalloc(&h->marks, (size_t)n * sizeof(int)));
     CUX(cudaMemsetAsync(h->marks, 0, (size_t)n * sizeof(int), h->stream));
-    CUX(cudaMalloc(&h->scratch_i, ((size_t)n + 8) * sizeof(int)));
-    CUX(cudaStreamSynchronize(h->stream));
+    CUX(cudaStreamSynchronize(h->stream));                // the host vectors go out of scope below
+    if (trace_alloc) fprintf(stderr, "[lps] create: stream %.3f  tables+slab %.3f  copies+invtab+sync %.3f ms (P = %d)\n", tc1 - tc0, tc2 - tc1, now_ms() - tc2, P);
     *out = h;
     return LPS_OK;
 }
 
 int lpsx_destroy(lps_handle* h) {
     if (!h) return LPS_OK;
+    static const bool trace = getenv("LPS_TRACE_ALLOC") != nullptr;
+    const double t0 = now_ms();
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    const double t1 = now_ms();
     ExactData* x = h->x;
     if (x) {
-        cudaFree(x->pr); cudaFree(x->invtab); cudaFree(x->half); cudaFree(x->wmant); cudaFree(x->wexp);
-        cudaFree(x->R); cudaFree(x->Dres); cudaFree(x->dinv_m); cudaFree(x->alpha_m); cudaFree(x->nbeta);
-        cudaFree(x->sigma); cudaFree(x->one); cudaFree(x->alive);
-        cudaFree(x->obj_sign); cudaFree(x->obj_top); cudaFree(x->obj_mant); cudaFree(x->obj_dig);
-        cudaFree(x->cr_sign); cudaFree(x->cr_top); cudaFree(x->cr_mant);
-        cudaFree(x->rd_sign); cudaFree(x->rd_top); cudaFree(x->rd_mant); cudaFree(x->rd_dig);
-        cudaFree(x->cand); cudaFree(x->wcol); cudaFree(x->xbasis); cudaFree(x->st);
-        if (x->st_host) cudaFreeHost(x->st_host);
+        cudaFree(x->R);
+        lps_pinned_put(x->st_host);
         delete x;
     }
+    const double t2 = now_ms();
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    const double t3 = now_ms();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
-    cudaFree(h->basis); cudaFree(h->marks); cudaFree(h->trace); cudaFree(h->scratch_i);
+    cudaFree(h->slab);
+    if (h->trace) cudaFree(h->trace);
+    const double t4 = now_ms();
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    const double t5 = now_ms();
+    if (trace) fprintf(stderr, "[lps] destroy: sync %.3f  free R %.3f  graph %.3f  free slab+trace %.3f  stream %.3f ms\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4);
     delete h;
     return LPS_OK;
 }
@@ -351,6 +358,7 @@ static int upload_common(lps_handle* h, const uint32_t* limbs, int nlimbs, const
     // which primes carry the tableau from the start: all of them, or the working set the weights ask for
     int P0 = x->Pcap;
     x->adaptive = false;
+    x->grows = 0; x->resume = false;                    // a handle may serve several tableaux in a row (the host pools them)
     if (wcol) {
         if (guard_bits < 0) return fail(LPS_E_INVALID, "bad guard");
         long long wmax = 0;

@@ -66,6 +66,7 @@ struct lps_handle {
     int* trace = nullptr;
     long long trace_cap = 0;
     int* scratch_i = nullptr;        // n + 8 ints (isCanonical)
+    void* slab = nullptr;            // the one allocation the small device buffers are carved from
     bool solving = false;
 
     // a burst of (select, update) pairs captured once as a CUDA graph: small tableaux are launch bound on the host
@@ -91,6 +92,28 @@ struct DevBuf {
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
+
+// One device allocation carved into a handle's many small buffers: cudaMalloc / cudaFree cost a driver round trip
+// each (and a device synchronisation on free), which dominated the life of a small tableau (50 x 100: 7.6 ms of a
+// 13.6 ms solve).  add() records a pointer and its size, commit() allocates once and assigns the pointers.
+struct Slab {
+    struct Item { void** p; size_t off; };
+    std::vector<Item> items;
+    size_t total = 0;
+    template <typename T> void add(T** p, size_t count) {
+        items.push_back(Item{reinterpret_cast<void**>(p), total});
+        total += (count * sizeof(T) + 255) / 256 * 256;
+    }
+    cudaError_t commit(void** base) {
+        cudaError_t e = cudaMalloc(base, total ? total : 256);
+        if (e != cudaSuccess) return e;
+        for (const Item& it : items) *it.p = static_cast<char*>(*base) + it.off;
+        return cudaSuccess;
+    }
+};
+// Small pinned host blocks (the state mirrors): recycled process-wide instead of cudaMallocHost / cudaFreeHost per handle.
+void* lps_pinned_get(size_t bytes);          // bytes <= 256; NULL when the pinned allocation fails
+void lps_pinned_put(void* p);
 
 int lps_use(const lps_handle* h);
 #define USE(h)                         \

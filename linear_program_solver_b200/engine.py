@@ -23,6 +23,23 @@ def _torch():
     return torch
 
 
+# Closed engines of small tableaux (grid, stream, handle) wait here for the next tableau of the same shape: creating and
+# destroying a handle costs milliseconds of driver calls, more than a small solve, and an upload overwrites the whole
+# grid anyway.  Bounded in count and size; sharded, re-shaped (`phase2`) or profiled engines are destroyed instead.
+_ENGINE_POOL: dict = {}
+_ENGINE_POOL_MAX = 8
+_ENGINE_POOL_BYTES = 256 << 20
+
+
+def drain_engine_pool():
+    """Destroy every pooled engine (tests, memory-sensitive callers)."""
+    L = N.lib()
+    for lst in _ENGINE_POOL.values():
+        for grid, stream, h in lst:
+            L.lps_destroy(h)
+    _ENGINE_POOL.clear()
+
+
 class F64Engine:
     """fp64 tableau on one GPU.  Grid layout: see include/lps_b200.h."""
 
@@ -36,6 +53,15 @@ class F64Engine:
         self.device = int(device)
         self.m, self.n = int(m), int(n)
         self.ld = int(self.L.lps_grid_ld(self.n))
+        self.row0, self.m_total, self.rank, self.nranks = 0, self.m, 0, 1
+        self.cand_send = self.cand_all = None
+        self._pool_key = (self.device, self.m, self.n)
+        pooled = _ENGINE_POOL.get(self._pool_key)
+        if pooled:
+            self.grid, self.stream, self.h = pooled.pop()
+            with torch.cuda.stream(self.stream):
+                self.grid.zero_()                         # a new engine starts from a zero grid
+            return
         with torch.cuda.device(self.device):
             self.grid = torch.zeros((self.m + 1, self.ld), dtype=torch.float64, device=f"cuda:{self.device}")
             # A stream of our own, handed to the library by handle: torch's default stream has handle 0,
@@ -46,13 +72,16 @@ class F64Engine:
         h = c_void_p()
         N.check(self.L.lps_create_f64(self.m, self.n, self.device, self.grid.data_ptr(), self.stream.cuda_stream, byref(h)))
         self.h = h
-        self.row0, self.m_total, self.rank, self.nranks = 0, self.m, 0, 1
-        self.cand_send = self.cand_all = None
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "h", None):
-            self.L.lps_destroy(self.h)
+            key = getattr(self, "_pool_key", None)
+            small = (self.m + 1) * self.ld * 8 <= _ENGINE_POOL_BYTES
+            if key is not None and small and sum(len(v) for v in _ENGINE_POOL.values()) < _ENGINE_POOL_MAX:
+                _ENGINE_POOL.setdefault(key, []).append((self.grid, self.stream, self.h))
+            else:
+                self.L.lps_destroy(self.h)
             self.h = None
             self.grid = None
 
@@ -71,6 +100,7 @@ class F64Engine:
 
     # -- sharding ------------------------------------------------------------------------------
     def set_shard(self, row0: int, m_total: int, rank: int, nranks: int):
+        self._pool_key = None
         torch = _torch()
         nb = int(self.L.lps_cand_bytes(self.n))
         dev = f"cuda:{self.device}"
@@ -88,6 +118,7 @@ class F64Engine:
 
     def p2p_attach(self, row0: int, m_total: int, rank: int, nranks: int, handles: np.ndarray):
         """Map every rank's exchange block (handles: uint8 [nranks, 64] in rank order) and switch to peer stores."""
+        self._pool_key = None
         handles = np.ascontiguousarray(handles, dtype=np.uint8)
         assert handles.size == 64 * nranks
         N.check(self.L.lps_p2p_attach(self.h, row0, m_total, rank, nranks, handles.ctypes.data))
@@ -102,6 +133,7 @@ class F64Engine:
 
     def p2p_attach_local(self, row0: int, m_total: int, rank: int, nranks: int, blocks):
         """Peer-store exchange between engines driven by one process; blocks: `p2p_block()` of every rank."""
+        self._pool_key = None
         from ctypes import c_void_p
         arr = (c_void_p * nranks)(*[int(b) for b in blocks])
         N.check(self.L.lps_p2p_attach_local(self.h, row0, m_total, rank, nranks, arr))
@@ -152,6 +184,7 @@ class F64Engine:
         assert cost.size == n_new + 1 and bas.size == self.m
         N.check(self.L.lps_phase2_f64(self.h, n_new, cost.ctypes.data, bas.ctypes.data))
         self.n = int(n_new)
+        self._pool_key = None                            # the handle's width changed: not reusable for the old shape
 
     def find_pivot(self, rule: int):
         r, c = c_int(-1), c_int(-1)
@@ -212,6 +245,7 @@ class F64Engine:
 
     # -- stepping (sharded driver) -----------------------------------------------------------------
     def solve_begin(self, basis: Optional[np.ndarray], marks: Optional[np.ndarray], max_pivots: int, trace_cap: int):
+        self._pool_key = None                            # a stepped solve may be left open: not reusable
         N.check(self.L.lps_solve_begin(self.h, max_pivots, basis.ctypes.data if basis is not None else None,
                                        marks.ctypes.data if marks is not None else None, trace_cap))
 
@@ -236,6 +270,7 @@ class F64Engine:
 
     # -- profiling -----------------------------------------------------------------------------
     def prof_reset(self):
+        self._pool_key = None                            # per-launch profiling stays on for the handle's life
         N.check(self.L.lps_prof_reset(self.h))
 
     def prof_read(self):

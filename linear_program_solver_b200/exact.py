@@ -197,6 +197,28 @@ class MixedRadix:
 # ------------------------------------------------------------------------------------------------
 # engine
 # ------------------------------------------------------------------------------------------------
+# Closed handles wait here for the next tableau of the same shape and prime set: creating and destroying a handle
+# costs several milliseconds of driver calls (allocation, stream, captured graph) -- more than a 50 x 100 solve --
+# and every upload resets the whole device state anyway.  Bounded; handles whose shape was changed (`phase2`) or that
+# were switched to per-launch profiling are destroyed instead.
+_HANDLE_POOL: dict = {}
+_HANDLE_POOL_MAX = 8
+_HANDLE_POOL_BYTES = 4 << 30
+
+
+def _pool_size() -> int:
+    return sum(len(v) for v in _HANDLE_POOL.values())
+
+
+def drain_handle_pool():
+    """Destroy every pooled handle (tests, memory-sensitive callers)."""
+    L = N.lib()
+    for lst in _HANDLE_POOL.values():
+        for h in lst:
+            L.lps_destroy(h)
+    _HANDLE_POOL.clear()
+
+
 class ExactEngine:
     """Exact rational tableau on one GPU (same method surface as `engine.F64Engine`)."""
 
@@ -218,17 +240,29 @@ class ExactEngine:
     # -- lifetime ------------------------------------------------------------------------------
     def _create(self, primes: Sequence[int]):
         self.close()
-        arr = np.asarray(primes, dtype=np.uint32)
-        h = c_void_p()
-        N.check(self.L.lps_create_exact(self.m, self.n, len(primes), arr.ctypes.data, self.device, None, byref(h)))
+        key = (self.device, self.m, self.n, tuple(int(p) for p in primes))
+        pooled = _HANDLE_POOL.get(key)
+        if pooled:
+            h = pooled.pop()
+        else:
+            arr = np.asarray(primes, dtype=np.uint32)
+            h = c_void_p()
+            N.check(self.L.lps_create_exact(self.m, self.n, len(primes), arr.ctypes.data, self.device, None, byref(h)))
         self.h = h
+        self._pool_key = key
         self.primes = [int(p) for p in primes]
         self.codec = MixedRadix(self.primes)
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.lps_destroy(self.h)
+            key = getattr(self, "_pool_key", None)
+            small = (self.m + 1) * (self.n + 32) * 4 * len(self.primes) <= _HANDLE_POOL_BYTES   # bound on its residue planes
+            if key is not None and small and _pool_size() < _HANDLE_POOL_MAX:
+                _HANDLE_POOL.setdefault(key, []).append(self.h)
+            else:
+                self.L.lps_destroy(self.h)
         self.h = None
+        self._pool_key = None
 
     def __del__(self):
         try:
@@ -356,6 +390,7 @@ class ExactEngine:
         self.n = n_new
         self.sigma = sig
         self.phase2_info = None
+        self._pool_key = None                            # the handle's width changed: not reusable for the old shape
         return True
 
     def _read(self, what: int, index: int, count: int) -> List[int]:
@@ -480,6 +515,7 @@ class ExactEngine:
 
     # -- profiling -----------------------------------------------------------------------------
     def prof_reset(self):
+        self._pool_key = None                            # per-launch profiling stays on for the handle's life
         N.check(self.L.lps_prof_reset(self.h))
 
     def prof_read(self):

@@ -97,8 +97,8 @@ class Tableau:
 
     def _need_host(self):
         if not self._host_ok:
-            if self._int_grid is not None and not self._dev_ok:
-                self._grid = [[Fraction(int(x)) for x in row] for row in self._int_grid]
+            if self._int_grid is not None:           # still the tableau: every edit, host or device side, drops it
+                self._grid = [[Fraction(x) for x in row] for row in self._int_grid.tolist()]
             else:
                 self._grid = self._need_dev().download()
             self._int_grid = None
@@ -134,6 +134,8 @@ class Tableau:
         """Row i of the grid (n+1 values) without downloading the whole tableau."""
         if self._host_ok:
             return self._grid[i]
+        if self._int_grid is not None:
+            return [Fraction(x) for x in self._int_grid[i].tolist()]
         key = ("r", i)
         if key not in self._peek:
             self._peek[key] = self._need_dev().read_row(i)
@@ -145,6 +147,8 @@ class Tableau:
             if self._mode == "fp64":
                 return self._grid[:, j]
             return [row[j] for row in self._grid]
+        if self._int_grid is not None:
+            return [Fraction(x) for x in self._int_grid[:, j].tolist()]
         key = ("c", j)
         if key not in self._peek:
             self._peek[key] = self._need_dev().read_col(j)
@@ -321,7 +325,19 @@ class Tableau:
             t._grid = None
             t._host_ok = False
         else:
-            t._grid = [[x if isinstance(x, Fraction) else Fraction(x) for x in row] for row in grid]
+            # integer input (ints only, all below 2^62) takes the array route: nothing is converted entry by entry
+            ints = None
+            if all(type(x) is int for row in grid for x in row):
+                try:
+                    ints = np.array(grid, dtype=np.int64)
+                except (OverflowError, ValueError):
+                    ints = None
+            if ints is not None and ints.ndim == 2 and int(np.abs(ints).max(initial=0)) < (1 << 62):
+                t._int_grid = ints
+                t._grid = None
+                t._host_ok = False
+            else:
+                t._grid = [[x if type(x) is Fraction else Fraction(x) for x in row] for row in grid]
         if names:
             t._cl = list(names)
         return t
