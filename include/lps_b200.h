@@ -203,6 +203,18 @@ int lps_upload_exact(lps_handle *h, const uint32_t *limbs, int nlimbs, const uns
  * (p_0, p_1, ...): |x| = d_0 + d_1 p_0 + d_2 p_0 p_1 + ...   */
 int lps_read_exact(lps_handle *h, int what, int index, signed char *sign_out, uint32_t *digits_out);
 int lps_read_alive(lps_handle *h, int *alive);   /* m+1 flags: row still carries its sigma_i */
+/* Scattered cells (rows[e], cols[e]), e < count <= max(n, m) + 1 (getAij, tableau.py:98-100, for a list of cells):
+ * same outputs as lps_read_exact. */
+int lps_read_exact_cells(lps_handle *h, int count, const int *rows, const int *cols, signed char *sign_out,
+                         uint32_t *digits_out);
+/* Simplex.findPivotAll simplex.py:330-360 and the per-column half of Simplex.findPivotMaxIncrease :286-328 in exact
+ * mode: the ratio test of EVERY column on the device (a batch of columns per launch, one block per column, the
+ * floating filter and exact tie-break of the solve loop).  minrow[j], j < n: lowest row of minimum ratio
+ * b_i / a_ij over a_ij > 0 (strict "<" of simplex.py:308); -1: no positive entry; -2: column not tested
+ * (only_negative != 0 and c_j >= 0).  With tie_off (n+1 offsets) and ties: all rows of minimum ratio, ascending,
+ * column after column; at most ties_cap entries are written, tie_off[n] is their number. */
+int lps_exact_col_ratios(lps_handle *h, int only_negative, int *minrow, long long *tie_off, int *ties,
+                         long long ties_cap);
 int lps_exact_info(lps_handle *h, int *nprimes, int *bad_prime, size_t *residue_bytes);
 /* Working prime set.  lps_create_exact allocates the primes a static Hadamard bound of the uploaded matrix asks for;
  * the numbers of a tableau are minors over the CURRENT basis columns only, usually far smaller.  After

@@ -72,6 +72,8 @@ SIGNATURES = {
     "lps_upload_exact_weighted": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_int, c_void_p, c_int]),
     "lps_read_exact": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lps_read_alive": (c_int, [c_void_p, c_void_p]),
+    "lps_read_exact_cells": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lps_exact_col_ratios": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_longlong]),
     "lps_exact_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     "lps_exact_set_weights": (c_int, [c_void_p, c_void_p, c_int]),
     "lps_exact_working": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

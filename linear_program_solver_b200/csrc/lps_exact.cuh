@@ -266,7 +266,7 @@ __device__ __forceinline__ double garner_mant(const XGrid& g, const GarnerShared
 }
 
 // ---- batch reconstruction of a row, a column, the (column c, rhs) pair, or custom residues -----------
-enum { XSRC_ROW = 0, XSRC_COL = 1, XSRC_COLPAIR = 2, XSRC_CUSTOM = 3 };
+enum { XSRC_ROW = 0, XSRC_COL = 1, XSRC_COLPAIR = 2, XSRC_CUSTOM = 3, XSRC_COLPAIRS = 4 };   // 4: (column, rhs) pairs of columns index, index+1, ...
 struct GarnerJob {
     int src;                 // XSRC_*
     int index;               // row / column; column -1 means "the entering column st->c"
@@ -298,6 +298,10 @@ __global__ void __launch_bounds__(kLaneThreads) k_garner(XGrid g, const XState* 
                 if (job.src == XSRC_ROW) v = plane[(size_t)job.index * g.ld + e];
                 else if (job.src == XSRC_COL) v = plane[(size_t)e * g.ld + col];
                 else if (job.src == XSRC_COLPAIR) v = (e <= g.m) ? plane[(size_t)e * g.ld + col] : plane[(size_t)(e - g.m - 1) * g.ld + g.n];
+                else if (job.src == XSRC_COLPAIRS) {
+                    const int per = 2 * (g.m + 1), jj = e / per, rem = e - jj * per;
+                    v = (rem <= g.m) ? plane[(size_t)rem * g.ld + job.index + jj] : plane[(size_t)(rem - g.m - 1) * g.ld + g.n];
+                }
                 else v = job.custom[(size_t)k * job.cstride + e];
             }
             t[s][b] = v;
@@ -694,6 +698,152 @@ __global__ void __launch_bounds__(kLaneThreads) k_xforced(XGrid g, XState* st, X
         st->r = r; st->c = c; st->sgn_p = sg; st->sgn_br = 0; st->sel_rule = 2;
         if (bad >= 0) { st->bad_prime = bad; st->status = LPS_BAD_PRIME; }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole-tableau rules in exact mode (Simplex.findPivotAll simplex.py:330-360, the per-column half of
+// Simplex.findPivotMaxIncrease :286-328): the ratio test of MANY columns in one launch, one block per column, on
+// the numbers a XSRC_COLPAIRS reconstruction left in `cr` (2(m+1) per column: the column, then the right-hand side).
+// Same filter and exact tie-break as k_xratio; nothing of the solver state is touched.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_xdinv(XGrid g, XPivotConst pc) { compute_dinv(g, pc); }
+
+struct XColsArgs {
+    XGrid g;
+    const XState* st;
+    XMeta cr;                 // ncols * 2(m+1) numbers
+    const uint32_t* dinv_m;   // [P] Montgomery form of D^-1 (k_xdinv)
+    int j0, ncols;            // columns j0 .. j0+ncols-1
+    const signed char* obj_sign;   // objective row signs: only columns with c_j < 0 are tested; NULL: every column
+    int* cand;                // ncols * m ints of scratch
+    int* minrow;              // [ncols] lowest row of minimum ratio; -1: no positive entry; -2: column not tested
+    int* nties;               // [ncols] rows of minimum ratio (NULL: not wanted)
+    int* ties;                // [ncols * m] those rows, in no particular order
+};
+
+template <int SPT>
+__global__ void __launch_bounds__(kLaneThreads) k_xratio_cols(XColsArgs a) {
+    __shared__ GarnerShared<1> S;
+    __shared__ int s_cls[kLaneThreads], s_e[kLaneThreads];
+    __shared__ double s_f[kLaneThreads];
+    __shared__ int s_count, s_int, s_nt;
+    const XGrid& g = a.g;
+    const int tid = threadIdx.x, jj = blockIdx.x, c = a.j0 + jj, m = g.m, sgnD = a.st->sgnD;
+    if (a.obj_sign && (int)a.obj_sign[c] * sgnD >= 0) {         // c_j >= 0: not a candidate of findPivotMaxIncrease
+        if (tid == 0) { a.minrow[jj] = -2; if (a.nties) a.nties[jj] = 0; }
+        return;
+    }
+    const size_t off = (size_t)jj * 2 * (m + 1);
+    const signed char* sa = a.cr.sign + off;
+    const signed char* sb = sa + (m + 1);
+    const int* ta = a.cr.top + off;
+    const int* tb = ta + (m + 1);
+    const double* ma = a.cr.mant + off;
+    const double* mb = ma + (m + 1);
+    int* cand = a.cand + (size_t)jj * m;
+    int* ties = a.ties ? a.ties + (size_t)jj * m : nullptr;
+
+    auto key_of = [&](int i) {
+        RKey k;
+        k.cls = (int)sb[i] * (int)sa[i];
+        k.e = 0; k.f = 0.0;
+        if (k.cls != 0) {
+            int ex;
+            const double fr = frexp((mb[i] * g.wmant[tb[i]]) / (ma[i] * g.wmant[ta[i]]), &ex);
+            k.f = fr;
+            k.e = ex + g.wexp[tb[i]] - g.wexp[ta[i]];
+        }
+        return k;
+    };
+    // sign of N_kn N_rc - N_rn N_kc, exactly (block-uniform result)
+    auto cmp_rows = [&](int k, int r) {
+        uint32_t t[SPT][1];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            const int kk = tid + s * blockDim.x;
+            uint32_t v = 0u;
+            if (kk < g.P) {
+                const PrimeQ p = g.pr[kk];
+                const uint32_t* pl = g.R + (size_t)kk * g.plane;
+                const uint32_t x = mmul(pl[(size_t)k * g.ld + g.n], pl[(size_t)r * g.ld + c], p.q, p.qinv);
+                const uint32_t y = mmul(pl[(size_t)r * g.ld + g.n], pl[(size_t)k * g.ld + c], p.q, p.qinv);
+                v = mmul(mmul(msub(x, y, p.q), a.dinv_m[kk], p.q, p.qinv), p.r2, p.q, p.qinv);
+            }
+            t[s][0] = v;
+        }
+        __syncthreads();
+        block_garner<1, SPT>(g, t, S);
+        const int sg = garner_sign<1>(S, 0) * sgnD;
+        __syncthreads();
+        return sg;
+    };
+
+    RKey best{2, 0, 0.0};
+    for (int i = tid; i < m; i += blockDim.x) {
+        if ((int)sa[i] * sgnD <= 0) continue;
+        const RKey k = key_of(i);
+        if (rkey_less(k, best)) best = k;
+    }
+    s_cls[tid] = best.cls; s_e[tid] = best.e; s_f[tid] = best.f;
+    if (tid == 0) { s_count = 0; s_int = INT_MAX; s_nt = 0; }
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (tid < o) {
+            const RKey x{s_cls[tid], s_e[tid], s_f[tid]}, y{s_cls[tid + o], s_e[tid + o], s_f[tid + o]};
+            if (rkey_less(y, x)) { s_cls[tid] = y.cls; s_e[tid] = y.e; s_f[tid] = y.f; }
+        }
+        __syncthreads();
+    }
+    best = RKey{s_cls[0], s_e[0], s_f[0]};
+    __syncthreads();
+    if (best.cls == 2) {                                         // no positive entry in this column
+        if (tid == 0) { a.minrow[jj] = -1; if (a.nties) a.nties[jj] = 0; }
+        return;
+    }
+    int r;
+    if (best.cls == 0) {                                         // ratio exactly 0: every such row ties
+        int low = INT_MAX;
+        for (int i = tid; i < m; i += blockDim.x)
+            if ((int)sa[i] * sgnD > 0 && sb[i] == 0) {
+                low = min(low, i);
+                if (ties) ties[atomicAdd(&s_nt, 1)] = i;
+            }
+        low = __reduce_min_sync(0xffffffffu, low);
+        if ((tid & 31) == 0 && low != INT_MAX) atomicMin(&s_int, low);
+        __syncthreads();
+        r = s_int;
+    } else {
+        for (int i = tid; i < m; i += blockDim.x) {
+            if ((int)sa[i] * sgnD <= 0) continue;
+            const RKey k = key_of(i);
+            if (rkey_close(k, best)) cand[atomicAdd(&s_count, 1)] = i;
+        }
+        __syncthreads();
+        const int count = s_count;
+        r = cand[0];
+        for (int qi = 1; qi < count; ++qi) {
+            const int k = cand[qi];
+            const int sg = cmp_rows(k, r);
+            if (sg < 0 || (sg == 0 && k < r)) r = k;
+        }
+        if (ties) {                                              // rows whose ratio equals the minimum exactly
+            for (int qi = 0; qi < count; ++qi) {
+                const int k = cand[qi];
+                const int sg = (k == r) ? 0 : cmp_rows(k, r);
+                if (sg == 0 && tid == 0) ties[s_nt++] = k;
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) { a.minrow[jj] = r; if (a.nties) a.nties[jj] = s_nt; }
+}
+
+// residues of scattered cells (rows[e], cols[e]) as a XSRC_CUSTOM source: out[k*ostride + e]
+__global__ void __launch_bounds__(256) k_xgather_cells(XGrid g, const int* rows, const int* cols, int count, uint32_t* out, size_t ostride) {
+    const int k = blockIdx.y;
+    const uint32_t* pl = g.R + (size_t)k * g.plane;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x)
+        out[(size_t)k * ostride + e] = pl[(size_t)rows[e] * g.ld + cols[e]];
 }
 
 // ------------------------------------------------------------------------------------------------

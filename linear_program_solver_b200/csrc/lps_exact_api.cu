@@ -553,6 +553,102 @@ extern "C" int lps_read_exact(lps_handle* h, int what, int index, signed char* s
     return LPS_OK;
 }
 
+// Scattered cells (rows[e], cols[e]), e < count <= max(n, m) + 1, reconstructed like lps_read_exact does rows.
+extern "C" int lps_read_exact_cells(lps_handle* h, int count, const int* rows, const int* cols, signed char* sign_out, uint32_t* digits_out) {
+    USE(h);
+    NEED_MODE(h, 1);
+    ExactData* x = h->x;
+    if (count <= 0 || (size_t)count > x->rd_stride || !rows || !cols || !sign_out || !digits_out) return fail(LPS_E_INVALID, "bad arguments");
+    for (int e = 0; e < count; ++e)
+        if (rows[e] < 0 || rows[e] > h->m || cols[e] < 0 || cols[e] > h->n) return fail(LPS_E_INVALID, "cell (%d,%d) out of range", rows[e], cols[e]);
+    DevBuf b_idx, b_res;
+    CU(b_idx.alloc(2 * (size_t)count * sizeof(int)));
+    CU(b_res.alloc((size_t)x->P * count * sizeof(uint32_t)));
+    int* d_rows = b_idx.as<int>();
+    int* d_cols = d_rows + count;
+    CU(cudaMemcpyAsync(d_rows, rows, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_cols, cols, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    k_xgather_cells<<<dim3((count + 255) / 256, x->P), 256, 0, h->stream>>>(xgrid_of(h), d_rows, d_cols, count, b_res.as<uint32_t>(), (size_t)count);
+    h->launches_all++;
+    GarnerJob job{};
+    job.check_status = 0;
+    job.meta = XMeta{x->rd_sign, x->rd_top, x->rd_mant};
+    job.dig = x->rd_dig; job.dstride = x->rd_stride;
+    job.src = XSRC_CUSTOM; job.custom = b_res.as<uint32_t>(); job.cstride = (size_t)count; job.count = count; job.index = 0;
+    TRY(launch_garner<8>(h, job));
+    CU(cudaMemcpyAsync(sign_out, x->rd_sign, count, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpy2DAsync(digits_out, (size_t)count * sizeof(uint32_t), x->rd_dig, x->rd_stride * sizeof(uint32_t),
+                         (size_t)count * sizeof(uint32_t), x->P, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+
+// Simplex.findPivotAll (simplex.py:330-360) and the per-column half of Simplex.findPivotMaxIncrease (:286-328) in
+// exact mode: the ratio test of every column on the device, a batch of columns per launch pair (reconstruction of
+// the (column, rhs) pairs, then k_xratio_cols: one block per column).  minrow[j] (n ints): the lowest row of minimum
+// ratio b_i / a_ij over a_ij > 0; -1: no positive entry; -2: column not tested (only_negative and c_j >= 0).  With
+// tie_off (n + 1 offsets) and ties: every row of minimum ratio, ascending, column after column; at most ties_cap
+// entries are written, tie_off[n] is the total.
+extern "C" int lps_exact_col_ratios(lps_handle* h, int only_negative, int* minrow, long long* tie_off, int* ties, long long ties_cap) {
+    USE(h);
+    NEED_MODE(h, 1);
+    ExactData* x = h->x;
+    if (!minrow || (tie_off && ties_cap > 0 && !ties) || ties_cap < 0) return fail(LPS_E_INVALID, "bad arguments");
+    if (!x->R) return fail(LPS_E_STATE, "upload first");
+    const int m = h->m, n = h->n;
+    const long long per = 2LL * (m + 1);
+    const int batch = (int)std::max<long long>(1, std::min<long long>(n, (1LL << 22) / per));
+    const bool want_ties = tie_off != nullptr;
+    DevBuf b_sign, b_top, b_mant, b_cand, b_min, b_nt, b_ties;
+    CU(b_sign.alloc((size_t)batch * per));
+    CU(b_top.alloc((size_t)batch * per * sizeof(int)));
+    CU(b_mant.alloc((size_t)batch * per * sizeof(double)));
+    CU(b_cand.alloc((size_t)batch * m * sizeof(int)));
+    CU(b_min.alloc((size_t)batch * sizeof(int)));
+    if (want_ties) { CU(b_nt.alloc((size_t)batch * sizeof(int))); CU(b_ties.alloc((size_t)batch * m * sizeof(int))); }
+    if (only_negative) {                                  // signs of the reduced costs
+        GarnerJob job{};
+        job.src = XSRC_ROW; job.index = m; job.count = n + 1; job.check_status = 0;
+        job.meta = XMeta{x->obj_sign, x->obj_top, x->obj_mant};
+        TRY(launch_garner<8>(h, job));
+    }
+    k_xdinv<<<1, 1024, 0, h->stream>>>(xgrid_of(h), pconst_of(h));
+    h->launches_all++;
+    std::vector<int> h_nt(batch), h_ties;
+    if (want_ties) h_ties.resize((size_t)batch * m);
+    long long total = 0;
+    for (int j0 = 0; j0 < n; j0 += batch) {
+        const int nc = std::min(batch, n - j0);
+        GarnerJob cj{};
+        cj.src = XSRC_COLPAIRS; cj.index = j0; cj.count = (int)(nc * per); cj.check_status = 0;
+        cj.meta = XMeta{b_sign.as<signed char>(), b_top.as<int>(), b_mant.as<double>()};
+        TRY(launch_garner<8>(h, cj));
+        XColsArgs a{xgrid_of(h), x->st, cj.meta, x->dinv_m, j0, nc, only_negative ? x->obj_sign : nullptr,
+                    b_cand.as<int>(), b_min.as<int>(), want_ties ? b_nt.as<int>() : nullptr, want_ties ? b_ties.as<int>() : nullptr};
+        if (x->spt == 1) k_xratio_cols<1><<<nc, kLaneThreads, 0, h->stream>>>(a);
+        else k_xratio_cols<kMaxSPT><<<nc, kLaneThreads, 0, h->stream>>>(a);
+        h->launches_all++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(minrow + j0, b_min.p, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        if (want_ties) {
+            CU(cudaMemcpyAsync(h_nt.data(), b_nt.p, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(h_ties.data(), b_ties.p, (size_t)nc * m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        if (want_ties) {
+            for (int jj = 0; jj < nc; ++jj) {
+                tie_off[j0 + jj] = total;
+                int* src = h_ties.data() + (size_t)jj * m;
+                std::sort(src, src + h_nt[jj]);
+                for (int t = 0; t < h_nt[jj]; ++t, ++total)
+                    if (total < ties_cap) ties[total] = src[t];
+            }
+        }
+    }
+    if (want_ties) tie_off[n] = total;
+    return LPS_OK;
+}
+
 extern "C" int lps_read_alive(lps_handle* h, int* alive) {
     USE(h);
     NEED_MODE(h, 1);

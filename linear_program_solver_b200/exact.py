@@ -471,6 +471,68 @@ class ExactEngine:
             return "unbounded"
         return r.value, c.value
 
+    # -- whole-tableau rules (simplex.py:286-360) ---------------------------------------------------------
+    def read_cells(self, rows: Sequence[int], cols: Sequence[int]) -> List[Fraction]:
+        """Entries (rows[e], cols[e]) as Fractions (one reconstruction pass on the device)."""
+        count = len(rows)
+        if count == 0:
+            return []
+        out: List[Fraction] = []
+        D, alive = self.denominator(), self._alive()
+        step = max(self.n, self.m) + 1
+        for lo in range(0, count, step):
+            rr = np.ascontiguousarray(rows[lo:lo + step], dtype=np.int32)
+            cc = np.ascontiguousarray(cols[lo:lo + step], dtype=np.int32)
+            k = rr.size
+            sign = np.empty(k, dtype=np.int8)
+            digits = np.zeros((len(self.primes), k), dtype=np.uint32)
+            N.check(self.L.lps_read_exact_cells(self.h, k, rr.ctypes.data, cc.ctypes.data, sign.ctypes.data, digits.ctypes.data))
+            vals = self.codec.decode(sign, digits)
+            out += [Fraction(v, self._row_den(D, alive, int(i))) for v, i in zip(vals, rr)]
+        return out
+
+    def col_ratios(self, only_negative: bool, want_ties: bool = False):
+        """Minimum-ratio row of every column (`lps_exact_col_ratios`): (minrow [n], tie lists or None)."""
+        minrow = np.empty(self.n, dtype=np.int32)
+        if not want_ties:
+            N.check(self.L.lps_exact_col_ratios(self.h, 1 if only_negative else 0, minrow.ctypes.data, None, None, 0))
+            return minrow, None
+        off = np.zeros(self.n + 1, dtype=np.int64)
+        cap = self.n + self.m
+        while True:
+            ties = np.empty(max(cap, 1), dtype=np.int32)
+            N.check(self.L.lps_exact_col_ratios(self.h, 1 if only_negative else 0, minrow.ctypes.data, off.ctypes.data,
+                                                ties.ctypes.data, cap))
+            if off[self.n] <= cap:
+                return minrow, [ties[off[j]:off[j + 1]].tolist() for j in range(self.n)]
+            cap = int(off[self.n])
+
+    def find_pivot_all(self):
+        """Simplex.findPivotAll (simplex.py:330-360): every (row, column) of minimum ratio, column by column."""
+        _, ties = self.col_ratios(False, want_ties=True)
+        return [(i, j) for j, rows in enumerate(ties) for i in rows]
+
+    def find_pivot_max_increase(self):
+        """Simplex.findPivotMaxIncrease (simplex.py:286-328).  The m x n part -- the ratio test of every column with
+        c_j < 0 -- runs on the device; what is left is one exact product per candidate column, -c_j * b_i / a_ij,
+        compared in column order with the reference's strict ">" (first column among equals)."""
+        minrow, _ = self.col_ratios(True)
+        cand = [j for j in range(self.n) if minrow[j] != -2]
+        if not cand:
+            return "optimal"
+        if any(minrow[j] == -1 for j in cand):
+            return "unbounded"
+        rows = [int(minrow[j]) for j in cand]
+        cost = self.read_row(self.m)
+        rhs = self.read_col(self.n)
+        piv = self.read_cells(rows, cand)
+        best, si, sj = None, -1, -1
+        for j, i, a in zip(cand, rows, piv):
+            inc = -cost[j] * (rhs[i] / a)
+            if best is None or inc > best:
+                best, si, sj = inc, i, j
+        return si, sj
+
     def is_canonical(self, want_cols: bool = True, cols: Optional[np.ndarray] = None):
         """(canonical?, bcols).  The library leaves bcols untouched when some b_i < 0 (tableau.py:476-477): pass
         `cols` pre-filled to tell."""

@@ -191,79 +191,19 @@ class Simplex:
 
     def findPivotMaxIncrease(self, do_pivot: bool = False) -> PivotResult:
         """pivot of maximum objective decrease (simplex.py:286-328).  Not on the solve path (SURVEY.md section 8f
-        rank 3).  fp64 mode: one pass over the device tableau (`lps_find_pivot_max_increase`); exact mode: evaluated
-        over a snapshot of the tableau with the reference's Fraction arithmetic."""
-        tab = self._tab
-        if tab.mode == "fp64":
-            found = tab._need_dev().find_pivot_max_increase()
-            if isinstance(found, str):
-                return found
-            if do_pivot:
-                self._pivot(*found)
+        rank 3).  The ratio test of every column with c_j < 0 is one pass over the device tableau
+        (`lps_find_pivot_max_increase`; exact mode: `lps_exact_col_ratios`, then one exact product per column)."""
+        found = self._tab._need_dev().find_pivot_max_increase()
+        if isinstance(found, str):
             return found
-        return self._max_increase_host(do_pivot)
-
-    def _max_increase_host(self, do_pivot: bool = False) -> PivotResult:
-        tab = self._tab
-        m, n = tab.getTableauSize()
-        cost, b = tab._row(m), tab._col(n)
-        best = None
-        si, sj = -1, -1
-        any_negative = False
-        for j in range(n):
-            cj = cost[j]
-            if cj >= 0:
-                continue
-            any_negative = True
-            col = tab._col(j)
-            ratio = colinc = None
-            isel = -1
-            for i in range(m):
-                if col[i] <= 0:
-                    continue
-                r = b[i] / col[i]
-                if ratio is None or r < ratio:
-                    ratio, colinc, isel = r, -cj * r, i
-                elif r == ratio and colinc is not None and -cj * r > colinc:
-                    colinc, isel = -cj * r, i
-            if colinc is None:
-                return "unbounded"
-            if best is None or colinc > best:
-                best = colinc
-                si, sj = isel, j
-        if not any_negative:
-            return "optimal"
         if do_pivot:
-            self._pivot(si, sj)
-        return si, sj
+            self._pivot(*found)
+        return found
 
     def findPivotAll(self) -> List[Tuple[int, int]]:
-        """every pivot that keeps canonical form (simplex.py:330-360).  fp64 mode: on the device
-        (`lps_find_pivot_all`); exact mode: snapshot evaluation."""
-        tab = self._tab
-        if tab.mode == "fp64":
-            return tab._need_dev().find_pivot_all()
-        return self._find_all_host()
-
-    def _find_all_host(self) -> List[Tuple[int, int]]:
-        tab = self._tab
-        m, n = tab.getTableauSize()
-        b = tab._col(n)
-        out: List[Tuple[int, int]] = []
-        for j in range(n):
-            col = tab._col(j)
-            ratio = None
-            picks: List[Tuple[int, int]] = []
-            for i in range(m):
-                if col[i] <= 0:
-                    continue
-                r = b[i] / col[i]
-                if ratio is None or r < ratio:
-                    ratio, picks = r, [(i, j)]
-                elif r == ratio:
-                    picks.append((i, j))
-            out += picks
-        return out
+        """every pivot that keeps canonical form (simplex.py:330-360): the ratio test of every column on the device
+        (`lps_find_pivot_all` / `lps_exact_col_ratios`)"""
+        return self._tab._need_dev().find_pivot_all()
 
     # ------------------------------------------------------------------------------------
     # text (simplex.py:362-379)

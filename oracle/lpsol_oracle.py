@@ -163,6 +163,61 @@ def find_pivot(grid: Grid, rule: int):
     return r, c
 
 
+def find_pivot_max_increase(grid: Grid):
+    """`Simplex.findPivotMaxIncrease` with do_pivot=False (simplex.py:286-328): among the columns with c_j < 0,
+    the pivot of largest objective decrease -c_j * min ratio; within a column the first row of minimum ratio
+    (the tie clause of :316-318 never fires: equal ratios give equal decreases), across columns the first
+    column among equals (strict ">", :323); 'unbounded' as soon as a column with c_j < 0 has no positive entry."""
+    m, n = shape(grid)
+    best = None
+    si = sj = -1
+    any_negative = False
+    for j in range(n):
+        cj = grid[m][j]
+        if cj >= 0:
+            continue
+        any_negative = True
+        ratio = colinc = None
+        isel = -1
+        for i in range(m):
+            aij = grid[i][j]
+            if aij <= 0:
+                continue
+            r = grid[i][n] / aij
+            if ratio is None or r < ratio:
+                ratio, colinc, isel = r, -cj * r, i
+            elif r == ratio and colinc is not None and -cj * r > colinc:
+                colinc, isel = -cj * r, i
+        if colinc is None:
+            return UNBOUNDED
+        if best is None or colinc > best:
+            best, si, sj = colinc, isel, j
+    if not any_negative:
+        return OPTIMAL
+    return si, sj
+
+
+def find_pivot_all(grid: Grid) -> List[Tuple[int, int]]:
+    """`Simplex.findPivotAll` (simplex.py:330-360): for every column, all rows of minimum ratio b_i / a_ij over
+    a_ij > 0, rows ascending, column after column."""
+    m, n = shape(grid)
+    out: List[Tuple[int, int]] = []
+    for j in range(n):
+        ratio = None
+        picks: List[Tuple[int, int]] = []
+        for i in range(m):
+            aij = grid[i][j]
+            if aij <= 0:
+                continue
+            r = grid[i][n] / aij
+            if ratio is None or r < ratio:
+                ratio, picks = r, [(i, j)]
+            elif r == ratio:
+                picks.append((i, j))
+        out += picks
+    return out
+
+
 def is_optimal(grid: Grid) -> bool:
     """`Tableau.isOptimal` (tableau.py:500-502)."""
     m, n = shape(grid)

@@ -218,13 +218,12 @@ def test_whole_tableau_rules_on_the_device_match_the_snapshot_evaluation(m, seed
     """findPivotMaxIncrease / findPivotAll (simplex.py:286-360): the device pass against the host evaluation that
     follows the reference line by line, at every state along a solve (small integer data: many ratio ties)."""
     from linear_program_solver_b200 import Simplex
+    from oracle import lpsol_oracle as O
     c, A, b = problems.dense_lp(m, seed, 1, hi)
     s = Simplex(_tab(c, A, b))
     for step in range(3 * m):
-        t = s._tab
-        t._need_host()                                            # the host evaluation reads a snapshot
-        want_max, want_all = s._max_increase_host(), s._find_all_host()
-        t._need_dev()
+        snap = [[float(x) for x in row] for row in s._tab._eng.download()]     # the oracle reads a snapshot
+        want_max, want_all = O.find_pivot_max_increase(snap), O.find_pivot_all(snap)
         assert s.findPivotMaxIncrease() == want_max, step
         assert s.findPivotAll() == want_all, step
         if isinstance(want_max, str):
@@ -236,12 +235,30 @@ def test_whole_tableau_rules_on_the_device_match_the_snapshot_evaluation(m, seed
         raise AssertionError("did not reach the optimum")
 
 
+@pytest.mark.parametrize("rec", [r for r in load_golden("rules") if "float" in r], ids=lambda r: f"m{r['m']}s{r['seed']}")
+def test_whole_tableau_rules_match_float_rebound_reference(rec):
+    """The same rules against the reference's own answers (float-rebound run, tests/golden/rules.json)."""
+    from linear_program_solver_b200 import Simplex
+    c, A, b = problems.dense_lp(rec["m"], rec["seed"], rec["lo"], rec["hi"])
+    s = Simplex(_tab(c, A, b))
+    for step, want in enumerate(rec["float"]):
+        got = s.findPivotMaxIncrease()
+        assert (list(got) if isinstance(got, tuple) else got) == want["max_increase"], step
+        assert [list(p) for p in s.findPivotAll()] == want["all"], step
+        if isinstance(got, str):
+            break
+        nxt = s.findPivotMaxIncrease(True) if step % 2 else s.findPivotStandard(True)
+        assert not isinstance(nxt, str)
+
+
 def test_max_increase_reports_unbounded_and_optimal():
     from linear_program_solver_b200 import Simplex
     unb = _tab([-1, -2, 0], [[1, -1, 1]], [1])                  # column 1 is attractive and has no positive entry
+    from oracle import lpsol_oracle as O
     s = Simplex(unb)
-    assert s.findPivotMaxIncrease() == "unbounded" == s._max_increase_host()
+    assert s.findPivotMaxIncrease() == "unbounded" == O.find_pivot_max_increase(O.make_grid([-1, -2, 0], [[1, -1, 1]], [1], num=float))
     opt = _tab([1, 2, 0], [[1, 1, 1]], [1])
     s = Simplex(opt)
-    assert s.findPivotMaxIncrease() == "optimal" == s._max_increase_host()
-    assert s.findPivotAll() == s._find_all_host()
+    g = O.make_grid([1, 2, 0], [[1, 1, 1]], [1], num=float)
+    assert s.findPivotMaxIncrease() == "optimal" == O.find_pivot_max_increase(g)
+    assert s.findPivotAll() == O.find_pivot_all(g)

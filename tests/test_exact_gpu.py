@@ -349,3 +349,47 @@ def test_c3_full_solve_carries_an_exact_optimality_certificate():
     assert Fraction(int(np.dot(Y, np.array(b, dtype=object))), dd) == z
     info = t._eng.info()
     assert info["primes"] < info["allocated_primes"]       # solved on the working prime set
+
+
+# ---- whole-tableau rules in exact mode (lps_exact_col_ratios) ---------------------------------------------------
+def _walk_rules(s, states):
+    for step, want in enumerate(states):
+        got = s.findPivotMaxIncrease()
+        assert (list(got) if isinstance(got, tuple) else got) == want["max_increase"], step
+        assert [list(p) for p in s.findPivotAll()] == want["all"], step
+        if isinstance(got, str):
+            return
+        nxt = s.findPivotMaxIncrease(True) if step % 2 else s.findPivotStandard(True)
+        assert not isinstance(nxt, str)
+
+
+@pytest.mark.parametrize("rec", load_golden("rules"), ids=lambda r: f"{r['family']}m{r['m']}s{r['seed']}")
+def test_whole_tableau_rules_match_reference(rec):
+    """findPivotMaxIncrease / findPivotAll (simplex.py:286-360) against the unmodified reference's answers at every
+    state of the recorded walk; the ratio tests of all columns run on the device (many equal ratios in this data)."""
+    from linear_program_solver_b200 import Simplex
+    if rec["family"] == "dense":
+        c, A, b = problems.dense_lp(rec["m"], rec["seed"], rec["lo"], rec["hi"])
+    else:
+        c, A, b = problems.equality_lp(rec["m"], rec["n"], rec["seed"])
+    _walk_rules(Simplex(_tab(c, A, b)), rec["exact"])
+
+
+def test_whole_tableau_rules_larger_against_the_oracle():
+    """150 x 300 with 1..3 coefficients: heavy ties, several batches of columns; oracle on a downloaded snapshot."""
+    from linear_program_solver_b200 import Simplex
+    from oracle import lpsol_oracle as O
+    c, A, b = problems.dense_lp(150, 2, 1, 3)
+    s = Simplex(_tab(c, A, b))
+    for step in range(6):
+        snap = s._tab._eng.download()
+        want = O.find_pivot_max_increase(snap)
+        assert s.findPivotMaxIncrease() == want
+        assert s.findPivotAll() == O.find_pivot_all(snap)
+        if isinstance(want, str):
+            break
+        s.findPivotMaxIncrease(True) if step % 2 else s.findPivotStandard(True)
+    unb = Simplex(_tab([-1, -2, 0], [[1, -1, 1]], [1]))
+    assert unb.findPivotMaxIncrease() == "unbounded"
+    opt = Simplex(_tab([1, 2, 0], [[1, 1, 1]], [1]))
+    assert opt.findPivotMaxIncrease() == "optimal" and opt.findPivotAll() == [(0, 0), (0, 1), (0, 2)]

@@ -131,3 +131,26 @@ def test_bareiss_form_equals_fraction_form_at_every_pivot():
             for i in range(m + 1):
                 for j in range(2 * m + 1):
                     assert Fraction(N[i][j], D) == grid[i][j]
+
+
+@pytest.mark.parametrize("rec", load_golden("rules"), ids=lambda r: f"{r['family']}m{r['m']}s{r['seed']}")
+def test_whole_tableau_rules_match_reference(rec):
+    """findPivotMaxIncrease / findPivotAll (simplex.py:286-360) against the reference's answers at every state of
+    the walk tools/make_golden_rules.py recorded (alternating max-increase and Dantzig pivots)."""
+    if rec["family"] == "dense":
+        c, A, b = problems.dense_lp(rec["m"], rec["seed"], rec["lo"], rec["hi"])
+    else:
+        c, A, b = problems.equality_lp(rec["m"], rec["n"], rec["seed"])
+    for kind, num in (("exact", Fraction), ("float", float)):
+        if kind not in rec:
+            continue
+        grid = O.make_grid(c, A, b, num=num)
+        grid, basis = O.find_bfs(grid)
+        for step, want in enumerate(rec[kind]):
+            got = O.find_pivot_max_increase(grid)
+            assert (list(got) if isinstance(got, tuple) else got) == want["max_increase"], (kind, step)
+            assert [list(p) for p in O.find_pivot_all(grid)] == want["all"], (kind, step)
+            if isinstance(got, str):
+                break
+            r, cc = got if step % 2 else O.find_pivot(grid, O.RULE_DANTZIG)
+            O.pivot(grid, r, cc)
