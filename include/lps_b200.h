@@ -232,6 +232,16 @@ int lps_upload_exact_weighted(lps_handle *h, const uint32_t *limbs, int nlimbs, 
                               size_t ld_host, const uint32_t *sigma_limbs, int sigma_nlimbs, const int *wcol,
                               int guard_bits);
 int lps_exact_working(lps_handle *h, int *working, int *allocated, int *extensions);
+/* Row operations outside a pivot in exact mode (rowMult / rowDiv tableau.py:254-267, rowAdd / rowSub :269-280,
+ * rowAddToObj / rowSubFromObj :282-293) on the residues:  N_rd <- a N_rd + b N_rs  (rs < 0: N_rd <- a N_rd; rd == m:
+ * the objective row), a and b signed multi-limb integers, sigma the new scale of row rd.  Needs a handle with a
+ * working prime set.  The tableau's numbers stop being minors of the uploaded matrix: guard_bits is the caller's new
+ * allowance on top of the column-weight bound.  Returns LPS_NEED_PRIMES with nothing modified when all the handle's
+ * primes cannot hold it (the caller re-encodes: download, edit, upload); lps_pivot / lps_solve may then report
+ * LPS_NEED_PRIMES as well. */
+int lps_row_combine_exact(lps_handle *h, int rd, int rs, const uint32_t *a_limbs, int a_nlimbs, int a_neg,
+                          const uint32_t *b_limbs, int b_nlimbs, int b_neg, const uint32_t *sigma_limbs,
+                          int sigma_nlimbs, int guard_bits);
 /* lps_phase2_f64 for the exact mode.  cost: n_new + 1 signed integers C_j = sigma_m c_j (limbs as in
  * lps_upload_exact; C_n: the _z cell), sigma_m the new scale of the objective row (a multiple of every
  * row scale and of the cost denominators); mult: m signed integers G_i = C_{basis[i]} / s_i with s_i

@@ -77,6 +77,7 @@ SIGNATURES = {
     "lps_exact_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     "lps_exact_set_weights": (c_int, [c_void_p, c_void_p, c_int]),
     "lps_exact_working": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "lps_row_combine_exact": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int]),
     "lps_phase2_exact": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                  c_void_p, c_int]),
     "lps_exact_loop_state": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_longlong), POINTER(c_int), POINTER(c_int)]),

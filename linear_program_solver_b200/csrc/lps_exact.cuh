@@ -1027,6 +1027,24 @@ __global__ void __launch_bounds__(256) k_xencode_vec(XGrid g, const uint32_t* li
     }
 }
 
+// row operations outside a pivot (tableau.py:254-293): N_rd <- a N_rd + b N_rs (mod p_k), rs < 0: N_rd <- a N_rd
+__global__ void __launch_bounds__(256) k_xrow_combine(XGrid g, int rd, int rs, const uint32_t* a_res, const uint32_t* b_res) {
+    const int k = blockIdx.y;
+    const PrimeQ p = g.pr[k];
+    uint32_t* dst = g.R + (size_t)k * g.plane + (size_t)rd * g.ld;
+    const uint32_t* src = rs >= 0 ? g.R + (size_t)k * g.plane + (size_t)rs * g.ld : nullptr;
+    const uint32_t am = mmul(a_res[k], p.r2, p.q, p.qinv);        // Montgomery forms: mmul(am, x) = a x
+    const uint32_t bm = src ? mmul(b_res[k], p.r2, p.q, p.qinv) : 0u;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= g.n; j += gridDim.x * blockDim.x) {
+        uint32_t v = mmul(am, dst[j], p.q, p.qinv);
+        if (src) {
+            v += mmul(bm, src[j], p.q, p.qinv);
+            if (v >= p.q) v -= p.q;
+        }
+        dst[j] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // leaving phase 1 on the device (Simplex._find_bfs simplex.py:95-105, every row kept)
 // ------------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@ struct ExactData {
     int* wcol = nullptr;                        // device [n+1] column weights (NULL until lps_exact_set_weights)
     int* xbasis = nullptr;                      // device [m] last pivot column per row since the upload
     bool adaptive = false;
+    bool static_ok = true;                      // the numbers are still minors of the uploaded matrix (no row operation since)
     long long wmax256 = 0, guard256 = 0;
     int grows = 0;
     PrimeQ* pr = nullptr;
@@ -281,7 +282,8 @@ static int pick_working(const ExactData* x, long long need, int at_least) {
     return x->Pcap;
 }
 static long long wlimit_of(const ExactData* x, int P) {
-    return P >= x->Pcap ? (1LL << 62) : cap256(x, P) - 2 * x->wmax256 - x->guard256;   // all primes: the static bound holds
+    return (P >= x->Pcap && x->static_ok) ? (1LL << 62)     // all primes: the static bound of the uploaded matrix holds
+                                          : cap256(x, P) - 2 * x->wmax256 - x->guard256;
 }
 
 template <int NB>
@@ -317,6 +319,8 @@ static int grow_working(lps_handle* h) {
         x->grows++;
     }
     s.wlimit = wlimit_of(x, x->P);
+    if (s.wnext > s.wlimit) return LPS_NEED_PRIMES;      // every prime of the handle is in use and the bound (grown by row
+                                                         // operations) still does not fit: the caller re-encodes the tableau
     s.status = LPS_OK;
     TRY(xwrite_state(h));
     return LPS_OK;
@@ -358,7 +362,7 @@ static int upload_common(lps_handle* h, const uint32_t* limbs, int nlimbs, const
     // which primes carry the tableau from the start: all of them, or the working set the weights ask for
     int P0 = x->Pcap;
     x->adaptive = false;
-    x->grows = 0; x->resume = false;                    // a handle may serve several tableaux in a row (the host pools them)
+    x->grows = 0; x->resume = false; x->static_ok = true;   // a handle may serve several tableaux in a row (the host pools them)
     if (wcol) {
         if (guard_bits < 0) return fail(LPS_E_INVALID, "bad guard");
         long long wmax = 0;
@@ -423,6 +427,72 @@ extern "C" int lps_upload_exact_weighted(lps_handle* h, const uint32_t* limbs, i
     NEED_MODE(h, 1);
     if (!wcol) return fail(LPS_E_INVALID, "null weights");
     return upload_common(h, limbs, nlimbs, neg, ld_host, sigma_limbs, sigma_nlimbs, wcol, guard_bits);
+}
+
+// Row operations outside a pivot on the residues (rowMult / rowDiv tableau.py:254-267, rowAdd / rowSub :269-280,
+// rowAddToObj / rowSubFromObj :282-293):   N_rd <- a N_rd + b N_rs   (rs < 0: N_rd <- a N_rd),   rd == m: the
+// objective row.  a, b: signed multi-limb integers; sigma_new: row rd's new scale (the row carries a scale again).
+// The numbers stop being minors of the uploaded matrix: guard_bits is the caller's new allowance on top of the
+// column-weight bound (it grows by log2(|a| + |b|) per operation) and the static bound no longer waives the capacity
+// test.  LPS_NEED_PRIMES, with nothing modified, when even all the handle's primes cannot hold that.
+extern "C" int lps_row_combine_exact(lps_handle* h, int rd, int rs, const uint32_t* a_limbs, int a_nlimbs, int a_neg,
+                                     const uint32_t* b_limbs, int b_nlimbs, int b_neg, const uint32_t* sigma_limbs, int sigma_nlimbs,
+                                     int guard_bits) {
+    USE(h);
+    NEED_MODE(h, 1);
+    ExactData* x = h->x;
+    if (!x->R) return fail(LPS_E_STATE, "upload first");
+    if (!x->adaptive) return fail(LPS_E_STATE, "row operations on the residues need the working prime set (column weights)");
+    if (rd < 0 || rd > h->m || rs >= h->m) return fail(LPS_E_INVALID, "rows (%d,%d) out of range", rd, rs);
+    if (!a_limbs || a_nlimbs <= 0 || (rs >= 0 && (!b_limbs || b_nlimbs <= 0)) || !sigma_limbs || sigma_nlimbs <= 0 || guard_bits < 0)
+        return fail(LPS_E_INVALID, "bad arguments");
+    TRY(xread_state(h));
+    XState& s = *x->st_host;
+    if (s.status == LPS_NEED_PRIMES || s.status == LPS_BAD_PRIME) return fail(LPS_E_STATE, "a pivot is pending");
+    const long long guard_new = 256LL * guard_bits;
+    const long long need = s.wsum + 2 * x->wmax256 + guard_new;
+    if (cap256(x, x->Pcap) < need) return LPS_NEED_PRIMES;
+    x->guard256 = guard_new;
+    x->static_ok = false;
+    if (s.wsum > wlimit_of(x, x->P)) {
+        const int Pnew = pick_working(x, need, x->P + 1);
+        if (Pnew > x->P) {
+            TRY(ensure_planes(h, Pnew, x->P));
+            TRY(launch_extend<4>(h, Pnew, nullptr, (long long)(h->m + 1) * (h->n + 1)));
+            TRY(launch_extend<4>(h, Pnew, x->Dres, 1));
+            TRY(set_working(h, Pnew));
+            x->grows++;
+        }
+    }
+    s.wlimit = wlimit_of(x, x->P);
+    s.wnext = s.wsum;
+    TRY(xwrite_state(h));
+    const XGrid g = xgrid_of(h);
+    DevBuf buf_limbs, b_res;
+    const size_t nl = (size_t)a_nlimbs + (rs >= 0 ? b_nlimbs : 0) + sigma_nlimbs;
+    CU(buf_limbs.alloc(nl * sizeof(uint32_t) + 2));
+    CU(b_res.alloc(2 * (size_t)x->P * sizeof(uint32_t)));
+    uint32_t* d_a = buf_limbs.as<uint32_t>();
+    uint32_t* d_b = d_a + a_nlimbs;
+    uint32_t* d_s = d_b + (rs >= 0 ? b_nlimbs : 0);
+    unsigned char negs[2] = {(unsigned char)(a_neg ? 1 : 0), (unsigned char)(b_neg ? 1 : 0)};
+    unsigned char* d_neg = reinterpret_cast<unsigned char*>(d_s + sigma_nlimbs);
+    CU(cudaMemcpyAsync(d_a, a_limbs, (size_t)a_nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    if (rs >= 0) CU(cudaMemcpyAsync(d_b, b_limbs, (size_t)b_nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_s, sigma_limbs, (size_t)sigma_nlimbs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_neg, negs, 2, cudaMemcpyHostToDevice, h->stream));
+    uint32_t* ra = b_res.as<uint32_t>();
+    uint32_t* rb = ra + x->P;
+    k_xencode_vec<<<dim3(1, x->P), 32, 0, h->stream>>>(g, d_a, a_nlimbs, 1, ra, 1, d_neg);
+    if (rs >= 0) k_xencode_vec<<<dim3(1, x->P), 32, 0, h->stream>>>(g, d_b, b_nlimbs, 1, rb, 1, d_neg + 1);
+    k_xencode_vec<<<dim3(1, x->Pcap), 32, 0, h->stream>>>(g, d_s, sigma_nlimbs, 1, x->sigma + rd, x->sstride);
+    k_xrow_combine<<<dim3(std::max(1, std::min((h->n + 256) / 256, 64)), x->P), 256, 0, h->stream>>>(g, rd, rs, ra, rb);
+    h->launches_all += 4;
+    CU(cudaGetLastError());
+    const int one = 1;
+    CU(cudaMemcpyAsync(x->alive + rd, &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
 }
 
 // Leaving phase 1 without a host round trip of the tableau (Simplex._find_bfs simplex.py:95-105 when no row is
@@ -760,10 +830,12 @@ int lpsx_pivot(lps_handle* h, int r, int c) {
         TRY(xlaunch_apply(h, 0));
         TRY(xread_state(h));
         if (x->st_host->status != LPS_NEED_PRIMES || attempt > 0) break;
-        TRY(grow_working(h));                            // nothing was modified: extend the working set, try again
+        const int grc = grow_working(h);                 // nothing was modified: extend the working set, try again
+        if (grc < 0) return grc;
+        if (grc == LPS_NEED_PRIMES) break;
     }
     const int st = x->st_host->status;
-    return (st == LPS_ZERO_PIVOT || st == LPS_BAD_PRIME) ? st : LPS_OK;
+    return (st == LPS_ZERO_PIVOT || st == LPS_BAD_PRIME || st == LPS_NEED_PRIMES) ? st : LPS_OK;
 }
 
 int lpsx_find_pivot(lps_handle* h, int rule, int* r, int* c) {
@@ -898,7 +970,9 @@ int lpsx_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int*
         TRY(xread_state(h));
         if (x->st_host->status == LPS_NEED_PRIMES) {     // the pending pivot needs a larger working prime set
             enqueued = x->st_host->npiv;                 // the launches behind it were no-ops
-            TRY(grow_working(h));
+            const int grc = grow_working(h);
+            if (grc < 0) return grc;
+            if (grc == LPS_NEED_PRIMES) break;           // reported: the host re-encodes and resumes (like LPS_BAD_PRIME)
             continue;
         }
         if (x->st_host->status != LPS_OK) break;

@@ -129,6 +129,19 @@ def bound_bits_from_squares(row_sq: Sequence[float], col_sq: Sequence[float]) ->
     return int(math.ceil(min(by_rows, by_cols))) + 3
 
 
+def row_combine_coefficients(s_d: int, s_s: Optional[int], mult: Fraction) -> Tuple[int, int, int]:
+    """(a, b, scale) of a row operation in the fraction-free form.  Entries are N / (D s) with s the row's scale:
+    row_d + (p/q) row_s = (q s_s N_d + p s_d N_s) / (D s_d q s_s);  s_s None: (p/q) row_d = p N_d / (D s_d q).
+    Common factors of the three integers are removed."""
+    p, q = mult.numerator, mult.denominator
+    if s_s is None:
+        a, b, scale = p, 0, s_d * q
+    else:
+        a, b, scale = q * s_s, p * s_d, s_d * q * s_s
+    g = math.gcd(a, b, scale)
+    return a // g, b // g, scale // g
+
+
 def primes_for_bits(bits: int, skip: Sequence[int] = ()) -> List[int]:
     """Enough primes that their product exceeds 2^(bits+2): symmetric range plus one guard bit."""
     need = bits + 2
@@ -314,10 +327,13 @@ class ExactEngine:
         limbs = np.ascontiguousarray(limbs)
         neg = np.ascontiguousarray(neg)
         self.sigma = sigma
+        self.op_bits = 0                                 # growth allowed for by row operations since this upload
+        self.wmax_bits = 0
         if self.adaptive and self.forced_primes is None:
             # working prime set: sized by the norms of the current basis columns, extended on the device on demand;
             # only its residue planes are allocated and encoded now
             wcol = np.ascontiguousarray(column_weights(G if G is not None else ints), dtype=np.int32)
+            self.wmax_bits = (int(wcol.max(initial=0)) + 255) // 256
             N.check(self.L.lps_upload_exact_weighted(self.h, limbs.ctypes.data, nl, neg.ctypes.data, self.n + 1,
                                                      sl.ctypes.data, snl, wcol.ctypes.data, sigma_bits + 3))
         else:
@@ -378,8 +394,9 @@ class ExactEngine:
             G.append(q)
         sq = [info["col_sq_a"][j] + C[j] * C[j] for j in range(n_new)] + [info["col_sq_a"][self.n] + C[n_new] * C[n_new]]
         wcol = np.ascontiguousarray(weights_from_squares(sq), dtype=np.int32)
+        self.wmax_bits = (int(wcol.max(initial=0)) + 255) // 256
         sig = self.sigma[:m] + [sigma_m]
-        guard = max(s.bit_length() for s in sig) + 3
+        guard = max(s.bit_length() for s in sig) + 3 + self.op_bits
         cl, cn, cnl = to_limbs(C)
         gl, gn, gnl = to_limbs(G)
         sl, _, snl = to_limbs([sigma_m])
@@ -441,15 +458,17 @@ class ExactEngine:
                 "allocated_primes": a.value, "extensions": g.value}
 
     # -- re-encoding when a prime divides a pivot element -----------------------------------------
-    def _reencode(self):
-        """Download the (still intact) tableau, drop the offending prime, upload again."""
-        bad = self.info()["bad_prime"]
-        if self.forced_primes is not None:
-            if len(self.forced_primes) <= 1:
-                raise N.NativeError("prime set exhausted while re-encoding")
-            self.forced_primes = [p for k, p in enumerate(self.forced_primes) if k != bad]
-        else:
-            self.banned.append(self.primes[bad])
+    def _reencode(self, drop_prime: bool = True):
+        """Download the (still intact) tableau and upload it again: without the offending prime (LPS_BAD_PRIME), or
+        -- after row operations outgrew the handle's primes (LPS_NEED_PRIMES) -- as a new matrix with its own bound."""
+        if drop_prime:
+            bad = self.info()["bad_prime"]
+            if self.forced_primes is not None:
+                if len(self.forced_primes) <= 1:
+                    raise N.NativeError("prime set exhausted while re-encoding")
+                self.forced_primes = [p for k, p in enumerate(self.forced_primes) if k != bad]
+            else:
+                self.banned.append(self.primes[bad])
         grid = self.download()
         self.reencodes += 1
         self.upload(grid)
@@ -458,9 +477,9 @@ class ExactEngine:
     def pivot(self, r: int, c: int) -> int:
         while True:
             rc = N.check(self.L.lps_pivot(self.h, r, c))
-            if rc != N.BAD_PRIME:
+            if rc not in (N.BAD_PRIME, N.NEED_PRIMES):
                 return rc
-            self._reencode()
+            self._reencode(drop_prime=(rc == N.BAD_PRIME))
 
     def find_pivot(self, rule: int):
         r, c = c_int(-1), c_int(-1)
@@ -470,6 +489,36 @@ class ExactEngine:
         if rc == N.UNBOUNDED:
             return "unbounded"
         return r.value, c.value
+
+    # -- row operations outside a pivot (tableau.py:254-293) ------------------------------------------------
+    def row_combine(self, rd: int, rs: Optional[int], mult: Fraction) -> bool:
+        """row rd <- row rd + mult * row rs, or (rs None) row rd <- mult * row rd, on the device residues
+        (`lps_row_combine_exact`); rd == m addresses the objective row.  In the fraction-free form, with s the scale a
+        row carries (1 once pivoted) and mult = p/q:   N_rd <- (q s_rs) N_rd + (p s_rd) N_rs,  scale s_rd q s_rs
+        (common factors removed).  False, with nothing changed, when this handle cannot do it (fixed prime set, or the
+        grown magnitude bound does not fit its primes): the caller edits a host copy instead."""
+        if self.h is None or not self.adaptive or self.forced_primes is not None:
+            return False
+        alive = self._alive()
+        s_d = self.sigma[rd] if alive[rd] else 1
+        s_s = None if rs is None else (self.sigma[rs] if alive[rs] else 1)
+        a, b, new_sigma = row_combine_coefficients(s_d, s_s, mult)
+        # magnitudes grow by at most |a| + |b|; a row addition may also pair entries with the basis of the other row
+        grow = (abs(a) + abs(b) - 1).bit_length() + (self.wmax_bits + 1 if rs is not None else 0)
+        sig = self.sigma[:]
+        sig[rd] = new_sigma
+        guard = max(s.bit_length() for s in sig) + 3 + self.op_bits + grow
+        al, _, anl = to_limbs([a])
+        bl, _, bnl = to_limbs([b])
+        sl, _, snl = to_limbs([new_sigma])
+        rc = N.check(self.L.lps_row_combine_exact(self.h, rd, -1 if rs is None else rs, al.ctypes.data, anl, 1 if a < 0 else 0,
+                                                  bl.ctypes.data, bnl, 1 if b < 0 else 0, sl.ctypes.data, snl, guard))
+        if rc == N.NEED_PRIMES:
+            return False
+        self.sigma = sig
+        self.op_bits += grow
+        self.phase2_info = None                          # the uploaded matrix is no longer what the cost hint was sized for
+        return True
 
     # -- whole-tableau rules (simplex.py:286-360) ---------------------------------------------------------
     def read_cells(self, rows: Sequence[int], cols: Sequence[int]) -> List[Fraction]:
@@ -562,13 +611,13 @@ class ExactEngine:
             if trace is not None:
                 pieces.append(trace[: min(k, trace.shape[0])])
             total += k
-            if rc != N.BAD_PRIME:
+            if rc not in (N.BAD_PRIME, N.NEED_PRIMES):
                 break
-            # a prime divides the next pivot element (probability ~2^-31 per prime and pivot):
-            # re-encode without that prime and continue the loop exactly where it stopped
+            # a prime divides the next pivot element (probability ~2^-31 per prime and pivot), or row operations
+            # outgrew the handle's primes: re-encode and continue the loop exactly where it stopped
             rule, stuck, moved, pend = c_int(0), c_longlong(0), c_int(0), c_int(0)
             N.check(self.L.lps_exact_loop_state(self.h, 0, byref(rule), byref(stuck), byref(moved), byref(pend)))
-            self._reencode()
+            self._reencode(drop_prime=(rc == N.BAD_PRIME))
             N.check(self.L.lps_exact_loop_state(self.h, 1, byref(rule), byref(stuck), byref(moved), byref(pend)))
             if left >= 0:
                 left -= k

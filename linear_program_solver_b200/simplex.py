@@ -155,7 +155,8 @@ class Simplex:
     def pivot(self, r: int, c: int):
         """pivot after checking that (r, c) passes the minimum ratio test (simplex.py:199-216)"""
         tab = self._tab
-        col, b = tab._col(c), tab._col(tab.getNumVars())
+        col = [tab._out(v) for v in tab._col(c)]          # Python numbers: a zero a_rc raises ZeroDivisionError like
+        b = [tab._out(v) for v in tab._col(tab.getNumVars())]   # the reference's `getBi(r)/getAij(r,c)` (simplex.py:213)
         minratio = None
         for i in range(tab.getNumCons()):
             if col[i] <= 0:

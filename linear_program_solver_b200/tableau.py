@@ -59,6 +59,7 @@ class Tableau:
         self._int_grid = None        # exact mode, from_grid(integer ndarray): uploaded as is, Fractions only on demand
         self._cost_hint = None       # exact mode, phase 1: the objective `_leave_phase1` will install (sizes the prime set)
         self.phase2_on_device = 0    # how many times `_leave_phase1` ran as a device call (tests look at it)
+        self.row_ops_on_device = 0   # exact mode: row operations applied to the device residues (tests look at it)
 
     # -- number handling -----------------------------------------------------------------
     def _num(self, x):
@@ -461,10 +462,23 @@ class Tableau:
     # ------------------------------------------------------------------------------------
     # math operations (tableau.py:254-308): on the device
     # ------------------------------------------------------------------------------------
+    def _dev_row_op(self, rd: int, rs, mult) -> bool:
+        """exact mode, tableau resident on the device: the row operation on the residues (`lps_row_combine_exact`).
+        False when the host copy is the valid one, or the handle cannot hold the grown numbers -- the caller then
+        edits the host copy, which re-encodes at the next device operation like a setter."""
+        if self._host_ok or not self._dev_ok or self._eng is None:
+            return False
+        if not self._eng.row_combine(rd, rs, mult):
+            return False
+        self._peek.clear()
+        self._int_grid = None
+        self.row_ops_on_device += 1
+        return True
+
     def _host_row_axpy(self, rd: int, rs: int, mult):
-        """exact mode: row rd += mult * row rs on the host copy.  The exact device encoding is
-        defined by the uploaded integer matrix (its magnitude bound sizes the prime set), so a row
-        edit outside a pivot re-encodes at the next device operation, exactly like a setter."""
+        """exact mode: row rd += mult * row rs.  On the device when the tableau lives there; else on the host copy."""
+        if self._dev_row_op(rd, rs, mult):
+            return
         self._touch_host()
         dst, src = self._grid[rd], self._grid[rs]
         for j in range(self._n + 1):
@@ -477,6 +491,8 @@ class Tableau:
         r = self._chk_i(r)
         if self._mode == "fp64":
             self._touch_dev().row_scale(r, mult)
+            return
+        if self._dev_row_op(r, None, mult):
             return
         self._touch_host()
         row = self._grid[r]

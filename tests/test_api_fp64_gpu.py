@@ -174,9 +174,15 @@ def test_find_pivot_rules_and_checked_pivot():
     O.pivot(grid, r, cc)
     assert s.getBasicSequence()[r] == cc
     assert s._tab.getA() == [row[:-1] for row in grid[:-1]]
-    with pytest.raises(ValueError, match="bad pivot by min ratio test"):
-        r2, c2 = s.findPivotStandard()
-        s.pivot((r2 + 1) % 12, c2)
+    r2, c2 = s.findPivotStandard()
+    col = [row[c2] for row in grid[:-1]]
+    lowest = min(grid[i][-1] / col[i] for i in range(12) if col[i] > 0)
+    bad = next(i for i in range(12) if col[i] > 0 and grid[i][-1] / col[i] > lowest)     # positive entry, not the minimum ratio
+    with pytest.raises(ValueError, match=f"bad pivot by min ratio test, r = {bad}, c = {c2}"):
+        s.pivot(bad, c2)
+    zero = next(i for i in range(12) if col[i] == 0.0)             # the reference divides first (simplex.py:213)
+    with pytest.raises(ZeroDivisionError):
+        s.pivot(zero, c2)
     assert all(isinstance(p, tuple) for p in s.findPivotAll())
     assert s.findPivotMaxIncrease() not in ("optimal", "unbounded")
 

@@ -393,3 +393,126 @@ def test_whole_tableau_rules_larger_against_the_oracle():
     assert unb.findPivotMaxIncrease() == "unbounded"
     opt = Simplex(_tab([1, 2, 0], [[1, 1, 1]], [1]))
     assert opt.findPivotMaxIncrease() == "optimal" and opt.findPivotAll() == [(0, 0), (0, 1), (0, 2)]
+
+
+# ---- row operations outside a pivot on the device residues (lps_row_combine_exact) -----------------------------
+def _view(t):
+    """The valid copy of the tableau: the device's when it is the only valid one, else the host's."""
+    return t._eng.download() if (t._dev_ok and not t._host_ok) else [list(row) for row in t._grid]
+
+
+def test_row_operations_on_the_device_match_the_reference_arithmetic():
+    """rowMult / rowDiv / rowAdd / rowSub / rowAddToObj / rowSubFromObj (tableau.py:254-293) on a tableau that lives on
+    the device (after a pivot), integer and rational multipliers, against the oracle's restatement entry by entry;
+    pivots and a whole solve afterwards still agree (the fraction-free divisions stay exact)."""
+    from linear_program_solver_b200 import Simplex
+    from oracle import lpsol_oracle as O
+    c, A, b = problems.dense_lp(10, 4)
+    t = _tab(c, A, b)
+    grid = O.make_grid(c, A, b)
+    t.pivot(2, 3)
+    O.pivot(grid, 2, 3)
+    ops = [("rowMult", (1, -1)), ("rowAdd", (0, 2, 3)), ("rowSub", (4, 2, Fraction(5, 2))), ("rowDiv", (5, 4)),
+           ("rowAddToObj", (6, Fraction(-7, 3))), ("rowSubFromObj", (2, 2)), ("rowMult", (2, Fraction(3, 7))),
+           ("rowAdd", (3, 3, 2)), ("rowAdd", (7, 5, Fraction(1, 4))), ("rowMult", (8, 1)), ("rowAdd", (8, 9, 0))]
+    for name, args in ops:
+        getattr(t, name)(*args)
+        if name == "rowMult":
+            O.row_scale(grid, args[0], Fraction(args[1]))
+        elif name == "rowDiv":
+            O.row_scale(grid, args[0], 1 / Fraction(args[1]))
+        elif name in ("rowAdd", "rowSub"):
+            O.row_axpy(grid, args[0], args[1], Fraction(args[2]) * (1 if name == "rowAdd" else -1))
+        else:
+            O.row_axpy(grid, 10, args[0], Fraction(args[1]) * (1 if name == "rowAddToObj" else -1))
+        assert _view(t) == grid, (name, args)
+    # the two no-ops (x1, +0) never reach the device; an operation whose allowance no longer fits the handle's primes
+    # (this 10 x 20 tableau has two) moves the tableau to the host, where the rest is applied
+    assert 5 <= t.row_ops_on_device <= 9
+    t.pivot(1, 0)
+    O.pivot(grid, 1, 0)
+    t.pivot(2, 5)                                                  # a row that carries a scale again
+    O.pivot(grid, 2, 5)
+    assert _view(t) == grid
+    t.rowAdd(4, 2, Fraction(-3, 2))                               # on the device again (new upload, new allowance)
+    O.row_axpy(grid, 4, 2, Fraction(-3, 2))
+    assert _view(t) == grid and not t._host_ok
+    with pytest.raises(ZeroDivisionError):
+        t.rowDiv(0, 0)
+    # the objective row was edited: bring it back to canonical form, then solve from this basis
+    basis = [-1] * 10
+    O.is_canonical(grid, basis)
+    got = [-1] * 10
+    t.isCanonical(got)
+    assert got == basis
+
+
+def test_row_operations_then_solve_and_reencode_when_the_primes_run_out():
+    """Row additions grow the magnitude allowance of the handle.  Accepted ones may leave too little room for the
+    pivots that follow: the loop then reports LPS_NEED_PRIMES with every prime in use, the host re-encodes the
+    tableau as a new matrix and the solve continues -- same pivots, basis and objective as the oracle either way.
+    An operation the handle's primes cannot hold at all is refused by the device and applied to a host copy."""
+    from linear_program_solver_b200 import Simplex
+    from oracle import lpsol_oracle as O
+    c, A, b = problems.dense_lp(8, 0)
+    reenc, on_dev = [], []
+    for k in range(1, 8):
+        t = _tab(c, A, b)
+        grid = O.make_grid(c, A, b)
+        s = Simplex(t)
+        basis = list(range(8, 16))
+        r, cc = s.findPivotStandard(True)                         # the tableau now lives on the device
+        O.pivot(grid, r, cc)
+        basis[r] = cc
+        for _ in range(k):                                        # row 5 doubled and halved: same values, larger allowance
+            t.rowAdd(5, 5, 1)
+            t.rowMult(5, Fraction(1, 2))
+            O.row_axpy(grid, 5, 5, Fraction(1))
+            O.row_scale(grid, 5, Fraction(1, 2))
+        on_dev.append(t.row_ops_on_device)
+        s.solve()
+        trace = []
+        O.solve(grid, basis, trace)
+        assert [tuple(p) for p in s.pivot_log[1:]] == [tuple(p) for p in trace], k
+        assert s.getBasicSequence() == basis and s.getObjValue() == O.objective(grid)
+        assert _view(t) == grid
+        reenc.append(t._eng.reencodes)
+    assert on_dev[0] == 2 and reenc[0] == 0, (on_dev, reenc)
+    # fill the handle's allowance to the last bit (each doubling of row 5 costs one bit; driven through the engine so
+    # that the refused one is simply not applied), then solve: the next pivot that adds a column to the basis cannot
+    # fit, every prime is in use, the tableau is re-encoded and the loop resumes
+    t = _tab(c, A, b)
+    grid = O.make_grid(c, A, b)
+    s = Simplex(t)
+    basis = list(range(8, 16))
+    r, cc = s.findPivotStandard(True)
+    O.pivot(grid, r, cc)
+    basis[r] = cc
+    applied = 0
+    for k in range(400):
+        mult = Fraction(2)
+        if not t._eng.row_combine(5, None, mult):
+            break
+        O.row_scale(grid, 5, mult)
+        applied += 1
+    t._peek.clear()
+    assert 4 <= applied < 400 and _view(t) == grid
+    s.solve()
+    trace = []
+    O.solve(grid, basis, trace)
+    assert len(trace) >= 2 and [tuple(p) for p in s.pivot_log[1:]] == [tuple(p) for p in trace]
+    assert s.getBasicSequence() == basis and s.getObjValue() == O.objective(grid) and _view(t) == grid
+    assert t._eng.reencodes >= 1
+    big = Fraction((1 << 400) + 1, (1 << 399) + 7)
+    col = next(j for j in range(16) if grid[0][j] != 0)
+    t.pivot(0, col)                                               # device copy is the valid one again
+    O.pivot(grid, 0, col)
+    before = t.row_ops_on_device
+    t.rowAdd(0, 1, big)                                           # cannot fit the handle's primes: host copy, re-encode
+    O.row_axpy(grid, 0, 1, big)
+    assert t.row_ops_on_device == before and t._host_ok
+    assert t.getA() == [row[:-1] for row in grid[:-1]]
+    col = next(j for j in range(16) if grid[1][j] != 0)
+    t.pivot(1, col)
+    O.pivot(grid, 1, col)
+    assert _view(t) == grid

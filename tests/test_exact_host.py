@@ -173,3 +173,55 @@ def test_phase2_objective_formula_and_bounds(m, n, seed, rational):
         alive[r] = 0
     den = lambda i: D * sig2[i] if alive[i] else D
     assert all(Fraction(Nc[i][j], den(i)) == want[i][j] for i in range(m + 1) for j in range(n + 1))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_row_operations_in_fraction_free_form(seed):
+    """What `lps_row_combine_exact` computes with the integers `row_combine_coefficients` prepares is the reference's
+    rowMult / rowAdd / rowAddToObj (tableau.py:254-293) on N / (D s_i), at any point of a pivot sequence, and the
+    pivots that follow still divide exactly (bareiss_pivot asserts it)."""
+    rng = random.Random(seed)
+    m, n = 6, 10
+    grid = [[Fraction(rng.randint(-9, 9), rng.choice([1, 1, 2, 3])) for _ in range(n + 1)] for _ in range(m + 1)]
+    ints, sigma = X.clear_denominators(grid)
+    N, D, alive = [row[:] for row in ints], 1, [1] * (m + 1)
+    den = lambda i: D * sigma[i] if alive[i] else D
+
+    def check():
+        assert all(Fraction(N[i][j], den(i)) == grid[i][j] for i in range(m + 1) for j in range(n + 1))
+
+    def pivot(r, c):
+        nonlocal D
+        O.pivot(grid, r, c)
+        D = O.bareiss_pivot(N, D, r, c)
+        alive[r] = 0
+
+    def row_op(rd, rs, mult):
+        s_d = sigma[rd] if alive[rd] else 1
+        s_s = None if rs is None else (sigma[rs] if alive[rs] else 1)
+        a, b, scale = X.row_combine_coefficients(s_d, s_s, mult)
+        N[rd] = [a * N[rd][j] + (b * N[rs][j] if rs is not None else 0) for j in range(n + 1)]
+        sigma[rd], alive[rd] = scale, 1
+        if rs is None:
+            O.row_scale(grid, rd, mult)
+        else:
+            O.row_axpy(grid, rd, rs, mult)
+
+    steps = 0
+    for rnd in range(12):
+        kind = rng.choice(["pivot", "pivot", "scale", "add", "add", "obj"])
+        if kind == "pivot":
+            r, c = rng.randrange(m), rng.randrange(n)
+            if grid[r][c] == 0:
+                continue
+            pivot(r, c)
+        elif kind == "scale":
+            row_op(rng.randrange(m), None, Fraction(rng.choice([-1, 2, -3, 5]), rng.choice([1, 2, 7])))
+        elif kind == "add":
+            rd, rs = rng.randrange(m), rng.randrange(m)
+            row_op(rd, rs, Fraction(rng.randint(-4, 4) or 1, rng.choice([1, 1, 3])))
+        else:
+            row_op(m, rng.randrange(m), Fraction(rng.randint(-5, 5) or 2, rng.choice([1, 2])))
+        check()
+        steps += 1
+    assert steps >= 6
