@@ -97,6 +97,9 @@ void *lps_grid_ptr(lps_handle *h);                          /* device pointer of
  * every shard can be generated on its own GPU.  Same values as
  * problems.hashed_dense_grid() and the oracle's orc_fill_dense_f64(). */
 int lps_fill_dense_f64(lps_handle *h, unsigned long long seed, int lo, int hi);
+/* A handle created on a lent grid (dev_grid != NULL) moves to another device grid of the same shape; the handle's
+ * small buffers, stream and state are kept (the host pools handles of large tableaux without pooling the grids). */
+int lps_rebind_grid_f64(lps_handle *h, void *dev_grid);
 
 /* ---- the hot path --------------------------------------------------------- */
 /* Tableau.pivot(r,c) tableau.py:295-308 (with rowDiv :262, rowAddToObj :282,

@@ -47,6 +47,7 @@ SIGNATURES = {
     "lps_read_col_f64": (c_int, [c_void_p, c_int, c_void_p]),
     "lps_grid_ptr": (c_void_p, [c_void_p]),
     "lps_fill_dense_f64": (c_int, [c_void_p, c_ulonglong, c_int, c_int]),
+    "lps_rebind_grid_f64": (c_int, [c_void_p, c_void_p]),
     "lps_pivot": (c_int, [c_void_p, c_int, c_int]),
     "lps_row_scale_f64": (c_int, [c_void_p, c_int, c_double]),
     "lps_row_axpy_f64": (c_int, [c_void_p, c_int, c_int, c_double]),

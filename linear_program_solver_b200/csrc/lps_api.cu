@@ -80,6 +80,9 @@ static void plan(lps_handle* h) {
     // (row blocks of 32 on shards of up to 16k rows: more waves of CTAs, a shorter tail -- +1.4 % at 4096 x 65536)
     if (tiles_wide >= 148 * 8) { h->chunk = kWideChunk; h->rows_per_cta = (h->m + 1 > 16384) ? 64 : 32; }
     else { h->chunk = kNarrowChunk; h->rows_per_cta = ((size_t)(h->m + 1) * h->ld >= (1u << 20)) ? 16 : 8; }
+    // tuning knobs for sweeps (tools/sweep_update.sh); not part of the ABI
+    if (const char* e = getenv("LPS_F64_CHUNK")) { const int v = atoi(e); if (v == kWideChunk || v == kNarrowChunk) h->chunk = v; }
+    if (const char* e = getenv("LPS_F64_ROWS")) { const int v = atoi(e); if (v >= 4 && v <= kMaxRowBlock && v % 4 == 0) h->rows_per_cta = v; }
     h->nchunks = (int)((h->ld + h->chunk - 1) / h->chunk);
     // k_select_f64 spins on an in-kernel flag: never more CTAs than SMs, so all of them are resident.  Small
     // tableaux take ONE CTA of 1024 threads instead: no ticket, no flag, no fences -- the launch is a plain
@@ -151,6 +154,20 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
     CU(cudaMemsetAsync(h->basis, 0xff, (size_t)m * sizeof(int), h->stream));
     CU(cudaMemsetAsync(h->marks, 0, (size_t)n * sizeof(int), h->stream));
     *out = h;
+    return LPS_OK;
+}
+
+// A handle created on a lent grid (dev_grid) moves to another one of the same shape: lets the host keep handles of
+// large tableaux (their small buffers, stream, state) across tableaux without keeping the grids themselves.
+extern "C" int lps_rebind_grid_f64(lps_handle* h, void* dev_grid) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (!dev_grid) return fail(LPS_E_INVALID, "null grid");
+    if (h->own_T) return fail(LPS_E_STATE, "the handle owns its grid");
+    if (h->solving) return fail(LPS_E_STATE, "solve in progress");
+    CU(cudaStreamSynchronize(h->stream));
+    h->T = (double*)dev_grid;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }   // the captured launches carry the old pointer
     return LPS_OK;
 }
 

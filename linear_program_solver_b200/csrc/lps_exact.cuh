@@ -328,6 +328,155 @@ __global__ void __launch_bounds__(kLaneThreads) k_garner(XGrid g, const XState* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same conversion with ONE NUMBER PER WARP (P <= 32 * SPT): lane l holds the residues modulo primes l, l + 32, ...;
+// the digit of a round travels by shuffle instead of through shared memory and a block barrier, so a round costs tens
+// of cycles instead of a barrier round trip.  This is what the solve loop uses while the working prime set is short
+// (k_garner_w); results are identical to block_garner's (digits of |x|, sign, leading digit, 3-digit mantissa).
+// ------------------------------------------------------------------------------------------------
+template <int SPT>
+__device__ __forceinline__ void warp_garner(const XGrid& g, uint32_t (&t)[SPT], int& sign_out, int& top_out, double& mant_out) {
+    const int lane = threadIdx.x & 31, P = g.P;
+    uint32_t q[SPT], qi[SPT], hf[SPT];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        const int k = lane + 32 * s;
+        q[s] = k < P ? g.pr[k].q : 3u;
+        qi[s] = k < P ? g.pr[k].qinv : 0u;
+        hf[s] = k < P ? g.half[k] : 0u;
+    }
+    for (int j = 0; j < P; ++j) {
+        if ((j & 3) == 0) {                                      // early exit, see block_garner
+            bool zero = true, ones = true;
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) {
+                const int k = lane + 32 * s;
+                if (k >= j && k < P) {
+                    zero &= (t[s] == 0u);
+                    ones &= (t[s] == q[s] - 1u);
+                }
+            }
+            if (__all_sync(0xffffffffu, zero) || __all_sync(0xffffffffu, ones)) break;
+        }
+        const int os = j >> 5, ol = j & 31;
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int s = 0; s < SPT; ++s)
+            if (s == os) mine = t[s];
+        const uint32_t v0 = __shfl_sync(0xffffffffu, mine, ol);
+        const uint32_t* invrow = g.invtab + (size_t)j * g.Pld;
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            const int k = lane + 32 * s;
+            if (k > j && k < P) {
+                uint32_t v = v0;
+                if (v >= q[s]) v %= q[s];
+                t[s] = mmul(msub(t[s], v, q[s]), __ldg(invrow + k), q[s], qi[s]);
+            }
+        }
+    }
+    // sign: compare with (M-1)/2 digit by digit from the top; lowest nonzero digit for the negation
+    int hi = -1, lo = INT_MAX;
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        const int k = lane + 32 * s;
+        if (k < P) {
+            if (t[s] != hf[s]) hi = max(hi, k);
+            if (t[s] != 0u) lo = min(lo, k);
+        }
+    }
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    int negv = 0;
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        const int k = lane + 32 * s;
+        if (k < P && k == hi) negv = t[s] > hf[s];
+    }
+    const int neg = __reduce_max_sync(0xffffffffu, negv);
+    int top = -1;
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        const int k = lane + 32 * s;
+        if (k < P) {
+            uint32_t a = t[s];
+            if (lo == INT_MAX) a = 0u;
+            else if (neg) a = k < lo ? 0u : (k == lo ? q[s] - a : q[s] - 1u - a);
+            t[s] = a;
+            if (a) top = max(top, k);
+        }
+    }
+    top = __reduce_max_sync(0xffffffffu, top);
+    // the three leading digits, fetched from their lanes
+    uint32_t d3[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int kd = top - u;
+        uint32_t mine = 0u;
+        if (kd >= 0) {
+#pragma unroll
+            for (int s = 0; s < SPT; ++s)
+                if (s == (kd >> 5)) mine = t[s];
+        }
+        d3[u] = kd >= 0 ? __shfl_sync(0xffffffffu, mine, kd & 31) : 0u;
+    }
+    double x = 0.0;
+    if (top >= 0) {
+        x = (double)d3[0];
+        if (top >= 1) {
+            double y = (double)d3[1];
+            if (top >= 2) y += (double)d3[2] / (double)g.pr[top - 2].q;
+            x += y / (double)g.pr[top - 1].q;
+        }
+    }
+    sign_out = lo == INT_MAX ? 0 : (neg ? -1 : 1);
+    top_out = top;
+    mant_out = x;
+}
+
+constexpr int kGarnerWarps = 8;       // numbers per block of k_garner_w
+
+template <int SPT>
+__global__ void __launch_bounds__(32 * kGarnerWarps) k_garner_w(XGrid g, const XState* st, GarnerJob job) {
+    if (job.check_status && st->status != LPS_OK) return;
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * kGarnerWarps + (threadIdx.x >> 5);
+    if (e >= job.count) return;                                  // whole warps leave
+    const int col = (job.index < 0) ? st->c : job.index;
+    uint32_t t[SPT];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        const int k = lane + 32 * s;
+        uint32_t v = 0u;
+        if (k < g.P) {
+            const uint32_t* plane = g.R + (size_t)k * g.plane;
+            if (job.src == XSRC_ROW) v = plane[(size_t)job.index * g.ld + e];
+            else if (job.src == XSRC_COL) v = plane[(size_t)e * g.ld + col];
+            else if (job.src == XSRC_COLPAIR) v = (e <= g.m) ? plane[(size_t)e * g.ld + col] : plane[(size_t)(e - g.m - 1) * g.ld + g.n];
+            else if (job.src == XSRC_COLPAIRS) {
+                const int per = 2 * (g.m + 1), jj = e / per, rem = e - jj * per;
+                v = (rem <= g.m) ? plane[(size_t)rem * g.ld + job.index + jj] : plane[(size_t)(rem - g.m - 1) * g.ld + g.n];
+            } else v = job.custom[(size_t)k * job.cstride + e];
+        }
+        t[s] = v;
+    }
+    int sg, top;
+    double mant;
+    warp_garner<SPT>(g, t, sg, top, mant);
+    if (lane == 0) {
+        job.meta.sign[e] = (signed char)sg;
+        job.meta.top[e] = top;
+        job.meta.mant[e] = mant;
+    }
+    if (job.dig) {
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            const int k = lane + 32 * s;
+            if (k < g.P) job.dig[(size_t)k * job.dstride + e] = t[s];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Extension of the working prime set from g.P to Pnew primes: every number is reconstructed from its residues
 // modulo the first g.P primes (Garner, with the early exit) and evaluated modulo each new prime by Horner's rule
 // on its mixed-radix digits, x = d_0 + p_0 (d_1 + p_1 (d_2 + ...)).  Source and destination are the residue

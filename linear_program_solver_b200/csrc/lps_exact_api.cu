@@ -587,6 +587,16 @@ extern "C" int lps_phase2_exact(lps_handle* h, int n_new, const uint32_t* cost_l
 template <int NB>
 static int launch_garner(lps_handle* h, const GarnerJob& job) {
     const ExactData* x = h->x;
+    static const bool no_warp = getenv("LPS_GARNER_BLOCK") != nullptr;   // A/B switch for measurements
+    if (x->P <= 128 && !no_warp) {                       // one number per warp, digits by shuffle
+        const int blocks = (job.count + kGarnerWarps - 1) / kGarnerWarps;
+        if (x->P <= 32) k_garner_w<1><<<blocks, 32 * kGarnerWarps, 0, h->stream>>>(xgrid_of(h), x->st, job);
+        else if (x->P <= 64) k_garner_w<2><<<blocks, 32 * kGarnerWarps, 0, h->stream>>>(xgrid_of(h), x->st, job);
+        else k_garner_w<4><<<blocks, 32 * kGarnerWarps, 0, h->stream>>>(xgrid_of(h), x->st, job);
+        h->launches_all++;
+        CU(cudaGetLastError());
+        return LPS_OK;
+    }
     const int blocks = (job.count + NB - 1) / NB;
     if (x->spt == 1) k_garner<NB, 1><<<blocks, x->lane_threads, 0, h->stream>>>(xgrid_of(h), x->st, job);
     else k_garner<NB, kMaxSPT><<<blocks, x->lane_threads, 0, h->stream>>>(xgrid_of(h), x->st, job);

@@ -23,9 +23,10 @@ def _torch():
     return torch
 
 
-# Closed engines of small tableaux (grid, stream, handle) wait here for the next tableau of the same shape: creating and
-# destroying a handle costs milliseconds of driver calls, more than a small solve, and an upload overwrites the whole
-# grid anyway.  Bounded in count and size; sharded, re-shaped (`phase2`) or profiled engines are destroyed instead.
+# Closed engines (grid, stream, handle) wait here for the next tableau of the same shape: creating and destroying a
+# handle costs milliseconds of driver calls (tens with gigabytes of pinned host memory mapped), more than a small solve,
+# and an upload overwrites the whole grid anyway.  Bounded in count; grids above 256 MB are released and the handle is
+# re-bound to a new one (`lps_rebind_grid_f64`); sharded, re-shaped (`phase2`) or profiled engines are destroyed.
 _ENGINE_POOL: dict = {}
 _ENGINE_POOL_MAX = 8
 _ENGINE_POOL_BYTES = 256 << 20
@@ -59,8 +60,14 @@ class F64Engine:
         pooled = _ENGINE_POOL.get(self._pool_key)
         if pooled:
             self.grid, self.stream, self.h = pooled.pop()
-            with torch.cuda.stream(self.stream):
-                self.grid.zero_()                         # a new engine starts from a zero grid
+            if self.grid is None:                         # a large engine was pooled without its grid
+                with torch.cuda.device(self.device):
+                    self.grid = torch.zeros((self.m + 1, self.ld), dtype=torch.float64, device=f"cuda:{self.device}")
+                    self.stream.wait_stream(torch.cuda.current_stream(self.device))
+                N.check(self.L.lps_rebind_grid_f64(self.h, self.grid.data_ptr()))
+            else:
+                with torch.cuda.stream(self.stream):
+                    self.grid.zero_()                     # a new engine starts from a zero grid
             return
         with torch.cuda.device(self.device):
             self.grid = torch.zeros((self.m + 1, self.ld), dtype=torch.float64, device=f"cuda:{self.device}")
@@ -78,8 +85,9 @@ class F64Engine:
         if getattr(self, "h", None):
             key = getattr(self, "_pool_key", None)
             small = (self.m + 1) * self.ld * 8 <= _ENGINE_POOL_BYTES
-            if key is not None and small and sum(len(v) for v in _ENGINE_POOL.values()) < _ENGINE_POOL_MAX:
-                _ENGINE_POOL.setdefault(key, []).append((self.grid, self.stream, self.h))
+            if key is not None and sum(len(v) for v in _ENGINE_POOL.values()) < _ENGINE_POOL_MAX:
+                # large tableaux: the handle (small buffers, stream, state) is kept, the grid goes back to the allocator
+                _ENGINE_POOL.setdefault(key, []).append((self.grid if small else None, self.stream, self.h))
             else:
                 self.L.lps_destroy(self.h)
             self.h = None
