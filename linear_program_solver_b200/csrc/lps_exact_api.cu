@@ -516,6 +516,8 @@ extern "C" int lps_phase2_exact(lps_handle* h, int n_new, const uint32_t* cost_l
     for (int i = 0; i < h->m; ++i)
         if (basis[i] < 0 || basis[i] >= n_new) return fail(LPS_E_INVALID, "basis[%d] = %d is not a column below %d", i, basis[i], n_new);
     if (x->adaptive && (!wcol || guard_bits < 0)) return fail(LPS_E_INVALID, "the working prime set needs the new column weights");
+    static const bool trace = getenv("LPS_TRACE_ALLOC") != nullptr;
+    const double tp0 = now_ms();
     TRY(xread_state(h));
     if (x->st_host->status == LPS_NEED_PRIMES || x->st_host->status == LPS_BAD_PRIME) return fail(LPS_E_STATE, "a pivot is pending");
 
@@ -531,6 +533,8 @@ extern "C" int lps_phase2_exact(lps_handle* h, int n_new, const uint32_t* cost_l
         if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }   // the captured launches carry the old n
     }
 
+    if (trace) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[lps] phase2: cut %.3f ms\n", now_ms() - tp0); }
+    const double tp1 = now_ms();
     // 2. weights of the new matrix; every row's basis column counts from now on
     if (x->adaptive) {
         long long wmax = 0, wsum = 0;
@@ -558,6 +562,8 @@ extern "C" int lps_phase2_exact(lps_handle* h, int n_new, const uint32_t* cost_l
     x->st_host->status = LPS_OK;
     TRY(xwrite_state(h));
 
+    if (trace) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[lps] phase2: weights + extension %.3f ms (P = %d)\n", now_ms() - tp1, x->P); }
+    const double tp2 = now_ms();
     // 3. residues of C and G on the working planes, of sigma_m on every prime; the new objective row
     const XGrid g = xgrid_of(h);
     const size_t cs = ((size_t)n_new + 1 + 3) / 4 * 4, gs = ((size_t)h->m + 3) / 4 * 4;
@@ -581,6 +587,7 @@ extern "C" int lps_phase2_exact(lps_handle* h, int n_new, const uint32_t* cost_l
     h->launches_all += 4;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));                // the scratch buffers go out of scope
+    if (trace) fprintf(stderr, "[lps] phase2: objective row %.3f ms\n", now_ms() - tp2);
     return LPS_OK;
 }
 

@@ -131,6 +131,21 @@ class Tableau:
         self._peek.clear()
         return eng
 
+    _INT_LIMIT = 1 << 62
+
+    def _int_host(self, *values):
+        """The integer host copy (exact mode, `from_grid` with integers) when it is the tableau and every value of an
+        edit is a small integer: the edit is applied to the array in place -- no Fraction is built for any entry -- and
+        the device copy becomes stale.  None: the caller takes the general (Fraction) path."""
+        if self._int_grid is None or self._host_ok:
+            return None
+        for v in values:
+            if v.denominator != 1 or not -self._INT_LIMIT < v.numerator < self._INT_LIMIT:
+                return None
+        self._dev_ok = False
+        self._peek.clear()
+        return self._int_grid
+
     def _row(self, i: int):
         """Row i of the grid (n+1 values) without downloading the whole tableau."""
         if self._host_ok:
@@ -255,11 +270,17 @@ class Tableau:
     # ------------------------------------------------------------------------------------
     def setZ(self, z):
         v = -self._num(z)
+        if self._mode == "exact" and (G := self._int_host(v)) is not None:
+            G[self._m, self._n] = v.numerator
+            return
         self._touch_host()
         self._grid[self._m][self._n] = v
 
     def setC(self, c: List[Any]):
         vals = [self._num(c[j]) for j in range(self._n)]
+        if self._mode == "exact" and (G := self._int_host(*vals)) is not None:
+            G[self._m, :self._n] = [v.numerator for v in vals]
+            return
         self._touch_host()
         for j, v in enumerate(vals):
             self._grid[self._m][j] = v
@@ -267,6 +288,9 @@ class Tableau:
     def setCj(self, j: int, cj):
         v = self._num(cj)
         j = self._chk_j(j)
+        if self._mode == "exact" and (G := self._int_host(v)) is not None:
+            G[self._m, j] = v.numerator
+            return
         self._touch_host()
         self._grid[self._m][j] = v
 
@@ -292,6 +316,9 @@ class Tableau:
     def setAij(self, i: int, j: int, aij):
         v = self._num(aij)
         i, j = self._chk_i(i), self._chk_j(j)
+        if self._mode == "exact" and (G := self._int_host(v)) is not None:
+            G[i, j] = v.numerator
+            return
         self._touch_host()
         self._grid[i][j] = v
 
@@ -322,7 +349,7 @@ class Tableau:
             t._grid = np.ascontiguousarray(grid, dtype=np.float64)
         elif isinstance(grid, np.ndarray) and grid.dtype.kind in "iu":
             # integer input goes to the device as it is; Fractions are only built if a host-side method asks
-            t._int_grid = np.ascontiguousarray(grid, dtype=np.int64)
+            t._int_grid = np.array(grid, dtype=np.int64, order="C")      # own copy: integer edits are applied to it in place
             t._grid = None
             t._host_ok = False
         else:
@@ -359,6 +386,18 @@ class Tableau:
 
     def addVars(self, vs: List[str]):
         k = len(vs)
+        if self._mode == "exact" and (G := self._int_host()) is not None:
+            m, n = self._m, self._n
+            wide = np.zeros((m + 1, n + k + 1), dtype=np.int64)
+            wide[:, :n] = G[:, :n]
+            wide[:, n + k] = G[:, n]
+            self._cl += list(vs)
+            self._cm += [False] * k
+            self._m, self._n = m, n + k
+            self._drop_engine()
+            self._cost_hint = None
+            self._int_grid = wide
+            return
         self._need_host()
         m, n = self._m, self._n
         new = self._blank(m + 1, n + k + 1)
@@ -475,9 +514,19 @@ class Tableau:
         self.row_ops_on_device += 1
         return True
 
+    def _int_row_room(self, G, rd: int, rs, mult: int) -> bool:
+        """Does row rd (+)= mult * row rs stay inside the integer host copy's range?"""
+        top = abs(mult) * int(np.abs(G[rd] if rs is None else G[rs]).max(initial=0)) + (0 if rs is None else int(np.abs(G[rd]).max(initial=0)))
+        return abs(mult) < self._INT_LIMIT and top < self._INT_LIMIT
+
     def _host_row_axpy(self, rd: int, rs: int, mult):
         """exact mode: row rd += mult * row rs.  On the device when the tableau lives there; else on the host copy."""
         if self._dev_row_op(rd, rs, mult):
+            return
+        if self._int_grid is not None and not self._host_ok and mult.denominator == 1 and \
+                self._int_row_room(self._int_grid, rd, rs, mult.numerator):
+            G = self._int_host()
+            G[rd] += mult.numerator * G[rs]
             return
         self._touch_host()
         dst, src = self._grid[rd], self._grid[rs]
@@ -493,6 +542,11 @@ class Tableau:
             self._touch_dev().row_scale(r, mult)
             return
         if self._dev_row_op(r, None, mult):
+            return
+        if self._int_grid is not None and not self._host_ok and mult.denominator == 1 and \
+                self._int_row_room(self._int_grid, r, None, mult.numerator):
+            G = self._int_host()
+            G[r] *= mult.numerator
             return
         self._touch_host()
         row = self._grid[r]

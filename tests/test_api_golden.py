@@ -52,3 +52,38 @@ def test_host_programs(case):
 @pytest.mark.parametrize("case", api_cases.DEVICE, ids=[c[0] for c in api_cases.DEVICE])
 def test_device_programs(case):
     _replay(*case)
+
+
+def test_integer_host_copy_takes_integer_edits_in_place():
+    """`Tableau.from_grid` with integers keeps an int64 array as the host copy; integer setters, `addVars` and integer
+    row operations edit it in place (what phase 1 does to a large integer tableau), a rational edit falls back to
+    Fractions.  Same tableau as the entry-by-entry path either way."""
+    import numpy as np
+    from fractions import Fraction
+    from linear_program_solver_b200 import Tableau
+    rng = np.random.default_rng(3)
+    grid = rng.integers(-9, 10, size=(5, 8))
+    a = Tableau.from_grid(grid, mode="exact")
+    b = Tableau.from_grid([[Fraction(int(x)) for x in row] for row in grid], mode="exact")
+    assert a._int_grid is not None and b._int_grid is None
+
+    def both(f):
+        f(a)
+        f(b)
+
+    both(lambda t: t.rowMult(1, -1))
+    both(lambda t: t.setC([0] * 7))
+    both(lambda t: t.setZ(0))
+    both(lambda t: t.addVars(["$a0", "$a2"]))
+    both(lambda t: (t.setCj(7, 1), t.setAij(0, 7, 1), t.rowSubFromObj(0, 1)))
+    both(lambda t: (t.setCj(8, 1), t.setAij(2, 8, 1), t.rowSubFromObj(2, 1)))
+    both(lambda t: t.rowAdd(3, 1, 4))
+    both(lambda t: t.rowSub(3, 2, 2))
+    assert a._int_grid is not None and a._grid is None or not a._host_ok      # still the integer array
+    assert a.getTableauSize() == (4, 9) and a.getVarNames()[-2:] == ["$a0", "$a2"]
+    assert a.getC() == b.getC() and a.getB() == b.getB() and a.getZ() == b.getZ()
+    assert a._int_grid is not None
+    both(lambda t: t.rowMult(2, Fraction(1, 3)))                   # rational: the Fraction path takes over
+    assert a._int_grid is None
+    both(lambda t: t.rowAdd(0, 2, 10 ** 30))                       # and so does an integer too large for the array
+    assert a == b
