@@ -168,6 +168,22 @@ class BatchResult:
         raise N.NativeError(f"batched solve ended with status {self.status_name(k)}")
 
 
+# Closed batch handles wait here for the next batch of the same shape and prime set (a branch-and-bound driver and the
+# benchmark ask for the same shapes again and again): creating and destroying one costs about 23 ms of driver calls
+# next to a 16 ms kernel.  Every upload / run resets the per-LP state; the two knobs are set again by `solve_batch`.
+_BATCH_POOL: dict = {}
+_BATCH_POOL_MAX = 4
+
+
+def drain_batch_pool():
+    """Destroy every pooled batch handle."""
+    L = N.lib()
+    for lst in _BATCH_POOL.values():
+        for h in lst:
+            L.lps_batch_destroy(h)
+    _BATCH_POOL.clear()
+
+
 class BatchExactSolver:
     """`count` LPs of one shape on one GPU.  `solve(grids)` = `[Simplex(Tableau(grid)).solve() for grid in grids]`."""
 
@@ -180,6 +196,13 @@ class BatchExactSolver:
         self.art_cap, self.trace_cap = int(art_cap), int(trace_cap)
         self.primes = sorted(int(p) for p in primes)       # ascending: digit j of the mixed radix is < every later prime
         self.codec = MixedRadix(self.primes)
+        self._pool_key = (self.device, self.count, self.m, self.n, tuple(self.primes), self.art_cap, int(cluster), self.trace_cap)
+        pooled = _BATCH_POOL.get(self._pool_key)
+        if pooled:
+            self.h = pooled.pop()
+            self.set_stuck_limit(-1)                      # a new solver starts from the defaults
+            self.set_capacity_check(False)
+            return
         arr = np.asarray(self.primes, dtype=np.uint32)
         h = c_void_p()
         N.check(self.L.lps_batch_create(self.count, self.m, self.n, self.art_cap, len(self.primes), arr.ctypes.data,
@@ -188,8 +211,14 @@ class BatchExactSolver:
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.lps_batch_destroy(self.h)
+            key = getattr(self, "_pool_key", None)
+            if key is not None and sum(len(v) for v in _BATCH_POOL.values()) < _BATCH_POOL_MAX:
+                self.L.lps_batch_sync(self.h)             # nothing of this batch may still be running on it
+                _BATCH_POOL.setdefault(key, []).append(self.h)
+            else:
+                self.L.lps_batch_destroy(self.h)
         self.h = None
+        self._keep = None
 
     def __del__(self):
         try:
@@ -226,6 +255,7 @@ class BatchExactSolver:
     def timing(self, read: bool = True):
         """Profiling aid: arm the per-phase cycle counters (read=False) or fetch [count, 16] cycles of the last run."""
         if not read:
+            self._pool_key = None                         # the counters stay armed for the handle's life
             N.check(self.L.lps_batch_timing(self.h, None))
             return None
         out = np.zeros((self.count, 16), dtype=np.int64)

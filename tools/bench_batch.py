@@ -156,7 +156,7 @@ def main():
             "smem_roofline": {"bound": "shared memory", "achieved": smem_bytes / (ms * 1e-3) / 1e9, "peak": smem_peak,
                               "unit": "GB/s", "frac": smem_bytes / (ms * 1e-3) / 1e9 / smem_peak,
                               "bytes_per_pivot": 8 * P * (m + 1) * (n + 1)},
-            "e2e": {"node_lps_per_s": count / e2e_s, "seconds": e2e_s, "h2d_bytes": int(grids.nbytes),
+            "e2e": {"node_lps_per_s": count / e2e_s, "seconds": e2e_s, "seconds_all": e2e_all, "h2d_bytes": int(grids.nbytes),
                     "d2h_bytes": int(count * (4 + 16 + 4 * m + (m + 2) * (1 + 4 * P))),
                     "api": "batch.solve_batch + objectives()"},
             "gen_seconds": gen_s,
