@@ -375,26 +375,23 @@ extern "C" int lps_row_axpy_f64(lps_handle* h, int rd, int rs, double mult) {
 
 // Leaving phase 1 without a host round trip of the tableau (Simplex._find_bfs simplex.py:95-105 when no row is
 // dropped): the artificial columns n_new..n-1 are cut, the objective row becomes `cost` (n_new reduced costs, then
-// the _z cell) priced out against the basis by the m rowSubFromObj steps of the reference, in its order and rounding.
+// the _z cell) and is priced out against the basis by the reference's m rowSubFromObj steps -- one small launch per
+// row, in row order, each reading its multiplier from the objective row the previous steps left (k_obj_step_f64).
 extern "C" int lps_phase2_f64(lps_handle* h, int n_new, const double* cost, const int* basis) {
     USE(h);
     NEED_MODE(h, 0);
     if (h->nranks != 1) return fail(LPS_E_STATE, "lps_phase2_f64 on a sharded handle");
     if (h->solving) return fail(LPS_E_STATE, "solve in progress");
     if (!cost || !basis || n_new <= 0 || n_new > h->n) return fail(LPS_E_INVALID, "bad arguments (n_new = %d, n = %d)", n_new, h->n);
-    std::vector<double> mult(h->m);
-    for (int i = 0; i < h->m; ++i) {
+    for (int i = 0; i < h->m; ++i)
         if (basis[i] < 0 || basis[i] >= n_new) return fail(LPS_E_INVALID, "basis[%d] = %d is not a column below %d", i, basis[i], n_new);
-        mult[i] = -cost[basis[i]];
-    }
     DevBuf b_vec;
-    const size_t nv = (size_t)h->m + 1 + (size_t)n_new + 1 + (size_t)h->m;
-    CU(b_vec.alloc(nv * sizeof(double)));
+    const size_t row_n = ((size_t)n_new + 1 + 15) / 16 * 16;
+    CU(b_vec.alloc(((size_t)h->m + 1 + 2 * row_n) * sizeof(double)));
     double* d_rhs = b_vec.as<double>();
-    double* d_cost = d_rhs + h->m + 1;
-    double* d_mult = d_cost + n_new + 1;
-    CU(cudaMemcpyAsync(d_cost, cost, ((size_t)n_new + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(d_mult, mult.data(), (size_t)h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    double* d_a = d_rhs + h->m + 1;
+    double* d_b = d_a + row_n;
+    CU(cudaMemcpyAsync(d_a, cost, ((size_t)n_new + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (n_new < h->n) {
         k_gather_col_f64<<<std::max(1, std::min((h->m + 256) / 256, 592)), 256, 0, h->stream>>>(grid_of(h), h->n, d_rhs);
         const long long cells = (long long)(h->m + 1) * (h->n - n_new + 1);
@@ -403,10 +400,16 @@ extern "C" int lps_phase2_f64(lps_handle* h, int n_new, const double* cost, cons
         h->n = n_new;                                   // ld, launch plan and buffers keep their (larger) sizes
         if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }   // the captured launches carry the old n
     }
-    k_restore_obj_f64<<<(n_new + 1 + 127) / 128, 128, 0, h->stream>>>(grid_of(h), d_cost, d_mult);
-    h->launches_all++;
+    const F64Grid g = grid_of(h);
+    const int blocks = std::max(1, std::min((n_new + 1 + 255) / 256, 296));
+    for (int i = 0; i < h->m; ++i) {
+        k_obj_step_f64<<<blocks, 256, 0, h->stream>>>(g, d_a, d_b, i, basis[i]);
+        std::swap(d_a, d_b);
+    }
+    h->launches_all += h->m;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(h->stream));               // host vectors and the scratch buffer go out of scope
+    CU(cudaMemcpyAsync(h->T + (size_t)h->m * h->ld, d_a, ((size_t)n_new + 1) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));               // the scratch buffer goes out of scope
     return LPS_OK;
 }
 

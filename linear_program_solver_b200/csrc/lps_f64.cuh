@@ -599,21 +599,16 @@ __global__ void k_cut_cols_f64(F64Grid g, int n_new, const double* rhs) {
         g.T[(size_t)i * g.ld + n_new + jj] = jj == 0 ? rhs[i] : 0.0;
     }
 }
-// setZ / setC followed by rowSubFromObj(i, c_{B_i}) for i = 0..m-1 (simplex.py:101-105 -> tableau.py:282-293): every
-// column adds mult_i * a_ij in row order, product and sum rounded separately like the reference's `c_j += m*a_rj`;
-// rows with a zero multiplier are skipped (tableau.py:285).  mult_i = -cost[B_i]: the basis columns are unit
-// vectors, so the objective row at B_i still holds cost[B_i] when row i's turn comes.
-__global__ void k_restore_obj_f64(F64Grid g, const double* cost, const double* mult) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > g.n) return;
-    double acc = cost[j];
-    const double* col = g.T + j;
-    for (int i = 0; i < g.m; ++i) {
-        const double ml = mult[i];
-        if (ml == 0.0) continue;
-        acc = __dadd_rn(acc, __dmul_rn(ml, col[(size_t)i * g.ld]));
-    }
-    g.T[(size_t)g.m * g.ld + j] = acc;
+// One step of simplex.py:104-105, `tab.rowSubFromObj(i, tab.getCj(j))` (-> tableau.py:282-293): the multiplier is the
+// CURRENT reduced cost of row i's basis column -- in floating point the basis columns are not exact unit vectors
+// (rowDiv multiplies by 1/a_rc, tableau.py:262-267), so earlier steps may have moved it by an ulp -- and every column
+// adds mult * a_ij with product and sum rounded separately; a zero multiplier leaves the row as it is (tableau.py:285).
+// src and dst are two buffers (the multiplier's own cell is rewritten by this step), swapped by the caller.
+__global__ void k_obj_step_f64(F64Grid g, const double* src, double* dst, int row, int bcol) {
+    const double ml = -src[bcol];
+    const double* a = g.T + (size_t)row * g.ld;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= g.n; j += gridDim.x * blockDim.x)
+        dst[j] = (ml == 0.0) ? src[j] : __dadd_rn(src[j], __dmul_rn(ml, a[j]));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -213,6 +213,11 @@ class F64Engine:
             return "unbounded"
         return r.value, c.value
 
+    def has_unbounded_column(self) -> bool:
+        """Tableau.isUnbounded (tableau.py:504-508): a column with c_j < 0 and no positive entry -- exactly when the
+        max-increase pass reports 'unbounded' (simplex.py:319-320)."""
+        return self.find_pivot_max_increase() == "unbounded"
+
     def find_pivot_all(self):
         """Simplex.findPivotAll (simplex.py:330-360) over the device tableau: list of (row, column)."""
         cap = self.n + self.m

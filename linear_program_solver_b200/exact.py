@@ -556,6 +556,11 @@ class ExactEngine:
                 return minrow, [ties[off[j]:off[j + 1]].tolist() for j in range(self.n)]
             cap = int(off[self.n])
 
+    def has_unbounded_column(self) -> bool:
+        """Tableau.isUnbounded (tableau.py:504-508): a column with c_j < 0 and no positive entry."""
+        minrow, _ = self.col_ratios(True)
+        return bool((minrow == -1).any())
+
     def find_pivot_all(self):
         """Simplex.findPivotAll (simplex.py:330-360): every (row, column) of minimum ratio, column by column."""
         _, ties = self.col_ratios(False, want_ties=True)

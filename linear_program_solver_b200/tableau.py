@@ -705,12 +705,11 @@ class Tableau:
     def isOptimal(self) -> bool:
         return self._need_dev().is_optimal()
 
-    # The three predicates below are not used by Simplex; they are
-    # evaluated over host snapshots of the rows/columns involved.
+    # The three predicates below are not used by Simplex.  isUnbounded reuses the device's
+    # per-column ratio pass; the other two are evaluated over host snapshots of the rows / columns involved.
     def isUnbounded(self) -> bool:
-        self._need_host()
-        g, m, n = self._grid, self._m, self._n
-        return any(g[m][j] < 0 and all(g[i][j] <= 0 for i in range(m)) for j in range(n))
+        """some column with c_j < 0 has no positive entry (tableau.py:504-508): the per-column ratio pass on the device"""
+        return self._need_dev().has_unbounded_column()
 
     def isInfeasible(self) -> bool:
         self._need_host()

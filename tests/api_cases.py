@@ -205,12 +205,6 @@ t = mk(['-1/2', 3, 0], [[1, '2/3', 0], [0, -4, 1]], ['5/7', 6], z='9/4', names=[
 """, ["t.printGrid()", "t.printGrid(False, False)", "t.printGrid(True, False, '[', ']')", "t.printText()",
       "t.printText(False)", "t.printText(True, True, 4, True)", "t.printLatex()", "t.printLatex(False, True)",
       "t.printCSV()", "t.printCSV(False, True)", "str(t)", "repr(t)[:9]"]),
-    ("tableau_host_predicates", """
-a = mk([-1, 2], [[-1, 1], [0, 1]], [1, 2])
-b = mk([1, 2], [[-1, -1], [1, 1]], [1, 2])
-c = mk([1, 2], [[1, 1], [1, 1]], [0, 2])
-""", ["a.isUnbounded()", "b.isUnbounded()", "a.isInfeasible()", "b.isInfeasible()", "c.isInfeasible()",
-      "a.isDegenerate()", "c.isDegenerate()"]),
 ]
 
 # -------------------------------------------------------------------------------------------------
@@ -306,4 +300,10 @@ sd.solve()
 """, ["Simplex(inf)", "inf.getTableauSize()", "su.findPivotStandard()", "su.findPivotMinIndex()",
       "su.findPivotMaxIncrease()", "su.solve()", "sd.getBasicSequence()", "sd.getBFS()", "sd.getObjValue()",
       "deg.isDegenerate()"]),
+    ("tableau_host_predicates", """
+a = mk([-1, 2], [[-1, 1], [0, 1]], [1, 2])
+b = mk([1, 2], [[-1, -1], [1, 1]], [1, 2])
+c = mk([1, 2], [[1, 1], [1, 1]], [0, 2])
+""", ["a.isUnbounded()", "b.isUnbounded()", "a.isInfeasible()", "b.isInfeasible()", "c.isInfeasible()",
+      "a.isDegenerate()", "c.isDegenerate()"]),
 ]

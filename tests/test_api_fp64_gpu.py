@@ -109,13 +109,25 @@ def test_leave_phase1_kernels_match_the_row_operations(m, n, k, seed):
     t = Tableau.from_grid(grid.copy(), mode="fp64")
     ref = [[float(x) for x in row] for row in grid]
     basis = list(range(n - m, n))
-    for step in range(min(m, 5)):                          # pivots: the basis columns stay exact unit vectors
+    for step in range(min(m, 5)):                          # a few pivots move the basis into the structural columns
         r, c = (step * 7) % m, step
         if ref[r][c] == 0.0:
             continue
         t.pivot(r, c)
         O.pivot(ref, r, c)
         basis[r] = c
+    # In floating point the basis columns are not exact unit vectors (rowDiv multiplies by 1/a_rc): plant a few
+    # rounding-sized entries in them, above and below the diagonal, so that the multiplier of a row depends on the
+    # steps before it -- the reference reads the CURRENT reduced cost (simplex.py:104-105)
+    with t._eng.on_stream():
+        for q in range(min(m, 40)):
+            i, kb = (q * 5 + 1) % m, (q * 3) % m
+            if i == kb:
+                continue
+            val = float((q % 7 - 3) * 2.0 ** -48)
+            ref[i][basis[kb]] = val
+            t._eng.grid[i, basis[kb]] = val
+    t._eng.sync()
     cost = [float(v) for v in rng.integers(-20, 21, size=n)]
     cost[basis[0]] = 0.0                                   # a zero multiplier: the row is skipped (tableau.py:285)
     z = 12.5

@@ -197,6 +197,30 @@ def test_large_prefix_matches_oracle(eng_mod):
     e.close()
 
 
+def test_c2_full_solve_bit_identical_to_oracle(eng_mod):
+    """Config 2 at full size, to optimality (about 3 600 pivots through the captured-graph loop): pivot count, trace,
+    basis and the WHOLE final tableau byte-identical to the C oracle.  Size-independent properties of the result on
+    top: every reduced cost and right-hand side is >= 0 and the basis columns are unit vectors with zero cost up to
+    rounding (rowDiv multiplies by 1/a_rc, tableau.py:262-267, so they are not exact in floating point)."""
+    from linear_program_solver_b200 import problems
+    from oracle import c_oracle as C
+    m = 2000
+    T = problems.hashed_dense_grid(m, 0).astype(np.float64)
+    e = eng_mod.F64Engine(m, 2 * m)
+    e.upload(T)
+    basis = np.arange(m, 2 * m, dtype=np.int32)
+    st, npiv, trace = e.solve(basis, None, trace_cap=1 << 14)
+    ob = np.arange(m, 2 * m, dtype=np.int32)
+    ost, ok, otrace = C.solve(T, ob)
+    assert (st, npiv) == (1, ok) and npiv > m and trace.tolist() == otrace.tolist() and basis.tolist() == ob.tolist()
+    got = e.download()
+    assert got.tobytes() == T.tobytes()
+    assert (got[m, :2 * m] >= 0).all() and (got[:m, 2 * m] >= 0).all()
+    cols = got[:m, basis]
+    assert np.abs(cols - np.eye(m)).max() < 1e-9 and np.abs(got[m, basis]).max() < 1e-9
+    e.close()
+
+
 def _mem_available() -> int:
     try:
         with open("/proc/meminfo") as f:
