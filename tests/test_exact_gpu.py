@@ -186,6 +186,48 @@ def test_phase1_leaves_on_the_device(m, n, seed, rational):
     assert t._eng.reencodes == 0
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_phase1_with_slack_rows_and_rational_data(seed):
+    """Half the rows come with a slack column (they keep their basis through phase 1 unless pivoted, and their row
+    scale with it), the other half are equalities that need artificials; entries are rationals.  The rows that are
+    never pivoted still carry a scale when the device leaves phase 1 (`lps_phase2_exact`, G_i = C_{B_i} / s_i)."""
+    from linear_program_solver_b200 import Simplex
+    from oracle import lpsol_oracle as O
+    rng = random.Random(100 + seed)
+    ms, me, nx = 5, 5, 9
+    m, n = ms + me, nx + ms
+    x0 = [rng.randint(0, 3) for _ in range(nx)]
+    A, b = [], []
+    for i in range(m):
+        den = rng.choice([1, 2, 3, 4])
+        row = [Fraction(rng.randint(-4, 9), den) for _ in range(nx)] + [Fraction(0)] * ms
+        val = sum(row[j] * x0[j] for j in range(nx))
+        if i < ms:
+            row[nx + i] = Fraction(1)
+            val += rng.randint(0, 5)                       # slack row: feasible with room to spare
+        A.append(row)
+        b.append(val)
+    c = [Fraction(rng.randint(1, 9), rng.choice([1, 2])) for _ in range(nx)] + [Fraction(0)] * ms
+    try:
+        want = O.simplex(c, A, b)
+    except (ValueError, IndexError) as e:
+        with pytest.raises(type(e).__mro__[1] if type(e).__name__ == "InfeasibleError" else type(e)):
+            Simplex(_tab(c, A, b))
+        return
+    t = _tab(c, A, b)
+    s = Simplex(t)
+    assert [tuple(p) for p in s.pivot_log] == [tuple(p) for p in want["phase1_pivots"]]
+    assert s.getBasicSequence() == want["initial_basis"]
+    if want["phase1_pivots"]:
+        assert t.phase2_on_device == 1
+    g0, _ = O.find_bfs(O.make_grid(c, A, b))
+    assert t._eng.download() == g0
+    n1 = len(s.pivot_log)
+    s.solve()
+    assert [tuple(p) for p in s.pivot_log[n1:]] == [tuple(p) for p in want["pivots"]]
+    assert s.getBasicSequence() == want["basis"] and s.getObjValue() == want["objective"] and s.getBFS() == want["bfs"]
+
+
 def test_special_cases():
     from linear_program_solver_b200 import Simplex
     sp = load_golden("special")
