@@ -435,12 +435,10 @@ __device__ __forceinline__ void warp_garner(const XGrid& g, uint32_t (&t)[SPT], 
 
 constexpr int kGarnerWarps = 8;       // numbers per block of k_garner_w
 
+// number e of a job, by the calling warp
 template <int SPT>
-__global__ void __launch_bounds__(32 * kGarnerWarps) k_garner_w(XGrid g, const XState* st, GarnerJob job) {
-    if (job.check_status && st->status != LPS_OK) return;
+__device__ __forceinline__ void garner_number(const XGrid& g, const XState* st, const GarnerJob& job, int e) {
     const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * kGarnerWarps + (threadIdx.x >> 5);
-    if (e >= job.count) return;                                  // whole warps leave
     const int col = (job.index < 0) ? st->c : job.index;
     uint32_t t[SPT];
 #pragma unroll
@@ -474,6 +472,21 @@ __global__ void __launch_bounds__(32 * kGarnerWarps) k_garner_w(XGrid g, const X
             if (k < g.P) job.dig[(size_t)k * job.dstride + e] = t[s];
         }
     }
+}
+
+template <int SPT>
+__global__ void __launch_bounds__(32 * kGarnerWarps) k_garner_w(XGrid g, const XState* st, GarnerJob job) {
+    if (job.check_status && st->status != LPS_OK) return;
+    const int e = blockIdx.x * kGarnerWarps + (threadIdx.x >> 5);
+    if (e >= job.count) return;                                  // whole warps leave
+    garner_number<SPT>(g, st, job, e);
+}
+
+// the same inside a single block that goes on to use the numbers (small tableaux: one launch instead of two)
+template <int SPT>
+__device__ __forceinline__ void garner_job_in_block(const XGrid& g, const XState* st, const GarnerJob& job) {
+    for (int e = threadIdx.x >> 5; e < job.count; e += blockDim.x >> 5) garner_number<SPT>(g, st, job, e);
+    __syncthreads();                                             // the block reads what its warps wrote
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -565,7 +578,7 @@ struct XPriceArgs {
     size_t dstride;
 };
 
-__global__ void __launch_bounds__(kLaneThreads) k_xprice(XPriceArgs a) {
+__device__ __forceinline__ void xprice_body(const XPriceArgs& a) {
     __shared__ int s_best[kLaneThreads];
     XState* st = a.st;
     const XGrid& g = a.g;
@@ -624,6 +637,14 @@ __global__ void __launch_bounds__(kLaneThreads) k_xprice(XPriceArgs a) {
             st->last_r = -1; st->last_c = -1;
         }
     }
+}
+__global__ void __launch_bounds__(kLaneThreads) k_xprice(XPriceArgs a) { xprice_body(a); }
+// small tableaux: the objective row is reconstructed by this block's warps first (one launch instead of two)
+template <int SPTW>
+__global__ void __launch_bounds__(kLaneThreads) k_xprice_fused(XPriceArgs a, GarnerJob job) {
+    if (a.st->status != LPS_OK) return;
+    garner_job_in_block<SPTW>(a.g, a.st, job);
+    xprice_body(a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -686,10 +707,12 @@ struct XRatioArgs {
     int* cand;               // m ints of scratch
     const int* wcol;         // [n+1] column weights, NULL: fixed prime set
     const int* xbasis;       // [m] last pivot column of each row since the upload, -1: never pivoted
+    uint32_t* nbeta;         // fused variant: the stage (k_xstage) runs at the end of this block
+    size_t nbeta_ld;
 };
 
 template <int SPT>
-__global__ void __launch_bounds__(kLaneThreads) k_xratio(XRatioArgs a) {
+__device__ __forceinline__ void xratio_body(const XRatioArgs& a) {
     __shared__ GarnerShared<1> S;
     __shared__ int s_cls[kLaneThreads], s_e[kLaneThreads];
     __shared__ double s_f[kLaneThreads];
@@ -809,6 +832,29 @@ __global__ void __launch_bounds__(kLaneThreads) k_xratio(XRatioArgs a) {
         st->sgn_br = (int)sb[r] * sgnD;
         if (bad >= 0) { st->bad_prime = bad; st->status = LPS_BAD_PRIME; }
     }
+}
+template <int SPT>
+__global__ void __launch_bounds__(kLaneThreads) k_xratio(XRatioArgs a) { xratio_body<SPT>(a); }
+
+// small tableaux: this block reconstructs the (column, rhs) pair itself, runs the ratio test, and -- when a pivot
+// was chosen -- stages the entering column (what k_xstage does): one launch instead of three
+template <int SPTW>
+__global__ void __launch_bounds__(kLaneThreads) k_xratio_fused(XRatioArgs a, GarnerJob job) {
+    XState* st = a.st;
+    const XGrid& g = a.g;
+    if (st->status != LPS_OK) return;
+    garner_job_in_block<SPTW>(g, st, job);
+    xratio_body<1>(a);
+    __syncthreads();
+    if (st->status != LPS_OK || st->dry_run) return;             // block-uniform: written by thread 0 before the barrier
+    const int c = st->c, r = st->r, rows = g.m + 1;
+    for (int idx = threadIdx.x; idx < g.P * rows; idx += blockDim.x) {
+        const int k = idx / rows, i = idx - k * rows;
+        const PrimeQ p = g.pr[k];
+        const uint32_t beta = mmul(mmul(g.R[(size_t)k * g.plane + (size_t)i * g.ld + c], p.r2, p.q, p.qinv), a.pc.dinv_m[k], p.q, p.qinv);
+        a.nbeta[(size_t)k * a.nbeta_ld + i] = beta ? p.q - beta : 0u;
+    }
+    for (int k = threadIdx.x; k < g.P; k += blockDim.x) a.pc.Dres[k] = g.R[(size_t)k * g.plane + (size_t)r * g.ld + c];
 }
 
 // Explicit pivot (Tableau.pivot(r,c)): sign / zero test of N_rc, pivot constants.

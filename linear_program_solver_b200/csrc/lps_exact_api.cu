@@ -46,6 +46,7 @@ struct ExactData {
     int chunk = 2048, rows_per_cta = 64;
     bool stream_hint = false;
     bool resume = false;             // next lps_solve continues the loop state set by lps_exact_loop_state
+    long long graph_launches = 6;    // kernel launches per pivot inside the captured burst graph
 };
 
 static XGrid xgrid_of(const lps_handle* h) {
@@ -783,31 +784,58 @@ extern "C" int lps_exact_loop_state(lps_handle* h, int set, int* rule, long long
 // ------------------------------------------------------------------------------------------------
 // launches of one pivot
 // ------------------------------------------------------------------------------------------------
-static int xlaunch_select(lps_handle* h) {
+// Small tableaux are launch bound (a pivot's six kernels take a few microseconds each): the single-block decision
+// kernels then reconstruct their numbers themselves and the ratio kernel stages the entering column, three launches
+// per pivot instead of six.  *staged tells the caller whether k_xstage is still due.
+static bool fuse_small(const ExactData* x) {
+    static const bool off = getenv("LPS_NO_FUSE") != nullptr;     // A/B switch for measurements
+    return !off && x->P <= 64;
+}
+static int xlaunch_select(lps_handle* h, bool* staged = nullptr) {
     ExactData* x = h->x;
+    const bool small = fuse_small(x);
     GarnerJob job{};
     job.src = XSRC_ROW; job.index = h->m; job.count = h->n + 1; job.check_status = 1;
     job.meta = XMeta{x->obj_sign, x->obj_top, x->obj_mant};
     job.dig = x->obj_dig; job.dstride = x->obj_dstride;
-    TRY(launch_garner<8>(h, job));
     XPriceArgs pa{xgrid_of(h), x->st, job.meta, x->obj_dig, x->obj_dstride};
-    k_xprice<<<1, kLaneThreads, 0, h->stream>>>(pa);
+    if (small && job.count <= 128) {                     // at most four numbers per warp of the block: beyond that
+                                                         // a grid of warps (k_garner_w) wins (profiles/r01f_ab_fuse.txt)
+        if (x->P <= 32) k_xprice_fused<1><<<1, kLaneThreads, 0, h->stream>>>(pa, job);
+        else k_xprice_fused<2><<<1, kLaneThreads, 0, h->stream>>>(pa, job);
+        h->launches_all += 1;
+    } else {
+        TRY(launch_garner<8>(h, job));
+        k_xprice<<<1, kLaneThreads, 0, h->stream>>>(pa);
+        h->launches_all += 1;
+    }
     GarnerJob cj{};
     cj.src = XSRC_COLPAIR; cj.index = -1; cj.count = 2 * (h->m + 1); cj.check_status = 1;
     cj.meta = XMeta{x->cr_sign, x->cr_top, x->cr_mant};
-    TRY(launch_garner<8>(h, cj));
-    XRatioArgs ra{xgrid_of(h), x->st, cj.meta, pconst_of(h), x->cand, x->adaptive ? x->wcol : nullptr, x->xbasis};
-    if (x->spt == 1) k_xratio<1><<<1, kLaneThreads, 0, h->stream>>>(ra);
-    else k_xratio<kMaxSPT><<<1, kLaneThreads, 0, h->stream>>>(ra);
-    h->launches_all += 2;
+    XRatioArgs ra{xgrid_of(h), x->st, cj.meta, pconst_of(h), x->cand, x->adaptive ? x->wcol : nullptr, x->xbasis, x->nbeta, x->nbeta_ld};
+    const bool fuse_col = small && staged && cj.count <= 128 && (long long)x->P * (h->m + 1) <= 8192;
+    if (fuse_col) {
+        if (x->P <= 32) k_xratio_fused<1><<<1, kLaneThreads, 0, h->stream>>>(ra, cj);
+        else k_xratio_fused<2><<<1, kLaneThreads, 0, h->stream>>>(ra, cj);
+        h->launches_all += 1;
+    } else {
+        TRY(launch_garner<8>(h, cj));
+        if (x->spt == 1) k_xratio<1><<<1, kLaneThreads, 0, h->stream>>>(ra);
+        else k_xratio<kMaxSPT><<<1, kLaneThreads, 0, h->stream>>>(ra);
+        h->launches_all += 1;
+    }
+    if (staged) *staged = fuse_col;
     CU(cudaGetLastError());
     return LPS_OK;
 }
 
-static int xlaunch_apply(lps_handle* h, int commit) {
+static int xlaunch_apply(lps_handle* h, int commit, bool staged = false) {
     ExactData* x = h->x;
     const XGrid g = xgrid_of(h);
-    k_xstage<<<dim3(std::max(1, std::min((h->m + 256) / 256, 64)), x->P), 256, 0, h->stream>>>(g, x->st, pconst_of(h), x->nbeta, x->nbeta_ld);
+    if (!staged) {
+        k_xstage<<<dim3(std::max(1, std::min((h->m + 256) / 256, 64)), x->P), 256, 0, h->stream>>>(g, x->st, pconst_of(h), x->nbeta, x->nbeta_ld);
+        h->launches_all++;
+    }
     XUpdateArgs a;
     a.g = g; a.st = x->st; a.alpha_m = x->alpha_m; a.nbeta = x->nbeta; a.nbeta_ld = x->nbeta_ld;
     a.rows_per_cta = x->rows_per_cta; a.basis = h->basis; a.marks = h->use_marks ? h->marks : nullptr;
@@ -824,7 +852,7 @@ static int xlaunch_apply(lps_handle* h, int commit) {
     }
     if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
     h->launches_update++;
-    h->launches_all += 2;
+    h->launches_all += 1;
     CU(cudaGetLastError());
     return LPS_OK;
 }
@@ -926,10 +954,12 @@ static int xensure_burst_graph(lps_handle* h, long long burst) {
     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     int rc = LPS_OK;
     for (long long k = 0; k < burst && rc == LPS_OK; ++k) {
-        rc = xlaunch_select(h);
-        if (rc == LPS_OK) rc = xlaunch_apply(h, 1);
+        bool staged = false;
+        rc = xlaunch_select(h, &staged);
+        if (rc == LPS_OK) rc = xlaunch_apply(h, 1, staged);
     }
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    x->graph_launches = std::max<long long>(1, (h->launches_all - la) / std::max<long long>(1, burst));
     h->launches_all = la; h->launches_update = lu;               // counted when the graph is launched
     if (rc != LPS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return fail(LPS_E_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
@@ -971,15 +1001,16 @@ int lpsx_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int*
             TRY(xensure_burst_graph(h, gburst));
             for (long long k = 0; k < burst; k += gburst) CU(cudaGraphLaunch(h->gexec, h->stream));
             const long long done = (burst + gburst - 1) / gburst * gburst;
-            h->launches_all += 6 * done;
+            h->launches_all += x->graph_launches * done;
             h->launches_update += done;
             enqueued += done;
         } else {
             const long long room = max_pivots >= 0 ? max_pivots - enqueued : burst;
             const long long now = std::min(burst, room);
             for (long long k = 0; k < now; ++k) {
-                TRY(xlaunch_select(h));
-                TRY(xlaunch_apply(h, 1));
+                bool staged = false;
+                TRY(xlaunch_select(h, &staged));
+                TRY(xlaunch_apply(h, 1, staged));
             }
             enqueued += now;
             if (now == 0) TRY(xlaunch_select(h));

@@ -216,7 +216,7 @@ class MixedRadix:
 # were switched to per-launch profiling are destroyed instead.
 _HANDLE_POOL: dict = {}
 _HANDLE_POOL_MAX = 8
-_HANDLE_POOL_BYTES = 4 << 30
+_HANDLE_POOL_BYTES = 1 << 30
 
 
 def _pool_size() -> int:
