@@ -375,6 +375,7 @@ class Tableau:
     # ------------------------------------------------------------------------------------
     def _reshape_host(self, new_grid, m: int, n: int):
         self._cost_hint = None
+        self._int_grid = None
         self._grid = new_grid
         self._m, self._n = m, n
         self._drop_engine()
