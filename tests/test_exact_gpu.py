@@ -344,32 +344,18 @@ def test_working_prime_set_covers_every_integer_of_a_solve():
         assert 256 * math.log2(big) <= cap
 
 
-# ---- full-size property check (BASELINE.json config 3): an exact optimality certificate -------------------------
-def test_c3_full_solve_carries_an_exact_optimality_certificate():
-    """C3 (exact 1000 x 2000, 8-bit coefficients) solved to optimality through the public API.  The reference needs
-    hours for this size, so instead of a recorded answer the result is proved on the CPU with Python integers,
-    independently of the device arithmetic: the reported basic solution satisfies A x = b, x >= 0 exactly; the
-    multipliers y read off the slack columns of the device's objective row reproduce EVERY reduced cost
-    d_j = c_j - y^T A_j exactly, all d_j >= 0, d_j = 0 on the basis; and c^T x = y^T b = the reported objective
-    (strong duality).  Together: the device's final tableau row, basis and rational objective are the exact optimum.
-    The pivot sequence's first six pivots are pinned by the reference fixture (dense_exact.json)."""
-    from linear_program_solver_b200 import Simplex, Tableau
-    m = 1000
-    c, A, b = problems.dense_lp(m, 0, 1, 127)
-    n = 2 * m
-    grid = np.array([A[i] + [b[i]] for i in range(m)] + [c + [0]], dtype=np.int64)
-    t = Tableau.from_grid(grid, mode="exact")
-    s = Simplex(t)
-    npiv = s.solve()
-    rec = next(r for r in load_golden("dense_exact") if r["m"] == m and r["hi"] == 127)
-    assert [list(p) for p in s.pivot_log[:len(rec["pivots"])]] == rec["pivots"]
-    assert npiv == len(s.pivot_log) > m // 2 and t.isOptimal()
+# ---- full-size property checks: an exact optimality certificate -------------------------------------------------
+def _certify_optimum(c, A, b, t, s):
+    """Prove on the CPU, with Python integers and independently of the device arithmetic, that the solved exact
+    tableau `t` / `s` is THE optimum of min c^T x, A x = b, x >= 0: the reported basic solution satisfies A x = b,
+    x >= 0 exactly; the multipliers y read off the slack columns of the device's objective row reproduce EVERY reduced
+    cost d_j = c_j - y^T A_j exactly, all d_j >= 0, d_j = 0 on the basis; and c^T x = y^T b = the reported objective
+    (strong duality).  A is [structural | identity]."""
+    m, n = len(A), len(c)
     basis = s.getBasicSequence()
-    assert len(set(basis)) == m
+    assert len(set(basis)) == m and t.isOptimal()
     bfs, z = s.getBFS(), s.getObjValue()
     d = t.getC()                                           # reduced costs, n Fractions (one Garner pass on the device)
-    assert z.denominator.bit_length() > 300                # a genuinely big rational, not a float-sized answer
-    # primal: A x = b, x >= 0, with one common denominator so that the products are integer
     den = 1
     for v in bfs.values():
         den = den * v.denominator // math.gcd(den, v.denominator)
@@ -378,19 +364,66 @@ def test_c3_full_solve_carries_an_exact_optimality_certificate():
         assert v >= 0
         X[j] = int(v * den)
     Aobj = np.array(A, dtype=object)
-    assert ((Aobj @ X) == np.array(b, dtype=object) * den).all()
-    assert Fraction(int(np.dot(np.array(c, dtype=object), X)), den) == z
-    # dual: y_i = -d_(m+i) (slack columns are unit vectors with zero cost)
+    cobj, bobj = np.array(c, dtype=object), np.array(b, dtype=object)
+    assert ((Aobj @ X) == bobj * den).all()
+    assert Fraction(int(np.dot(cobj, X)), den) == z
     dd = 1
     for v in d:
         dd = dd * v.denominator // math.gcd(dd, v.denominator)
     Dint = np.array([int(v * dd) for v in d], dtype=object)
     assert all(v >= 0 for v in Dint) and all(Dint[j] == 0 for j in basis)
-    Y = -Dint[m:]
-    assert ((np.array(c, dtype=object) * dd - (Y @ Aobj)) == Dint).all()
-    assert Fraction(int(np.dot(Y, np.array(b, dtype=object))), dd) == z
+    Y = -Dint[m:]                                          # slack columns are unit vectors with zero cost
+    assert ((cobj * dd - (Y @ Aobj)) == Dint).all()
+    assert Fraction(int(np.dot(Y, bobj)), dd) == z
+    return z, bfs
+
+
+def test_c3_full_solve_carries_an_exact_optimality_certificate():
+    """C3 (exact 1000 x 2000, 8-bit coefficients) solved to optimality through the public API.  The reference needs
+    hours for this size, so instead of a recorded answer the result is proved optimal on the CPU (`_certify_optimum`).
+    The pivot sequence's first six pivots are pinned by the reference fixture (dense_exact.json)."""
+    from linear_program_solver_b200 import Simplex, Tableau
+    m = 1000
+    c, A, b = problems.dense_lp(m, 0, 1, 127)
+    grid = np.array([A[i] + [b[i]] for i in range(m)] + [c + [0]], dtype=np.int64)
+    t = Tableau.from_grid(grid, mode="exact")
+    s = Simplex(t)
+    npiv = s.solve()
+    rec = next(r for r in load_golden("dense_exact") if r["m"] == m and r["hi"] == 127)
+    assert [list(p) for p in s.pivot_log[:len(rec["pivots"])]] == rec["pivots"]
+    assert npiv == len(s.pivot_log) > m // 2
+    z, _ = _certify_optimum(c, A, b, t, s)
+    assert z.denominator.bit_length() > 300                # a genuinely big rational, not a float-sized answer
     info = t._eng.info()
     assert info["primes"] < info["allocated_primes"]       # solved on the working prime set
+
+
+def test_c2_fp64_is_within_1e9_of_the_certified_exact_optimum():
+    """BASELINE.json config 2 at full size (2000 x 4000): the north star asks fp64 mode to be within 1e-9 relative of
+    the exact objective and primal values.  The reference's Fraction simplex needs hours here; the exact mode solves
+    the same LP in seconds, its answer is proved optimal on the CPU (`_certify_optimum`), and the fp64 result is
+    compared with it."""
+    from linear_program_solver_b200 import Simplex, Tableau
+    m = 2000
+    G = problems.hashed_dense_grid(m, 0)
+    A = [[int(v) for v in row[:2 * m]] for row in G[:m]]
+    b = [int(row[2 * m]) for row in G[:m]]
+    c = [int(v) for v in G[m, :2 * m]]
+    t = Tableau.from_grid(G.astype(np.int64), mode="exact")
+    s = Simplex(t)
+    s.solve()
+    z, bfs = _certify_optimum(c, A, b, t, s)
+    tf = Tableau.from_grid(G.astype(np.float64), mode="fp64")
+    sf = Simplex(tf)
+    sf.solve()
+    zf = Fraction(sf.getObjValue())
+    assert abs(zf - z) <= Fraction(1, 10 ** 9) * abs(z)
+    # primal values: compared when the float path ends on the same vertex (with ties it may stop on another vertex of
+    # the optimal face; this instance does not)
+    assert set(sf.getBasicSequence()) == set(s.getBasicSequence())
+    xf = sf.getBFS()
+    worst = max(abs(Fraction(xf.get(j, 0.0)) - v) / max(abs(v), 1) for j, v in bfs.items())
+    assert worst <= Fraction(1, 10 ** 9)
 
 
 # ---- whole-tableau rules in exact mode (lps_exact_col_ratios) ---------------------------------------------------
