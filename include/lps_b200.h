@@ -137,6 +137,9 @@ int lps_find_pivot_all(lps_handle *h, int *rows, int *cols, long long cap, long 
 int lps_is_canonical(lps_handle *h, int *bcols, int *canonical);
 /* Tableau.isOptimal tableau.py:500-502 */
 int lps_is_optimal(lps_handle *h, int *optimal);
+/* Tableau.isInfeasible tableau.py:510-514: some row with b_i > 0 has no positive entry (either mode; exact: the
+ * rows are reconstructed on the device in batches and only their signs are looked at). */
+int lps_is_infeasible(lps_handle *h, int *infeasible);
 
 /* Simplex.solve() simplex.py:110-148, the whole loop on the device: Dantzig
  * pricing while the stuck counter is below m+n (the counter compares with the

@@ -57,6 +57,7 @@ SIGNATURES = {
     "lps_find_pivot_all": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, POINTER(c_longlong)]),
     "lps_is_canonical": (c_int, [c_void_p, c_void_p, POINTER(c_int)]),
     "lps_is_optimal": (c_int, [c_void_p, POINTER(c_int)]),
+    "lps_is_infeasible": (c_int, [c_void_p, POINTER(c_int)]),
     "lps_solve": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, POINTER(c_longlong)]),
     "lps_solve_begin": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong]),
     "lps_step_select": (c_int, [c_void_p]),

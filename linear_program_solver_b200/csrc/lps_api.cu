@@ -442,6 +442,23 @@ extern "C" int lps_is_optimal(lps_handle* h, int* optimal) {
     return LPS_OK;
 }
 
+// Tableau.isInfeasible (tableau.py:510-514): some row with b_i > 0 and no positive entry.
+extern "C" int lps_is_infeasible(lps_handle* h, int* infeasible) {
+    USE(h);
+    if (!infeasible) return fail(LPS_E_INVALID, "null result");
+    if (h->mode == 1) return lpsx_is_infeasible(h, infeasible);
+    if (h->nranks != 1) return fail(LPS_E_STATE, "is_infeasible on a sharded handle");
+    DevBuf b_flag;
+    CU(b_flag.alloc(sizeof(int)));
+    CU(cudaMemsetAsync(b_flag.p, 0, sizeof(int), h->stream));
+    k_row_infeasible_f64<<<std::max(1, std::min((h->m + 7) / 8, 148 * 8)), 256, 0, h->stream>>>(grid_of(h), b_flag.as<int>());
+    h->launches_all++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(infeasible, b_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+
 // Simplex.findPivotMaxIncrease (simplex.py:286-328) on the device, fp64 mode.
 extern "C" int lps_find_pivot_max_increase(lps_handle* h, int* r, int* c) {
     USE(h);

@@ -266,7 +266,8 @@ __device__ __forceinline__ double garner_mant(const XGrid& g, const GarnerShared
 }
 
 // ---- batch reconstruction of a row, a column, the (column c, rhs) pair, or custom residues -----------
-enum { XSRC_ROW = 0, XSRC_COL = 1, XSRC_COLPAIR = 2, XSRC_CUSTOM = 3, XSRC_COLPAIRS = 4 };   // 4: (column, rhs) pairs of columns index, index+1, ...
+enum { XSRC_ROW = 0, XSRC_COL = 1, XSRC_COLPAIR = 2, XSRC_CUSTOM = 3, XSRC_COLPAIRS = 4, XSRC_ROWS = 5 };
+// 4: (column, rhs) pairs of columns index, index+1, ...;  5: rows index, index+1, ... (n+1 numbers each)
 struct GarnerJob {
     int src;                 // XSRC_*
     int index;               // row / column; column -1 means "the entering column st->c"
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(kLaneThreads) k_garner(XGrid g, const XState* 
                     const int per = 2 * (g.m + 1), jj = e / per, rem = e - jj * per;
                     v = (rem <= g.m) ? plane[(size_t)rem * g.ld + job.index + jj] : plane[(size_t)(rem - g.m - 1) * g.ld + g.n];
                 }
+                else if (job.src == XSRC_ROWS) { const int per = g.n + 1, ii = e / per; v = plane[(size_t)(job.index + ii) * g.ld + (e - ii * per)]; }
                 else v = job.custom[(size_t)k * job.cstride + e];
             }
             t[s][b] = v;
@@ -453,6 +455,9 @@ __device__ __forceinline__ void garner_number(const XGrid& g, const XState* st, 
             else if (job.src == XSRC_COLPAIRS) {
                 const int per = 2 * (g.m + 1), jj = e / per, rem = e - jj * per;
                 v = (rem <= g.m) ? plane[(size_t)rem * g.ld + job.index + jj] : plane[(size_t)(rem - g.m - 1) * g.ld + g.n];
+            } else if (job.src == XSRC_ROWS) {
+                const int per = g.n + 1, ii = e / per;
+                v = plane[(size_t)(job.index + ii) * g.ld + (e - ii * per)];
             } else v = job.custom[(size_t)k * job.cstride + e];
         }
         t[s] = v;
@@ -1031,6 +1036,19 @@ __global__ void __launch_bounds__(kLaneThreads) k_xratio_cols(XColsArgs a) {
         }
     }
     if (tid == 0) { a.minrow[jj] = r; if (a.nties) a.nties[jj] = s_nt; }
+}
+
+// Tableau.isInfeasible (tableau.py:510-514) on the signs of a batch of reconstructed rows (XSRC_ROWS): some row with
+// b_i > 0 has no positive entry.  One warp per row.
+__global__ void k_xrow_infeasible(const signed char* sign, int nrows, int n, const XState* st, int* flag) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, sgnD = st->sgnD;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nrows; i += gridDim.x * wpb) {
+        const signed char* row = sign + (size_t)i * (n + 1);
+        if ((int)row[n] * sgnD <= 0) continue;
+        bool pos = false;
+        for (int j = lane; j < n && !pos; j += 32) pos = (int)row[j] * sgnD > 0;
+        if (!__any_sync(0xffffffffu, pos) && lane == 0) atomicOr(flag, 1);
+    }
 }
 
 // residues of scattered cells (rows[e], cols[e]) as a XSRC_CUSTOM source: out[k*ostride + e]

@@ -939,6 +939,34 @@ int lpsx_is_canonical(lps_handle* h, int* bcols, int* canonical) {
     return LPS_OK;
 }
 
+// Tableau.isInfeasible (tableau.py:510-514): batches of rows reconstructed on the device, one warp per row on the signs.
+int lpsx_is_infeasible(lps_handle* h, int* infeasible) {
+    ExactData* x = h->x;
+    if (!x->R) return fail(LPS_E_STATE, "upload first");
+    const int m = h->m, n = h->n;
+    const long long per = (long long)n + 1;
+    const int batch = (int)std::max<long long>(1, std::min<long long>(m, (1LL << 22) / per));
+    DevBuf b_sign, b_top, b_mant, b_flag;
+    CU(b_sign.alloc((size_t)batch * per));
+    CU(b_top.alloc((size_t)batch * per * sizeof(int)));
+    CU(b_mant.alloc((size_t)batch * per * sizeof(double)));
+    CU(b_flag.alloc(sizeof(int)));
+    CU(cudaMemsetAsync(b_flag.p, 0, sizeof(int), h->stream));
+    for (int i0 = 0; i0 < m; i0 += batch) {
+        const int nr = std::min(batch, m - i0);
+        GarnerJob job{};
+        job.src = XSRC_ROWS; job.index = i0; job.count = (int)(nr * per); job.check_status = 0;
+        job.meta = XMeta{b_sign.as<signed char>(), b_top.as<int>(), b_mant.as<double>()};
+        TRY(launch_garner<8>(h, job));
+        k_xrow_infeasible<<<std::max(1, std::min((nr + 7) / 8, 148 * 8)), 256, 0, h->stream>>>(b_sign.as<signed char>(), nr, n, x->st, b_flag.as<int>());
+        h->launches_all++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(infeasible, b_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LPS_OK;
+}
+
 static int xensure_burst_graph(lps_handle* h, long long burst) {
     ExactData* x = h->x;
     unsigned long long sig = 1469598103934665603ull;

@@ -585,6 +585,18 @@ __global__ void k_gather_col_f64(F64Grid g, int j, double* out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= g.m; i += gridDim.x * blockDim.x) out[i] = g.T[(size_t)i * g.ld + j];
 }
 
+// Tableau.isInfeasible (tableau.py:510-514): some row with b_i > 0 has no positive entry.  One warp per row.
+__global__ void k_row_infeasible_f64(F64Grid g, int* flag) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < g.m; i += gridDim.x * wpb) {
+        const double* row = g.T + (size_t)i * g.ld;
+        if (!(row[g.n] > 0.0)) continue;
+        bool pos = false;
+        for (int j = lane; j < g.n && !pos; j += 32) pos = row[j] > 0.0;
+        if (!__any_sync(0xffffffffu, pos) && lane == 0) atomicOr(flag, 1);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // leaving phase 1 on the device (Simplex._find_bfs simplex.py:95-105, every row kept)
 // ------------------------------------------------------------------------------------------------

@@ -131,4 +131,5 @@ int lpsx_destroy(lps_handle* h);
 int lpsx_pivot(lps_handle* h, int r, int c);
 int lpsx_find_pivot(lps_handle* h, int rule, int* r, int* c);
 int lpsx_is_canonical(lps_handle* h, int* bcols, int* canonical);
+int lpsx_is_infeasible(lps_handle* h, int* infeasible);
 int lpsx_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int* trace, long long trace_cap, long long* npiv);

@@ -244,6 +244,12 @@ class F64Engine:
         N.check(self.L.lps_is_optimal(self.h, byref(flag)))
         return bool(flag.value)
 
+    def is_infeasible(self) -> bool:
+        """Tableau.isInfeasible (tableau.py:510-514) on the device."""
+        flag = c_int(0)
+        N.check(self.L.lps_is_infeasible(self.h, byref(flag)))
+        return bool(flag.value)
+
     def solve(self, basis: np.ndarray, marks: Optional[np.ndarray] = None, max_pivots: int = -1,
               trace_cap: int = 0) -> Tuple[int, int, Optional[np.ndarray]]:
         """Run `Simplex.solve` on the device.  basis / marks are int32 arrays updated in place."""

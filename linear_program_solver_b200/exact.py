@@ -601,6 +601,12 @@ class ExactEngine:
         N.check(self.L.lps_is_optimal(self.h, byref(flag)))
         return bool(flag.value)
 
+    def is_infeasible(self) -> bool:
+        """Tableau.isInfeasible (tableau.py:510-514) on the device."""
+        flag = c_int(0)
+        N.check(self.L.lps_is_infeasible(self.h, byref(flag)))
+        return bool(flag.value)
+
     def solve(self, basis: np.ndarray, marks: Optional[np.ndarray] = None, max_pivots: int = -1, trace_cap: int = 0):
         """`Simplex.solve` on the device; basis / marks are int32 arrays updated in place."""
         assert basis.dtype == np.int32 and basis.size == self.m

@@ -707,15 +707,14 @@ class Tableau:
         return self._need_dev().is_optimal()
 
     # The three predicates below are not used by Simplex.  isUnbounded reuses the device's
-    # per-column ratio pass; the other two are evaluated over host snapshots of the rows / columns involved.
+    # per-column ratio pass, isInfeasible is a row pass on the device, isDegenerate reads the right-hand side column.
     def isUnbounded(self) -> bool:
         """some column with c_j < 0 has no positive entry (tableau.py:504-508): the per-column ratio pass on the device"""
         return self._need_dev().has_unbounded_column()
 
     def isInfeasible(self) -> bool:
-        self._need_host()
-        g, m, n = self._grid, self._m, self._n
-        return any(g[i][n] > 0 and all(g[i][j] <= 0 for j in range(n)) for i in range(m))
+        """some row with b_i > 0 has no positive entry (tableau.py:510-514): one pass over the device tableau"""
+        return self._need_dev().is_infeasible()
 
     def isDegenerate(self) -> bool:
         col = self._col(self._n)

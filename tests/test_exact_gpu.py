@@ -591,3 +591,39 @@ def test_row_operations_then_solve_and_reencode_when_the_primes_run_out():
     t.pivot(1, col)
     O.pivot(grid, 1, col)
     assert _view(t) == grid
+
+
+# ---- form predicates on the device (tableau.py:504-521) ---------------------------------------------------------
+@pytest.mark.parametrize("mode", ["exact", "fp64"])
+def test_form_predicates_match_the_reference_definitions(mode):
+    """isUnbounded / isInfeasible / isDegenerate on random sparse-signed tableaux, before and after pivots, against the
+    reference's definitions evaluated on a snapshot (tableau.py:504-521); the api golden cases pin the same calls to
+    the unmodified reference's answers."""
+    rng = random.Random(11)
+    seen = set()
+    for trial in range(24):
+        m, n = rng.randint(2, 7), rng.randint(3, 9)
+        A = [[rng.choice([-3, -1, 0, 0, 0, 1, 2]) if rng.random() < 0.7 else -rng.randint(0, 2) for _ in range(n)] for _ in range(m)]
+        if trial % 3 == 0:
+            A[rng.randrange(m)] = [-abs(v) for v in A[0]]           # a row without positive entries
+        if trial % 4 == 0:
+            jj = rng.randrange(n)
+            for row in A:
+                row[jj] = -abs(row[jj])                            # a column without positive entries
+        b = [rng.randint(-1, 3) for _ in range(m)]
+        c = [rng.randint(-3, 2) for _ in range(n)]
+        t = _tab(c, A, b, mode=mode)
+        for step in range(3):
+            t._need_dev()
+            snap = t._eng.download()
+            g = [[float(x) for x in row] for row in snap] if mode == "fp64" else snap
+            want_unb = any(g[m][j] < 0 and all(g[i][j] <= 0 for i in range(m)) for j in range(n))
+            want_inf = any(g[i][n] > 0 and all(g[i][j] <= 0 for j in range(n)) for i in range(m))
+            want_deg = any(g[i][n] == 0 for i in range(m))
+            assert (t.isUnbounded(), t.isInfeasible(), t.isDegenerate()) == (want_unb, want_inf, want_deg), (trial, step)
+            seen.add((want_unb, want_inf))
+            piv = [(i, j) for i in range(m) for j in range(n) if g[i][j] != 0]
+            if not piv:
+                break
+            t.pivot(*piv[rng.randrange(len(piv))])
+    assert len(seen) == 4                                          # every combination came up

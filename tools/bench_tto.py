@@ -112,10 +112,15 @@ def main():
                           "objective_denominator_bits": z.denominator.bit_length(), "objective_float": float(z),
                           "cpu_oracle_seconds": None}), flush=True)
 
-    # ---- C2: fp64 2000 x 4000 ----------------------------------------------------------------------------
+    # ---- C2: fp64 2000 x 4000, and the same LP in exact mode -------------------------------------------------
     m = 2000
     T = problems.hashed_dense_grid(m, 0).astype(np.float64)
+    dtx, zx, basisx, kx = gpu_solve(problems.hashed_dense_grid(m, 0).astype(np.int64), "exact")
     dt, z, basis, k = gpu_solve(T.copy(), "fp64")
+    zx = Fraction(zx)
+    print(json.dumps({"case": "C2's LP in exact mode, 2000x4000, seed 0", "gpu_seconds": dtx, "pivots": kx,
+                      "objective_numerator_bits": zx.numerator.bit_length(), "objective_denominator_bits": zx.denominator.bit_length(),
+                      "fp64_relative_error_of_objective": float(abs(Fraction(z) - zx) / abs(zx)), "cpu_oracle_seconds": None}), flush=True)
     Tc = T.copy()
     ob = np.arange(m, 2 * m, dtype=np.int32)
     t0 = time.perf_counter()
