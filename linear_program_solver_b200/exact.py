@@ -384,6 +384,8 @@ class ExactEngine:
         info = getattr(self, "phase2_info", None)
         if info is None or self.h is None or info["n0"] != n_new or info["n_up"] != self.n or len(basis) != self.m:
             return False
+        if self.forced_primes is not None:               # a caller-chosen prime set was not sized for the new objective
+            return False
         m = self.m
         C, sigma_m = info["C"], info["sigma_m"]
         alive = self._alive()
