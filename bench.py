@@ -38,6 +38,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries the ONE JSON line of the contract: whatever NCCL has to say (its version banner under NCCL_DEBUG)
+# goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC, UNIT = "pivots_per_sec", "pivots/s"
 
