@@ -38,9 +38,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries the ONE JSON line of the contract: whatever NCCL has to say (its version banner under NCCL_DEBUG)
-# goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries the ONE JSON line of the contract.  Libraries write there too (NCCL's version banner on the first
+# communicator, for one): file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved one.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 METRIC, UNIT = "pivots_per_sec", "pivots/s"
 
@@ -177,7 +183,7 @@ def run_reference(a):
         "note": "the reference is single-threaded pure Python (fractions.Fraction) and cannot hold this tableau; "
                 "this arm is oracle/pivot_oracle.c, the C restatement of its float path, on all host cores",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -342,7 +348,7 @@ def run_ours(a):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
