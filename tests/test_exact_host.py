@@ -225,3 +225,27 @@ def test_row_operations_in_fraction_free_form(seed):
         check()
         steps += 1
     assert steps >= 6
+
+
+def test_prepare_phase2_agrees_between_array_and_list_inputs():
+    """The integer-array path of `ExactEngine._prepare_phase2` (what `Tableau.from_grid` with integers takes) gives the
+    same objective integers, scale and column norms as the entry-by-entry path, and a bound that covers both the
+    phase-1 matrix and the matrix with the original objective."""
+    rng = random.Random(9)
+    m, n0, k = 7, 11, 4
+    n = n0 + k
+    rows = [[rng.randint(-9, 9) for _ in range(n0)] + [1 if j == i else 0 for j in range(k)] + [rng.randint(0, 40)] for i in range(m)]
+    obj = [-sum(rows[i][j] for i in range(k)) for j in range(n + 1)]
+    grid = rows + [obj]
+    cost = [Fraction(rng.randint(1, 9)) for _ in range(n0)] + [Fraction(-5)]
+    eng = object.__new__(X.ExactEngine)
+    eng.m, eng.n = m, n
+    sigma = [1] * (m + 1)
+    bits_l, info_l = eng._prepare_phase2(cost, grid, sigma)
+    bits_a, info_a = eng._prepare_phase2(cost, np.array(grid, dtype=np.int64), sigma)
+    assert info_l["C"] == info_a["C"] and info_l["sigma_m"] == info_a["sigma_m"] == 1
+    assert info_l["col_sq_a"] == info_a["col_sq_a"] and abs(bits_l - bits_a) <= 1
+    with_cost = rows + [[int(v) for v in cost[:n0]] + [0] * k + [int(cost[n0])]]
+    assert bits_l >= max(X.hadamard_bits(grid), X.hadamard_bits(with_cost)) - 1
+    w = X.weights_from_squares([0, 1, 2, 1 << 40, (1 << 200) + 1])
+    assert w[0] == 0 and w[1] >= 0 and w[3] >= 256 * 20 and w[4] >= 256 * 100 and w == sorted(w)
