@@ -276,14 +276,30 @@ class Tableau:
         self._touch_host()
         self._grid[self._m][self._n] = v
 
+    @staticmethod
+    def _converted_prefix(convert, count: int):
+        """The reference's bulk setters assign element by element (tableau.py:131-153), so a bad or missing element
+        leaves everything before it stored.  -> (values converted before the failure, the exception or None)."""
+        vals = []
+        try:
+            for k in range(count):
+                vals.append(convert(k))
+        except Exception as e:
+            return vals, e
+        return vals, None
+
     def setC(self, c: List[Any]):
-        vals = [self._num(c[j]) for j in range(self._n)]
-        if self._mode == "exact" and (G := self._int_host(*vals)) is not None:
-            G[self._m, :self._n] = [v.numerator for v in vals]
-            return
-        self._touch_host()
-        for j, v in enumerate(vals):
-            self._grid[self._m][j] = v
+        vals, err = self._converted_prefix(lambda j: self._num(c[j]), self._n)
+        if not vals:
+            pass
+        elif self._mode == "exact" and (G := self._int_host(*vals)) is not None:
+            G[self._m, :len(vals)] = [v.numerator for v in vals]
+        else:
+            self._touch_host()
+            for j, v in enumerate(vals):
+                self._grid[self._m][j] = v
+        if err is not None:
+            raise err
 
     def setCj(self, j: int, cj):
         v = self._num(cj)
@@ -295,10 +311,13 @@ class Tableau:
         self._grid[self._m][j] = v
 
     def setB(self, b: List[Any]):
-        vals = [self._num(b[i]) for i in range(self._m)]
-        self._touch_host()
-        for i, v in enumerate(vals):
-            self._grid[i][self._n] = v
+        vals, err = self._converted_prefix(lambda i: self._num(b[i]), self._m)
+        if vals:
+            self._touch_host()
+            for i, v in enumerate(vals):
+                self._grid[i][self._n] = v
+        if err is not None:
+            raise err
 
     def setBi(self, i: int, bi):
         v = self._num(bi)
@@ -307,11 +326,14 @@ class Tableau:
         self._grid[i][self._n] = v
 
     def setA(self, a: List[List[Any]]):
-        vals = [[self._num(a[i][j]) for j in range(self._n)] for i in range(self._m)]
-        self._touch_host()
-        for i in range(self._m):
-            for j in range(self._n):
-                self._grid[i][j] = vals[i][j]
+        n = self._n
+        vals, err = self._converted_prefix(lambda k: self._num(a[k // n][k % n]), self._m * n)
+        if vals:
+            self._touch_host()
+            for k, v in enumerate(vals):
+                self._grid[k // n][k % n] = v
+        if err is not None:
+            raise err
 
     def setAij(self, i: int, j: int, aij):
         v = self._num(aij)

@@ -171,6 +171,12 @@ t.toggleVarMark(2)
 """, ["t.getZ()", "t.getC()", "t.getB()", "t.getA()", "t.getVarNames()", "t.getVarMarks()", "t.setC([1, 2])",
       "t.setB([1, 2, 3])", "t.setA([[1, 2, 3]])", "t.setA([[1, 2], [3, 4]])", "t.setVarNames(['a'])",
       "t.setVarMarks([True])", "t.setCj(3, 1)", "t.setBi(2, 1)", "t.setAij(0, 3, 1)"]),
+    # the bulk setters assign element by element (tableau.py:131-153): what precedes a bad or missing element stays
+    ("tableau_setters_stop_at_the_bad_element", """
+t = T(2, 3)
+""", ["t.setC([5, 'abc', 7])", "t.getC()", "t.setB(['1/2'])", "t.getB()", "t.setA([[1, 2, 3], [4, None, 6]])",
+      "t.getA()", "t.setA([[9, 8]])", "t.getA()", "t.setC([0.5])", "t.getC()", "t.setVarNames(['p', 'q'])",
+      "t.getVarNames()", "t.setVarMarks([True])", "t.getVarMarks()"]),
     ("tableau_resize", """
 t = mk([1, 2], [[3, 4], [5, 6]], [7, 8], names=['a', 'b'])
 t.addVar('c')

@@ -1,0 +1,238 @@
+"""Differential fuzz of the host-side class surface against the UNMODIFIED reference (build container only).
+
+Random programs over LinExpr / LinCon / LinVar (linprog.py:22-381) and over the Tableau bookkeeping that needs no
+device (setters, getters, addVars/addCons, permutations, copy, JSON, print formats, exact-mode row operations on a
+host-resident tableau: tableau.py:70-293,312-462) are run against `/root/reference/lpsol` and against this package;
+every step's repr (or exception type + message) must agree.  Usage: python tools/fuzz_host.py [--seed S] [--n N].
+Divergences found here become named programs in tests/api_cases.py (whose answers are recorded fixtures, so they
+travel to the GPU box; this script cannot).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import os
+import random
+import sys
+from fractions import Fraction
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.dont_write_bytecode = True
+
+
+def load_reference():
+    sys.path.insert(0, "/root/reference")
+    ref = importlib.import_module("lpsol")
+    sys.path.pop(0)
+    return ref
+
+
+NAMES = ["x", "y", "z", "w", "_a1", "Q"]
+BAD_NAMES = ["", "3x", "x y", None, 5]
+
+
+def rnum(rng):
+    k = rng.randrange(8)
+    if k == 0:
+        return 0
+    if k == 1:
+        return rng.randint(-5, 5)
+    if k == 2:
+        return f"{rng.randint(-9, 9)}/{rng.randint(1, 6)}"
+    if k == 3:
+        return rng.choice([0.5, -0.25, 1.5, 2.0])
+    if k == 4:
+        return Fraction(rng.randint(-9, 9), rng.randint(1, 7))
+    if k == 5:
+        return 1
+    if k == 6:
+        return rng.choice(["abc", None, [1]]) if rng.random() < 0.15 else -1
+    return rng.randint(-20, 20)
+
+
+def src_num(v):
+    return repr(v)
+
+
+def gen_expr(rng, depth=0):
+    """Python source of a LinExpr-valued expression."""
+    k = rng.randrange(7 if depth < 2 else 3)
+    if k == 0:
+        return f"LinExpr({src_num(rnum(rng))})"
+    if k == 1:
+        args = []
+        for _ in range(rng.randint(1, 3)):
+            args += [src_num(rnum(rng)), repr(rng.choice(NAMES if rng.random() < 0.93 else BAD_NAMES))]
+        if rng.random() < 0.5:
+            args.append(src_num(rnum(rng)))
+        return f"LinExpr({', '.join(args)})"
+    if k == 2:
+        return "LinExpr()"
+    a, b = gen_expr(rng, depth + 1), gen_expr(rng, depth + 1)
+    if k == 3:
+        return f"({a} {rng.choice('+-')} {b})"
+    if k == 4:
+        return f"({rng.choice('+-')}{a})"
+    if k == 5:
+        return f"({src_num(rnum(rng))} {rng.choice('+-')} {a})"
+    return f"({a} {rng.choice('+-')} {src_num(rnum(rng))})"
+
+
+def gen_vars(rng):
+    d = {}
+    for nm in NAMES:
+        if rng.random() < 0.6:
+            d[nm] = rnum(rng) if rng.random() < 0.7 else gen_expr(rng, 2)
+    return "{" + ", ".join(f"{k!r}: {v if isinstance(v, str) and v.startswith(('LinExpr', '(')) else src_num(v)}"
+                           for k, v in d.items()) + "}"
+
+
+def model_program(rng):
+    lines = []
+    e = gen_expr(rng)
+    f = gen_expr(rng)
+    lines += [f"e = {e}", f"f = {f}"]
+    exprs = ["str(e)", "repr(e)", "str(f)", "e == f", "e.getConstant()", "[e.getCoefficient(v) for v in 'xyzw']",
+             "str(e + f)", "str(e - f)", "repr(-e)", "e.copy() == e",
+             f"e.evaluate({gen_vars(rng)})", f"str(e.substitute({gen_vars(rng)}))",
+             f"repr(f.substitute({gen_vars(rng)}))"]
+    comp = rng.choice(["constrantEq", "constraintLeq", "constraintGeq"])
+    exprs += [f"str(e.{comp}(f))", f"repr(e.{comp}(f))", f"str(e.{comp}({src_num(rnum(rng))}))",
+              f"str(e.{comp}(f).simplify())", f"repr(e.{comp}(f).reverse())",
+              f"e.{comp}(f).evaluate({gen_vars(rng)})", f"e.{comp}(f) == e.{comp}(f).copy()",
+              f"e.{comp}(f) == f.{comp}(e)"]
+    op = rng.choice(["addLeft", "addRight", "subLeft", "subRight"])
+    lines += [f"c = e.{comp}(f)"]
+    exprs += [f"c.{op}({gen_expr(rng, 2)})", "str(c)", f"c.{op}({src_num(rnum(rng))})", "repr(c)", "str(c.simplify())"]
+    lb = rng.choice([None, rnum(rng)])
+    ub = rng.choice([None, rnum(rng)])
+    integral = rng.random() < 0.5
+    lines += [f"v = LinVar({rng.choice(NAMES)!r}, {integral}, {src_num(lb)}, {src_num(ub)})"]
+    exprs += ["str(v)", "repr(v)", "v.getBounds()", "v.isFeasible()", f"v.boundAbove({src_num(rnum(rng))})", "str(v)",
+              f"v.boundBelow({src_num(rnum(rng))})", "repr(v)", "v.getBounds()", "v.isFeasible()", "v.copy() == v",
+              f"LinVar({rng.choice(BAD_NAMES + NAMES)!r})"]
+    return "\n".join(lines), exprs
+
+
+def gen_row(rng, n):
+    return [rnum(rng) if rng.random() < 0.9 else rng.randint(-3, 3) for _ in range(n)]
+
+
+def tableau_program(rng):
+    m, n = rng.randint(1, 4), rng.randint(1, 5)
+    lines = [f"t = T({m}, {n})"]
+    exprs = ["t.getTableauSize()", "snap(t.getC())", "snap(t.getA())"]
+
+    def rr(extra=0):
+        return rng.randint(-1 if rng.random() < 0.1 else 0, m - 1 + extra + (1 if rng.random() < 0.1 else 0))
+
+    def cc(extra=0):
+        return rng.randint(-1 if rng.random() < 0.1 else 0, n - 1 + extra + (1 if rng.random() < 0.1 else 0))
+
+    for _ in range(rng.randint(4, 14)):
+        k = rng.randrange(22)
+        if k == 0:
+            exprs.append(f"t.setC({gen_row(rng, n if rng.random() < 0.9 else n + 1)!r})")
+        elif k == 1:
+            exprs.append(f"t.setB({gen_row(rng, m if rng.random() < 0.9 else m + 1)!r})")
+        elif k == 2:
+            exprs.append(f"t.setA({[gen_row(rng, n) for _ in range(m if rng.random() < 0.9 else m + 1)]!r})")
+        elif k == 3:
+            exprs.append(f"t.setZ({src_num(rnum(rng))})")
+        elif k == 4:
+            exprs.append(f"t.setAij({rr()}, {cc()}, {src_num(rnum(rng))})")
+        elif k == 5:
+            exprs.append(f"t.setCj({cc()}, {src_num(rnum(rng))})")
+        elif k == 6:
+            exprs.append(f"t.setBi({rr()}, {src_num(rnum(rng))})")
+        elif k == 7:
+            exprs.append(f"t.rowMult({rr()}, {src_num(rnum(rng))})")
+        elif k == 8:
+            exprs.append(f"t.rowDiv({rr()}, {src_num(rnum(rng))})")
+        elif k == 9:
+            exprs.append(f"t.rowAdd({rr()}, {rr()}, {src_num(rnum(rng))})")
+        elif k == 10:
+            exprs.append(f"t.rowSub({rr()}, {rr()})")
+        elif k == 11:
+            exprs.append(f"t.rowAddToObj({rr()}, {src_num(rnum(rng))})")
+        elif k == 12:
+            exprs.append(f"t.rowSubFromObj({rr()})")
+        elif k == 13:
+            cnt = rng.randint(0, 2)
+            exprs.append(f"t.addVars({[rng.choice(NAMES) for _ in range(cnt)]!r})")
+            n += cnt
+        elif k == 14:
+            exprs.append("t.addCon()")
+            m += 1
+        elif k == 15:
+            p = list(range(m))
+            rng.shuffle(p)
+            if rng.random() < 0.1:
+                p = p[:-1] + [0]
+            exprs.append(f"t.permuteRows({p!r})")
+        elif k == 16:
+            p = list(range(n))
+            rng.shuffle(p)
+            if rng.random() < 0.1:
+                p = p + [n]
+            exprs.append(f"t.permuteCols({p!r})")
+        elif k == 17:
+            exprs.append(f"t.setVarName({cc()}, {rng.choice(NAMES)!r})")
+        elif k == 18:
+            exprs.append(f"t.setVarMark({cc()}, {rng.random() < 0.5})")
+            exprs.append(f"t.toggleVarMark({cc()})")
+        elif k == 19:
+            exprs.append("t.copy() == t")
+            exprs.append("T(1, 1).loadJson(t.saveJson())")
+        elif k == 20:
+            exprs.append(f"t.getAij({rr()}, {cc()})")
+            exprs.append(f"t.getBi({rr()})")
+            exprs.append(f"t.getCj({cc()})")
+        else:
+            exprs.append(f"t.addCons({rng.randint(0, 2)})")
+            # size tracked below through getTableauSize; keep local m conservative
+        exprs.append("(t.getTableauSize(), t.getZ(), snap(t.getC()), snap(t.getB()), snap(t.getA()))")
+    exprs += ["t.saveJson()", "t.printCSV()", "t.printLatex()", "t.printText()", "t.printGrid()", "str(t)",
+              "t.getVarNames()", "t.getVarMarks()", "t.printCSV(labels=False, rownums=True)",
+              "t.printText(rownums=True, spacing=1, left=True)"]
+    return "\n".join(lines), exprs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--n", type=int, default=300)
+    ap.add_argument("--kind", choices=["model", "tableau", "both"], default="both")
+    a = ap.parse_args()
+    import api_cases
+    ref = load_reference()
+    import linear_program_solver_b200 as pkg
+    bad = 0
+    for k in range(a.n):
+        rng = random.Random(a.seed * 1000003 + k)
+        for kind, gen in (("model", model_program), ("tableau", tableau_program)):
+            if a.kind not in (kind, "both"):
+                continue
+            setup, exprs = gen(rng)
+            want = api_cases.run_case(ref, setup, exprs, make_tableau=lambda m, n: ref.Tableau(m, n))
+            got = api_cases.run_case(pkg, setup, exprs, make_tableau=lambda m, n: pkg.Tableau(m, n))
+            for i, (g, w) in enumerate(zip(got, want)):
+                same = g == w or any(g.startswith(x) and w.startswith(x) for x in ("!IndexError", "!TypeError"))
+                if not same:
+                    bad += 1
+                    print(f"--- program {k} ({kind}), seed {a.seed}")
+                    print(setup)
+                    print("expr:", exprs[i] if len(got) == len(exprs) else "(setup)")
+                    if i and len(got) == len(exprs):
+                        print("after:", exprs[i - 1], "->", got[i - 1][:120], "| reference:", want[i - 1][:120])
+                    print("  got ", g[:300])
+                    print("  want", w[:300])
+                    break
+    print(f"{bad} divergent programs of {a.n}")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
