@@ -86,12 +86,28 @@ class Simplex:
             for i, j in enumerate(self._bfs):
                 tab.rowSubFromObj(i, tab.getCj(j))
         if not all(rowkeep):
-            # the reference leaves its row count stale after dropping a dependent row
-            # (simplex.py:93) and fails on the next row scan; same exception, sane tableau
-            raise IndexError("list index out of range")
+            self._fail_like_stale_row_count()
         assert tab.isCanonical(), "tableau not canonical (internal error)"
         for j in self._bfs:
             tab.setVarMark(j, True)
+
+    def _fail_like_stale_row_count(self):
+        """The reference re-installs the OLD row count after dropping dependent rows (simplex.py:93), so its closing
+        `isCanonical` (simplex.py:106, tableau.py:466-496) walks that many rows over the fewer that are left: a
+        zero-cost column whose scan for its 1 (tableau.py:482-485) or whose all-others-zero check (:487-488) runs past
+        the last row dies with IndexError; when no column does, the dropped rows have no basic column and the assert
+        fires.  Same exception here, on a tableau that is left sane (rows really dropped).  Always raises."""
+        tab = self._tab
+        a, c = tab.getA(), tab.getC()
+        rows = range(len(a))
+        if not any(bi < 0 for bi in tab.getB()):
+            for j in range(len(c)):
+                if c[j] != 0:
+                    continue
+                one = next((i for i in rows if a[i][j] == 1), -1)
+                if one == -1 or all(i == one or a[i][j] == 0 for i in rows):
+                    raise IndexError("list index out of range")
+        raise AssertionError("tableau not canonical (internal error)")
 
     # ------------------------------------------------------------------------------------
     # the optimisation loop (simplex.py:110-148): one device call

@@ -327,9 +327,9 @@ def find_bfs(grid: Grid, trace: Optional[list] = None, stuck_limit: Optional[int
     negative) or their row is dropped, artificial columns are cut and the
     original objective is restored and priced out against the basis.
 
-    Deviation, documented: the reference resets `_m` to the OLD row count after
-    dropping a dependent row (simplex.py:93) and then crashes with IndexError
-    (SURVEY F5b).  This restatement raises the same IndexError in that case.
+    The reference resets `_m` to the OLD row count after dropping a dependent
+    row (simplex.py:93) and then fails in its closing `isCanonical` (SURVEY
+    F5b): `stale_row_count_failure` reproduces which exception that is.
     """
     m, n = shape(grid)
     num = type(grid[0][0])
@@ -373,9 +373,12 @@ def find_bfs(grid: Grid, trace: Optional[list] = None, stuck_limit: Optional[int
             basis[i] = col
             if trace is not None:
                 trace.append((i, col, 2))
+    m_old = m
     if not all(keep):
-        # simplex.py:93 leaves the row count stale; the next row access fails
-        raise IndexError("list index out of range")
+        # simplex.py:89-93 filters `_bfs`, `_b`, `_a` but re-installs the OLD row count
+        grid[:] = [row for i, row in enumerate(grid) if i == m or keep[i]]
+        basis[:] = [j for i, j in enumerate(basis) if keep[i]]
+        m = len(basis)
     # cut the artificial columns, restore and price out the original objective
     for i in range(m + 1):
         row = grid[i]
@@ -386,8 +389,28 @@ def find_bfs(grid: Grid, trace: Optional[list] = None, stuck_limit: Optional[int
         grid[m][j] = saved_cost[j]
     for i, j in enumerate(basis):
         row_axpy(grid, m, i, -grid[m][j])
+    if m != m_old:
+        stale_row_count_failure(grid, m_old)
     assert is_canonical(grid), "tableau not canonical (internal error)"
     return grid, basis
+
+
+def stale_row_count_failure(grid: Grid, m_old: int) -> None:
+    """What simplex.py:106 does after dependent rows were dropped: `isCanonical` (tableau.py:466-496)
+    walks `range(m_old)` over the FEWER rows that are left.  A zero-cost column whose scan for its 1 (tableau.py:482-485)
+    or whose all-others-zero check (:487-488) runs past the last row dies with IndexError; when no column does (every
+    zero-cost column holds a 1 and another nonzero, or no reduced cost is 0) the dropped rows have no basic column and
+    the constructor's assert fires instead.  Always raises."""
+    m, n = shape(grid)
+    assert m < m_old
+    if not any(grid[i][n] < 0 for i in range(m)):
+        for j in range(n):
+            if grid[m][j] != 0:
+                continue
+            one = next((i for i in range(m) if grid[i][j] == 1), -1)
+            if one == -1 or all(i == one or grid[i][j] == 0 for i in range(m)):
+                raise IndexError("list index out of range")
+    raise AssertionError("tableau not canonical (internal error)")
 
 
 def simplex(c, A, b, z=0, num: Callable = Fraction, max_pivots: Optional[int] = None, stuck_limit: Optional[int] = None):
