@@ -86,6 +86,7 @@ class BatchResult:
         self._sign, self._digits, self._codec = sign, digits, codec
         self.trace = trace                    # [count, trace_cap, 3] or None
         self._ints: Dict[int, List[int]] = {}
+        self.no_row_no_zero_cost = None       # [count] bool from `solve_batch`: all rows zero and no cost equal to 0
 
     def __len__(self) -> int:
         return len(self.status)
@@ -160,6 +161,12 @@ class BatchResult:
         if st == N.INFEASIBLE:
             raise ValueError(f"infeasible problem, artificial opt = {self.objective(k)}")
         if st == N.REDUNDANT_ROW:
+            # simplex.py:93 leaves the row count stale after dropping dependent rows; the closing isCanonical then runs
+            # past the last row (IndexError) as soon as it scans a zero-cost column -- every kept row has one (its basis
+            # column).  Only an LP whose rows are ALL zero keeps no row: then a cost of 0 still gives the IndexError,
+            # and with none the scan touches nothing and the constructor's assert fires (simplex.py:106).
+            if self.no_row_no_zero_cost is not None and self.no_row_no_zero_cost[k]:
+                raise AssertionError("tableau not canonical (internal error)")
             raise IndexError("list index out of range")
         if st == N.UNBOUNDED:
             raise AssertionError("unbounded artificial problem (internal error)")
@@ -363,8 +370,12 @@ def solve_batch(grids, trace_cap: int = 0, cluster: int = 0, device: Optional[in
             Gr = Gd[torch.from_numpy(redo).to(dev)].contiguous()
             torch.cuda.current_stream(dev).synchronize()
             second = run(Gr, primes, False)
-        return _merge_tiers(first, second, redo, MixedRadix(primes))
-    return run(Gd, primes, False)
+        out = _merge_tiers(first, second, redo, MixedRadix(primes))
+    else:
+        out = run(Gd, primes, False)
+    if (out.status == N.REDUNDANT_ROW).any():             # which exception `raise_for_status` owes the caller
+        out.no_row_no_zero_cost = ~G32[:, :m, :].any(axis=(1, 2)) & G32[:, m, :n].all(axis=1)
+    return out
 
 
 def _merge_tiers(first: "BatchResult", second: Optional["BatchResult"], redo: np.ndarray, codec: MixedRadix) -> "BatchResult":

@@ -32,6 +32,8 @@ class Simplex:
         #: (row, column, rule) of every pivot made through this object; rule 0 = Dantzig,
         #: 1 = Bland, 2 = explicit.  Not in the reference (its `num_piv` is a dead local).
         self.pivot_log: List[Tuple[int, int, int]] = []
+        #: pivots made by the latest `solve()` (which returns None like simplex.py:110)
+        self.last_pivots: int = 0
         self._find_bfs()
 
     # ------------------------------------------------------------------------------------
@@ -117,7 +119,7 @@ class Simplex:
         pivots when the objective seems stuck (simplex.py:110-148).
 
         `max_pivots` (not in the reference) stops after a prefix of pivots; the default runs to
-        optimality.  Returns the number of pivots made."""
+        optimality.  Returns None like the reference; the number of pivots made is `self.last_pivots`."""
         tab = self._tab
         eng = tab._touch_dev()
         m, n = tab.getTableauSize()
@@ -125,6 +127,7 @@ class Simplex:
         marks = np.asarray(tab._cm, dtype=np.int32)
         cap = max_pivots if max_pivots >= 0 else 1 << 16
         status, npiv, trace = eng.solve(basis, marks, max_pivots=max_pivots, trace_cap=cap)
+        self.last_pivots = int(npiv)
         self._bfs[:] = [int(j) for j in basis]
         tab._cm[:] = [bool(x) for x in marks]
         if trace is not None:
@@ -132,10 +135,7 @@ class Simplex:
         assert status != N.UNBOUNDED, "unbounded artificial problem (internal error)"
         if status == N.STALLED:
             raise AssertionError("objective value increased (internal error)")
-        if status == N.MAX_PIVOTS:
-            return npiv
-        assert status == N.OPTIMAL, "solver failed (internal error)"
-        return npiv
+        assert status in (N.OPTIMAL, N.MAX_PIVOTS), "solver failed (internal error)"
 
     # ------------------------------------------------------------------------------------
     # results (simplex.py:150-190)

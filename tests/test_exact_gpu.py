@@ -388,7 +388,8 @@ def test_c3_full_solve_carries_an_exact_optimality_certificate():
     grid = np.array([A[i] + [b[i]] for i in range(m)] + [c + [0]], dtype=np.int64)
     t = Tableau.from_grid(grid, mode="exact")
     s = Simplex(t)
-    npiv = s.solve()
+    assert s.solve() is None                               # simplex.py:110 returns nothing; the count is an attribute
+    npiv = s.last_pivots
     rec = next(r for r in load_golden("dense_exact") if r["m"] == m and r["hi"] == 127)
     assert [list(p) for p in s.pivot_log[:len(rec["pivots"])]] == rec["pivots"]
     assert npiv == len(s.pivot_log) > m // 2

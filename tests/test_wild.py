@@ -121,3 +121,44 @@ def test_fp64_mode_matches_float_rebound_reference_on_the_wild_corpus(chunk):
         except BaseException as e:
             bad.append((rec["id"], type(e).__name__, str(e)[:300]))
     assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_batched_node_lp_kernel_matches_reference_on_the_wild_corpus():
+    """The batched kernel (`k_bnb_nodes`: its own constructor + solve, one LP per thread-block cluster) on the
+    integer-data records, grouped by shape into batches: outcome (the exception the reference raises, through
+    `raise_for_status`), pivot trace with rules, basis, objective and basic solution."""
+    import numpy as np
+
+    from linear_program_solver_b200 import _native as N
+    from linear_program_solver_b200 import problems
+    from linear_program_solver_b200.batch import solve_batch
+    by_shape = {}
+    for rec in WILD:
+        if "float" in rec:
+            c, A, b = _data(rec, int)
+            by_shape.setdefault((len(A), len(c)), []).append((rec, np.asarray(problems.to_grid(c, A, b), dtype=np.int64)))
+    assert len(by_shape) >= 40
+    bad = []
+    for (m, n), group in sorted(by_shape.items()):
+        res = solve_batch(np.stack([g for _, g in group]), trace_cap=128)
+        for k, (rec, _) in enumerate(group):
+            try:
+                if "ctor_error" in rec or "solve_error" in rec:
+                    kind, msg = rec.get("ctor_error") or rec["solve_error"]
+                    with pytest.raises(ERR[kind]) as ei:
+                        res.raise_for_status(k)
+                    assert not isinstance(ei.value, N.NativeError)
+                    if kind != "IndexError":
+                        assert str(ei.value) == msg
+                    if "solve_error" in rec:
+                        assert [list(p) for p in res.pivots(k)] == rec["phase1_pivots"] + rec["pivots"]
+                    continue
+                assert int(res.status[k]) == N.OPTIMAL, res.status_name(k)
+                assert [list(p) for p in res.pivots(k)] == rec["phase1_pivots"] + rec["pivots"]
+                assert [int(j) for j in res.basis[k][:len(rec["basis"])]] == rec["basis"]
+                assert str(res.objective(k)) == rec["objective"]
+                assert {str(j): str(v) for j, v in res.bfs(k).items()} == rec["bfs"]
+            except BaseException as e:
+                bad.append((rec["id"], (m, n), type(e).__name__, str(e)[:300]))
+    assert not bad, "\n".join(map(str, bad))
