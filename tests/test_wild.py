@@ -162,3 +162,45 @@ def test_batched_node_lp_kernel_matches_reference_on_the_wild_corpus():
             except BaseException as e:
                 bad.append((rec["id"], (m, n), type(e).__name__, str(e)[:300]))
     assert not bad, "\n".join(map(str, bad))
+
+
+MEDIUM = [(12, 20, 0), (12, 20, 7), (12, 20, 9), (20, 30, 0), (20, 30, 3), (20, 30, 4), (20, 30, 5), (20, 30, 8),
+          (30, 50, 0), (30, 50, 3), (30, 50, 4), (30, 50, 7), (45, 70, 4), (45, 70, 7), (45, 70, 8)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["exact", "fp64"])
+@pytest.mark.parametrize("m,n,seed", MEDIUM, ids=lambda v: str(v))
+def test_medium_irregular_lps_match_the_oracle(m, n, seed, mode):
+    """The irregular family at 12..46 rows (optimal after 14..60 phase-1 pivots, infeasible, unbounded in phase 2,
+    dependent rows; some with rational data) against the oracle, which the small corpus above pins to the reference:
+    same exception, or same traces / basis / objective / solution -- exact strings, or floats bit for bit."""
+    import random
+
+    from linear_program_solver_b200 import Simplex, Tableau, problems
+    from oracle import lpsol_oracle as O
+    num = Fraction if mode == "exact" else float
+    c, A, b = problems.irregular_lp(random.Random(7000 + seed * 31 + m), m, n)
+    c, A, b = [num(v) for v in c], [[num(v) for v in r] for r in A], [num(v) for v in b]
+    try:
+        want = O.simplex(c, A, b, num=num)
+    except (ValueError, IndexError, AssertionError) as e:
+        want = e
+    t = Tableau(len(A), len(c), mode=mode)
+    t.setC(c)
+    t.setB(b)
+    t.setA(A)
+    if isinstance(want, Exception):
+        kind = next(k for k in (ValueError, IndexError, AssertionError) if isinstance(want, k))
+        with pytest.raises(kind) as ei:
+            Simplex(t).solve()
+        if kind is not IndexError:
+            assert str(ei.value) == str(want)
+        return
+    s = Simplex(t)
+    assert [list(p) for p in s.pivot_log] == [list(p) for p in want["phase1_pivots"]]
+    s.solve()
+    assert [list(p) for p in s.pivot_log[len(want["phase1_pivots"]):]] == [list(p) for p in want["pivots"]]
+    assert s.getBasicSequence() == want["basis"]
+    assert _fmt(s.getObjValue()) == _fmt(want["objective"])
+    assert {j: _fmt(v) for j, v in s.getBFS().items()} == {j: _fmt(v) for j, v in want["bfs"].items()}

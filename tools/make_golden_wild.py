@@ -26,56 +26,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import make_golden as MG  # noqa: E402
+from linear_program_solver_b200 import problems  # noqa: E402
 
 PIVOT_CAP = 400     # the reference's Bland variant (lowest ROW among ties) has no termination proof
-
-
-def wild_lp(rng: random.Random):
-    m = rng.randint(1, 7)
-    n = rng.randint(1, 10)
-    density = rng.choice([0.3, 0.6, 0.9, 1.0])
-    rational = rng.random() < 0.3
-    span = rng.choice([2, 3, 9])
-
-    def num(nonneg=False):
-        if rng.random() > density:
-            return Fraction(0)
-        v = Fraction(rng.randint(0 if nonneg else -span, span))
-        if rational and rng.random() < 0.5:
-            v /= rng.choice([2, 3, 4, 6])
-        return v
-
-    A = [[num() for _ in range(n)] for _ in range(m)]
-    style = rng.choice([0, 0, 0, 1, 2, 2, 3])
-    if style == 0:                                   # right-hand side of a known non-negative point: feasible
-        x = [Fraction(rng.randint(0, 3)) for _ in range(n)]
-        b = [sum(a * v for a, v in zip(row, x)) for row in A]
-    elif style == 1:
-        b = [Fraction(rng.randint(-6, 6)) for _ in range(m)]
-    elif style == 2:
-        b = [Fraction(rng.randint(0, 8)) for _ in range(m)]
-    else:
-        b = [Fraction(0) if rng.random() < 0.5 else Fraction(rng.randint(1, 5)) for _ in range(m)]
-    if rng.random() < 0.5:                           # slack columns on some rows (a partial or complete slack basis)
-        for i in range(m):
-            if rng.random() < 0.7:
-                for r in range(m):
-                    A[r].append(Fraction(1 if r == i else 0))
-                n += 1
-    if rng.random() < 0.4:                           # a bounding row  sum_j w_j x_j + s = K,  w > 0: no unbounded ray
-        for r in range(m):
-            A[r].append(Fraction(0))
-        A.append([Fraction(rng.randint(1, 3)) for _ in range(n)] + [Fraction(1)])
-        b.append(Fraction(rng.randint(0, 40)))
-        m, n = m + 1, n + 1
-    if m >= 2 and rng.random() < 0.2:                # a dependent row: copy or multiple of another one
-        src, dst = rng.sample(range(m), 2)
-        k = rng.choice([1, 2, -1, Fraction(1, 2)])
-        A[dst] = [k * v for v in A[src]]
-        b[dst] = k * b[src] + (0 if rng.random() < 0.7 else 1)
-    sign = rng.choice([-1, -1, 1, 0])
-    c = [Fraction(rng.randint(-span, span)) if sign == 0 else sign * Fraction(rng.randint(0, span)) for _ in range(n)]
-    return c, A, b
 
 
 def enc(x):
@@ -88,7 +41,7 @@ def main():
     stats = {}
     for k in range(int(os.environ.get("WILD_COUNT", "400"))):
         rng = random.Random(0xB200 + k)
-        c, A, b = wild_lp(rng)
+        c, A, b = problems.irregular_lp(rng)
         rec = MG.run(ref, c, A, b, max_pivots=PIVOT_CAP)
         rec["id"] = k
         rec["input"] = {"c": [enc(v) for v in c], "A": [[enc(v) for v in r] for r in A], "b": [enc(v) for v in b]}
