@@ -194,6 +194,19 @@ def tableau_program(rng):
             exprs.append(f"t.addCons({rng.randint(0, 2)})")
             # size tracked below through getTableauSize; keep local m conservative
         exprs.append("(t.getTableauSize(), t.getZ(), snap(t.getC()), snap(t.getB()), snap(t.getA()))")
+    # JSON: a saved tableau with one field damaged (loadJson's asserts and conversions, tableau.py:322-345)
+    for _ in range(rng.randint(0, 3)):
+        key = rng.choice(["m", "n", "z", "c", "b", "a", "cl", "cm", "extra"])
+        val = rng.choice(["0", "-1", "1", "'2'", "None", "[]", "[1]", "[[1]]", "'1/2'", "1.5", "['x']", "[True]", "{}"])
+        op = rng.choice([f"d[{key!r}] = {val}", f"d.pop({key!r}, None)"])
+        exprs.append(f"(lambda d: (d.__setitem__('_', 0), exec({op!r}, {{'d': d}}), d.pop('_'), "
+                     f"(lambda u: (u.loadJson(d), u.saveJson())[1])(T(1, 1)))[3])(t.saveJson())")
+    mpre, msuf = rng.choice([("(", ")"), ("[", "]"), ("", ""), ("<<", "")])
+    exprs += [f"t.printCSV(mpre={mpre!r}, msuf={msuf!r})", f"t.printLatex(labels={rng.random() < 0.5}, "
+              f"rownums={rng.random() < 0.5}, mpre={mpre!r}, msuf={msuf!r})",
+              f"t.printText(labels={rng.random() < 0.5}, rownums={rng.random() < 0.5}, spacing={rng.randint(0, 4)}, "
+              f"left={rng.random() < 0.5})", f"t.printGrid(labels={rng.random() < 0.5}, rownums={rng.random() < 0.5}, "
+              f"mpre={mpre!r}, msuf={msuf!r})", "__import__('re').sub('0x[0-9a-f]+', '0x', repr(t))"]
     exprs += ["t.saveJson()", "t.printCSV()", "t.printLatex()", "t.printText()", "t.printGrid()", "str(t)",
               "t.getVarNames()", "t.getVarMarks()", "t.printCSV(labels=False, rownums=True)",
               "t.printText(rownums=True, spacing=1, left=True)"]
