@@ -101,3 +101,93 @@ def test_peer_store_exchange_between_engines_of_one_process(m, parts, seed):
         got = e.download()
         assert got[:ml].tobytes() == T[row0:row0 + ml].tobytes() and got[ml].tobytes() == T[m].tobytes()
         e.close()
+
+
+def _tie_heavy_grid(m, parts, seed):
+    """Canonical LP whose ratio tests tie ACROSS shards: the structural part of row i repeats every m // parts rows
+    with the same right-hand side (small integers, so the ratios are exactly equal doubles); the twins of a leaving row
+    drop to b = 0, so degenerate pivots follow.  The leaving row must be the lowest GLOBAL row among the ties
+    (simplex.py:277), whichever shard holds it."""
+    import random
+    rng = random.Random(seed)
+    period = m // parts
+    base = [[rng.randint(1, 3) for _ in range(m)] for _ in range(period)]
+    rhs = [rng.randint(1, 4) * 6 for _ in range(period)]
+    T = np.zeros((m + 1, 2 * m + 1))
+    for i in range(m):
+        T[i, :m] = base[i % period]
+        T[i, m + i] = 1.0
+        T[i, 2 * m] = rhs[i % period]
+    T[m, :m] = [-rng.randint(1, 3) for _ in range(m)]
+    return T
+
+
+@pytest.mark.parametrize("m,parts,seed", [(48, 3, 0), (64, 4, 6), (60, 2, 2), (80, 4, 2)])
+def test_ties_across_shards_pick_the_lowest_global_row(m, parts, seed):
+    """Peer-store exchange on a tableau built so that the minimum ratio is attained on several shards at once."""
+    import torch
+    from linear_program_solver_b200.engine import F64Engine
+    from linear_program_solver_b200.sharded import shard_rows
+    from oracle import c_oracle as C
+    n = 2 * m
+    T = _tie_heavy_grid(m, parts, seed)
+    ndev = torch.cuda.device_count()
+    engs = []
+    for g in range(parts):
+        row0, ml = shard_rows(m, g, parts)
+        engs.append(F64Engine(ml, n, device=g % ndev))
+    blocks = [e.p2p_block() for e in engs]
+    for g, e in enumerate(engs):
+        row0, ml = shard_rows(m, g, parts)
+        e.p2p_attach_local(row0, m, g, parts, blocks)
+        e.upload(np.ascontiguousarray(np.vstack([T[row0:row0 + ml], T[m:m + 1]])))
+    basis = np.arange(m, n, dtype=np.int32)
+    for e in engs:
+        e.solve_begin(basis, None, -1, 8192)
+    done = False
+    for _ in range(200):
+        for _ in range(16):
+            for e in engs:
+                e.step_select()
+            for e in engs:
+                e.step_update()
+        st = {e.poll() for e in engs}
+        assert len(st) == 1, st
+        if next(iter(st))[0] != 0:
+            done = True
+            break
+    assert done
+    want = T.copy()
+    ob = np.arange(m, n, dtype=np.int32)
+    ost, ok, otrace = C.solve(want, ob)
+    ties = _count_cross_shard_ties(T, otrace, m, parts)
+    assert ties >= 3, ties                                   # the construction really produced cross-shard ties
+    for g, e in enumerate(engs):
+        b = basis.copy()
+        st, k, trace = e.solve_end(b, None, 8192)
+        assert (st, k) == (ost, ok) and trace.tolist() == otrace.tolist() and b.tolist() == ob.tolist()
+        row0, ml = shard_rows(m, g, parts)
+        got = e.download()
+        assert got[:ml].tobytes() == want[row0:row0 + ml].tobytes() and got[ml].tobytes() == want[m].tobytes()
+        e.close()
+
+
+def _count_cross_shard_ties(T0, trace, m, parts):
+    """Replays the oracle's trace and counts the pivots whose minimum ratio is attained on more than one shard."""
+    from linear_program_solver_b200.sharded import shard_rows
+    from oracle import c_oracle as C
+    T = T0.copy()
+    owner = np.empty(m, dtype=int)
+    for g in range(parts):
+        row0, ml = shard_rows(m, g, parts)
+        owner[row0:row0 + ml] = g
+    ties = 0
+    for r, c, _ in trace.tolist():
+        col, rhs = T[:m, c], T[:m, -1]
+        pos = col > 0
+        ratios = np.where(pos, rhs / np.where(pos, col, 1.0), np.inf)
+        at_min = np.nonzero(ratios == ratios.min())[0]
+        assert at_min[0] == r
+        ties += len(set(owner[at_min])) > 1
+        C.pivot(T, r, c)
+    return ties
