@@ -64,6 +64,25 @@ def equality_lp(m: int, n: int, seed: int = 0, lo: int = -5, hi: int = 9) -> Gri
     return c, A, b
 
 
+def tie_heavy_grid(m: int, parts: int, seed: int = 0):
+    """Canonical LP whose ratio tests tie ACROSS shards: the structural part of row i repeats every m // parts rows
+    with the same right-hand side (small integers, so the ratios are exactly equal doubles); the twins of a leaving row
+    drop to b = 0, so degenerate pivots follow.  The leaving row must be the lowest GLOBAL row among the ties
+    (simplex.py:277), whichever shard holds it."""
+    import numpy as np
+    rng = random.Random(seed)
+    period = m // parts
+    base = [[rng.randint(1, 3) for _ in range(m)] for _ in range(period)]
+    rhs = [rng.randint(1, 4) * 6 for _ in range(period)]
+    T = np.zeros((m + 1, 2 * m + 1))
+    for i in range(m):
+        T[i, :m] = base[i % period]
+        T[i, m + i] = 1.0
+        T[i, 2 * m] = rhs[i % period]
+    T[m, :m] = [-rng.randint(1, 3) for _ in range(m)]
+    return T
+
+
 def irregular_lp(rng: random.Random, m: int = 0, n: int = 0):
     """One LP of the irregular family (tests/golden/wild.json, tools/make_golden_wild.py): mixed signs, zeros, sometimes
     rational data, negative / zero right-hand sides, partial slack bases, a bounding row, a dependent row -- feasible,

@@ -101,13 +101,14 @@ class OracleShardEngine:
         stuck = int(np.frombuffer(s[24:32].tobytes(), dtype=np.int64)[0])
         v = np.frombuffer(s[HEADER:].tobytes(), dtype=np.float64)
         lr = grow - self.row0
+        mine = 0 <= lr < self.m                    # (lr == self.m is the next rank's first row, not the objective row)
         for i in range(self.m + 1):
-            if i == lr:
+            if mine and i == lr:
                 continue
             mult = -self.T[i, c]
             if mult != 0.0:
                 self.T[i] = self.T[i] + mult * v       # product then sum, like the reference
-        if 0 <= lr < self.m:
+        if mine:
             self.T[lr] = v
         self.basis[grow] = c
         self.trace.append((grow, int(c), int(rule)))
@@ -122,14 +123,25 @@ class OracleShardEngine:
         return self.status, self.npiv, np.array(self.trace[:trace_cap], dtype=np.int32).reshape(-1, 3)
 
 
-def _worker(rank, world, port, m, seed, max_pivots, out):
+def _grid(m, seed, world, family):
+    from linear_program_solver_b200 import problems
+    if family == "ties":            # minimum ratios attained on several shards at once (lowest GLOBAL row must win)
+        return problems.tie_heavy_grid(m, world, seed)
+    return problems.hashed_dense_grid(m, seed).astype(np.float64)
+
+
+def _worker(rank, world, port, m, seed, max_pivots, family, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from linear_program_solver_b200 import problems
     from linear_program_solver_b200.sharded import ShardedF64Solver, shard_rows
     sv = ShardedF64Solver(m, 2 * m, rank, world, engine_factory=OracleShardEngine, burst=3)
     row0, ml = shard_rows(m, rank, world)
-    sv.eng.T[:] = problems.hashed_dense_grid(m, seed, 1, 9, row0, ml).astype(np.float64)
+    if family == "dense":         # every rank generates its own rows, like the device fill
+        sv.eng.T[:] = problems.hashed_dense_grid(m, seed, 1, 9, row0, ml).astype(np.float64)
+    else:
+        T = _grid(m, seed, world, family)
+        sv.eng.T[:] = np.vstack([T[row0:row0 + ml], T[m:m + 1]])
     basis = np.arange(m, 2 * m, dtype=np.int32)
     st, k, trace = sv.solve(basis, None, max_pivots=max_pivots, trace_cap=10 ** 6)
     out[rank] = (st, k, trace.tolist(), basis.tolist(), row0, sv.eng.T.copy())
@@ -137,18 +149,20 @@ def _worker(rank, world, port, m, seed, max_pivots, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,m,seed,max_pivots", [(2, 24, 0, -1), (3, 31, 1, -1), (2, 40, 2, 7)])
-def test_sharded_protocol_equals_single_process_oracle(world, m, seed, max_pivots):
+@pytest.mark.parametrize("world,m,seed,max_pivots,family", [(2, 24, 0, -1, "dense"), (3, 31, 1, -1, "dense"),
+                                                             (2, 40, 2, 7, "dense"), (2, 60, 2, -1, "ties"),
+                                                             (3, 48, 0, -1, "ties")])
+def test_sharded_protocol_equals_single_process_oracle(world, m, seed, max_pivots, family):
     from linear_program_solver_b200 import problems
     from oracle import c_oracle as C
     mgr = mp.Manager()
     out = mgr.dict()
     port = 29500 + (os.getpid() + 7 * world + m) % 2000
-    mp.spawn(_worker, args=(world, port, m, seed, max_pivots, out), nprocs=world, join=True)
-    T = problems.hashed_dense_grid(m, seed).astype(np.float64)
+    mp.spawn(_worker, args=(world, port, m, seed, max_pivots, family, out), nprocs=world, join=True)
+    T = _grid(m, seed, world, family)
     basis = np.arange(m, 2 * m, dtype=np.int32)
     st, k, trace = C.solve(T, basis, max_pivots=max_pivots)
-    assert len(out) == world
+    assert len(out) == world and (family != "ties" or k >= 7)
     for rank in range(world):
         rst, rk, rtrace, rbasis, row0, shard = out[rank]
         assert (rst, rk) == (st, k) and rtrace == trace.tolist() and rbasis == basis.tolist()

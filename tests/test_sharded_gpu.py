@@ -103,25 +103,6 @@ def test_peer_store_exchange_between_engines_of_one_process(m, parts, seed):
         e.close()
 
 
-def _tie_heavy_grid(m, parts, seed):
-    """Canonical LP whose ratio tests tie ACROSS shards: the structural part of row i repeats every m // parts rows
-    with the same right-hand side (small integers, so the ratios are exactly equal doubles); the twins of a leaving row
-    drop to b = 0, so degenerate pivots follow.  The leaving row must be the lowest GLOBAL row among the ties
-    (simplex.py:277), whichever shard holds it."""
-    import random
-    rng = random.Random(seed)
-    period = m // parts
-    base = [[rng.randint(1, 3) for _ in range(m)] for _ in range(period)]
-    rhs = [rng.randint(1, 4) * 6 for _ in range(period)]
-    T = np.zeros((m + 1, 2 * m + 1))
-    for i in range(m):
-        T[i, :m] = base[i % period]
-        T[i, m + i] = 1.0
-        T[i, 2 * m] = rhs[i % period]
-    T[m, :m] = [-rng.randint(1, 3) for _ in range(m)]
-    return T
-
-
 @pytest.mark.parametrize("m,parts,seed", [(48, 3, 0), (64, 4, 6), (60, 2, 2), (80, 4, 2)])
 def test_ties_across_shards_pick_the_lowest_global_row(m, parts, seed):
     """Peer-store exchange on a tableau built so that the minimum ratio is attained on several shards at once."""
@@ -130,7 +111,7 @@ def test_ties_across_shards_pick_the_lowest_global_row(m, parts, seed):
     from linear_program_solver_b200.sharded import shard_rows
     from oracle import c_oracle as C
     n = 2 * m
-    T = _tie_heavy_grid(m, parts, seed)
+    T = problems.tie_heavy_grid(m, parts, seed)
     ndev = torch.cuda.device_count()
     engs = []
     for g in range(parts):
