@@ -115,3 +115,48 @@ def test_golden_milp_fixtures():
         assert {k: str(v) for k, v in got["values"].items()} == rec["values"]
         assert got["nodes"] == rec["nodes"]
         assert [[d, s, None if o is None else str(o)] for d, s, o in got["trace"]] == rec["trace"]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_oracle_bnb_matches_an_independent_milp_solver(seed):
+    """The MILP layer has no reference implementation, so its oracle is pinned from outside as well: the
+    optimum of random mixed-integer programs -- free variables, variables bounded only from above, negative lower
+    bounds, equality and >= rows, rational right-hand sides, both senses -- against scipy's HiGHS (`optimize.milp`) on
+    the ORIGINAL general-form model, never on our lowering.  Objective within 1e-7; infeasibility must agree."""
+    import numpy as np
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    rng = random.Random(9000 + seed)
+    variables, cons, obj = random_ip(rng, rng.randint(2, 5), rng.randint(1, 4), pure=seed % 3 == 0)
+    if seed % 4 == 1:                            # a free variable and one bounded only from above, kept bounded by rows
+        variables[0] = (variables[0][0], False, None, None)
+        cons.append(({variables[0][0]: 1}, ">=", -7))
+        cons.append(({variables[0][0]: 1}, "<=", F(15, 2)))
+        if len(variables) > 1:
+            variables[1] = (variables[1][0], variables[1][1], None, 5)
+            cons.append(({variables[1][0]: 2}, ">=", -9))
+    names = [v[0] for v in variables]
+    oc, const, sense = obj
+    sgn = 1.0 if sense == "min" else -1.0
+    c = np.array([sgn * float(oc.get(nm, 0)) for nm in names])
+    rows, lo, hi = [], [], []
+    for coefs, comp, rhs in cons:
+        rows.append([float(coefs.get(nm, 0)) for nm in names])
+        lo.append(-np.inf if comp == "<=" else float(rhs))
+        hi.append(np.inf if comp == ">=" else float(rhs))
+    res = milp(c, constraints=LinearConstraint(np.array(rows), lo, hi),
+               integrality=np.array([1 if v[1] else 0 for v in variables]),
+               bounds=Bounds([-np.inf if v[2] is None else float(v[2]) for v in variables],
+                             [np.inf if v[3] is None else float(v[3]) for v in variables]))
+    assert res.status in (0, 2), res.message     # optimal or infeasible: the rows above keep every program bounded
+    got = B.branch_and_bound(variables, cons, obj)
+    if res.status == 2:
+        assert got["status"] == "infeasible"
+        return
+    assert got["status"] == "optimal"
+    assert abs(float(got["objective"]) - (sgn * res.fun + const)) <= 1e-7 * max(1.0, abs(res.fun))
+    x = got["values"]                            # our optimum is feasible for the original model, exactly
+    for nm, isint, lb, ub in variables:
+        assert (lb is None or x[nm] >= lb) and (ub is None or x[nm] <= ub) and (not isint or x[nm].denominator == 1)
+    for coefs, comp, rhs in cons:
+        lhs = sum(F(cf) * x[nm] for nm, cf in coefs.items())
+        assert {"<=": lhs <= rhs, ">=": lhs >= rhs, "==": lhs == rhs}[comp]
