@@ -155,7 +155,7 @@ def _worker(rank, world, port, m, seed, max_pivots, family, out):
 def test_sharded_protocol_equals_single_process_oracle(world, m, seed, max_pivots, family):
     from linear_program_solver_b200 import problems
     from oracle import c_oracle as C
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()     # not fork: the pytest process is multi-threaded by now
     out = mgr.dict()
     port = 29500 + (os.getpid() + 7 * world + m) % 2000
     mp.spawn(_worker, args=(world, port, m, seed, max_pivots, family, out), nprocs=world, join=True)
