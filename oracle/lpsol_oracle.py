@@ -17,8 +17,10 @@ instantiation is bit-identical to that rebound run.
 Parity status: PINNED.  `tests/test_oracle.py` checks this restatement against
 (a) the reference's only known-answer test on the path
 (`test_tableau.py:220-227`), (b) the known answers SURVEY.md section 8c records,
-and (c) `tests/golden/*.json`, which `tools/make_golden.py` produced by running
-the unmodified reference in the build container.
+(c) `tests/golden/*.json`, which `tools/make_golden.py` produced by running
+the unmodified reference in the build container, and (d) the irregular corpus
+`tests/golden/wild.json` (`tools/make_golden_wild.py`: 400 small LPs with every
+constructor / solve outcome, exact and float-rebound; `tests/test_wild.py`).
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu-baseline /
 `--impl reference` legs may import this module.  The product package
