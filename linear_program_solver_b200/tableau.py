@@ -326,14 +326,23 @@ class Tableau:
         self._grid[i][self._n] = v
 
     def setA(self, a: List[List[Any]]):
-        n = self._n
-        vals, err = self._converted_prefix(lambda k: self._num(a[k // n][k % n]), self._m * n)
+        m, n = self._m, self._n
+        try:                                   # the usual case: every element converts, row by row
+            rows = [[self._num(a[i][j]) for j in range(n)] for i in range(m)]
+        except Exception:
+            rows = None
+        if rows is not None:
+            if m and n:
+                self._touch_host()
+                for i in range(m):
+                    self._grid[i][:n] = rows[i]
+            return
+        vals, err = self._converted_prefix(lambda k: self._num(a[k // n][k % n]), m * n)
         if vals:
             self._touch_host()
             for k, v in enumerate(vals):
                 self._grid[k // n][k % n] = v
-        if err is not None:
-            raise err
+        raise err
 
     def setAij(self, i: int, j: int, aij):
         v = self._num(aij)
