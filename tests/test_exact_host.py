@@ -249,3 +249,96 @@ def test_prepare_phase2_agrees_between_array_and_list_inputs():
     assert bits_l >= max(X.hadamard_bits(grid), X.hadamard_bits(with_cost)) - 1
     w = X.weights_from_squares([0, 1, 2, 1 << 40, (1 << 200) + 1])
     assert w[0] == 0 and w[1] >= 0 and w[3] >= 256 * 20 and w[4] >= 256 * 100 and w == sorted(w)
+
+
+def _det(M):
+    """Exact determinant of a small integer matrix (fraction-free elimination)."""
+    M = [row[:] for row in M]
+    n, sign, prev = len(M), 1, 1
+    for k in range(n):
+        piv = next((i for i in range(k, n) if M[i][k] != 0), None)
+        if piv is None:
+            return 0
+        if piv != k:
+            M[k], M[piv] = M[piv], M[k]
+            sign = -sign
+        for i in range(k + 1, n):
+            for j in range(k + 1, n):
+                M[i][j] = (M[i][j] * M[k][k] - M[i][k] * M[k][j]) // prev
+        prev = M[k][k]
+    return sign * M[n - 1][n - 1]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_static_bound_covers_every_minor_of_irregular_matrices(seed):
+    """`hadamard_bits` (what sizes the ALLOCATED prime set) against brute force: every square minor of small matrices
+    with mixed signs, zero rows / columns and entries up to 8 bits stays below 2^bits."""
+    import itertools
+    rng = random.Random(70 + seed)
+    nr, nc = rng.randint(2, 4), rng.randint(2, 5)
+    span = rng.choice([1, 3, 9, 127])
+    G = [[0 if rng.random() < 0.3 else rng.randint(-span, span) for _ in range(nc)] for _ in range(nr)]
+    if seed % 2:
+        G[rng.randrange(nr)] = [0] * nc
+    bits = X.hadamard_bits(G)
+    assert X.hadamard_bits_np(np.array(G, dtype=np.int64)) >= bits
+    for k in range(1, min(nr, nc) + 1):
+        for rows in itertools.combinations(range(nr), k):
+            for cols in itertools.combinations(range(nc), k):
+                d = _det([[G[i][j] for j in cols] for i in rows])
+                assert abs(d).bit_length() <= bits, (rows, cols, d, bits)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_working_set_bound_covers_every_bareiss_integer_on_irregular_lps(seed):
+    """The WORKING prime set rests on: every tableau integer and D is, up to sign, a minor of the
+    uploaded matrix over the last pivot columns of the rows pivoted so far plus at most one more column, hence
+    log2|x| <= sum of those columns' weights (`column_weights`, 1/256 bit) + the heaviest other column.  Checked along
+    whole oracle solves of the irregular family (mixed signs, zero columns, slack columns, dependent rows),
+    phase 1 included, with the artificial problem's matrix as the uploaded one."""
+    rng = random.Random(500 + seed)
+    while True:                                  # integer data whose constructor and solve go through
+        c, A, b = problems.irregular_lp(rng, rng.randint(4, 9), rng.randint(5, 12))
+        if any(v.denominator != 1 for row in A + [b, c] for v in row):
+            continue
+        try:
+            O.simplex(c, A, b)
+        except (ValueError, IndexError, AssertionError):
+            continue
+        break
+    grid = O.make_grid(c, A, b)
+    m, n = O.shape(grid)
+    for i in range(m):
+        if grid[i][n] < 0:
+            O.row_scale(grid, i, Fraction(-1))
+    basis = [-1] * m
+    if not O.is_canonical(grid, basis):          # the artificial problem of simplex.py:47-60, as one uploaded matrix
+        missing = [i for i in range(m) if basis[i] == -1]
+        k = len(missing)
+        for i in range(m + 1):
+            row = grid[i]
+            row[n:] = [Fraction(0)] * k + [row[n]]
+        for j in range(n + k + 1):
+            grid[m][j] = Fraction(0)
+        for idx, i in enumerate(missing):
+            grid[i][n + idx] = Fraction(1)
+            basis[i] = n + idx
+            for j in range(n + k + 1):           # cost 1 on the artificial, priced out at once
+                if j != n + idx:
+                    grid[m][j] -= grid[i][j]
+        n += k
+    N = [[int(x) for x in row] for row in grid]
+    w = X.column_weights(N)
+    assert X.column_weights(np.array(N, dtype=np.int64)) == w or all(
+        abs(a - b_) <= 1 for a, b_ in zip(X.column_weights(np.array(N, dtype=np.int64)), w))
+    D, last, trace = 1, {}, []
+    O.solve(grid, basis, trace)
+    assert trace, "the walk made no pivot"
+    for r, cc, _ in trace:
+        D = O.bareiss_pivot(N, D, r, cc)
+        last[r] = cc
+        wsum = sum(w[j] for j in last.values())
+        assert abs(D).bit_length() - 1 <= wsum / 256 + 1e-9
+        heaviest = max(w[j] for j in range(n + 1))
+        top = max(abs(x).bit_length() for row in N for x in row)
+        assert top - 1 <= (wsum + heaviest) / 256 + 1e-9, (top, wsum, heaviest)
