@@ -72,3 +72,43 @@ def test_c_modp_pivot_matches_bareiss_integers():
         C.pivot_modp(R, r, cc, q, pow(D % q, -1, q))
         D = O.bareiss_pivot(N, D, r, cc)
         assert R.tolist() == [[x % q for x in row] for row in N]
+
+
+def _irregular_canonical(m, seed):
+    """Canonical float tableau with mixed signs, zeros, degenerate (b = 0) rows and non-integer data: slack basis, a
+    bounding row so that most draws are bounded, ties in the ratio test from repeated small integers."""
+    import random
+    rng = random.Random(seed)
+    T = np.zeros((m + 1, 2 * m + 1))
+    for i in range(m - 1):
+        for j in range(m):
+            if rng.random() < 0.6:
+                T[i, j] = rng.choice([-2, -1, 1, 1, 2, 3, 0.5, 1.25, 1 / 3])
+        T[i, 2 * m] = rng.choice([0, 0, 1, 2, 2, 4, 4.5])
+    T[m - 1, :m] = [rng.choice([1, 2, 3]) for _ in range(m)]
+    T[m - 1, 2 * m] = rng.choice([6, 10, 12.5])
+    T[:m, m:2 * m] = np.eye(m)
+    T[m, :m] = [rng.choice([-3, -2, -1, -1, 0, 1, -0.75]) for _ in range(m)]
+    return T
+
+
+@pytest.mark.parametrize("m,seed", [(6, 0), (9, 1), (14, 2), (20, 3), (33, 4), (48, 5), (64, 6), (20, 7), (33, 8)])
+def test_c_solve_bit_identical_on_irregular_and_tie_heavy_tableaux(m, seed):
+    """Degenerate pivots, ties, negative and fractional entries, the stuck counter: trace, status and every byte of
+    the final tableau equal the Python float oracle's (which tests/test_wild.py pins to the float-rebound reference)."""
+    for T0 in (_irregular_canonical(m, seed), problems.tie_heavy_grid(m - m % 2, 2, seed)):
+        mm = T0.shape[0] - 1
+        grid = [[float(x) for x in row] for row in T0]
+        pb = list(range(mm, 2 * mm))
+        ptrace = []
+        try:
+            O.solve(grid, pb, ptrace)
+            want_status = C.OPTIMAL
+        except O.UnboundedError:
+            want_status = C.UNBOUNDED
+        T = T0.copy()
+        basis = np.arange(mm, 2 * mm, dtype=np.int32)
+        st, npiv, trace = C.solve(T, basis)
+        assert st == want_status
+        assert trace.tolist() == [list(p) for p in ptrace] and basis.tolist() == pb
+        assert T.tobytes() == np.array(grid, dtype=np.float64).tobytes()
