@@ -1,0 +1,36 @@
+"""bench.py's reference arm (the CPU leg of the contract) at a small size, as the driver launches it: ONE JSON line on
+stdout with the contract's keys, nothing from any rank but rank 0, exit code 0.  The GPU arm needs a B200 and is
+exercised by the driver itself (profiles/*bench*.json are its lines)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(extra_env):
+    env = dict(os.environ, **extra_env)
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--m",
+                           "256", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
+
+
+def test_reference_arm_prints_one_contract_line():
+    p = _run({"RANK": "0", "WORLD_SIZE": "2"})
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "pivots_per_sec" and d["unit"] == "pivots/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 2 and d["steps"] == 2 and d["warmup"] == 1
+    assert d["value"] > 0 and abs(d["value"] * d["ms_per_step"] - 1e3) < 1e-6 * 1e3      # one pivot per step
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert d["config"]["workload"].startswith("C4 fp64 256x512") and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "256 x 512" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_is_silent_on_other_ranks():
+    p = _run({"RANK": "1", "WORLD_SIZE": "2"})
+    assert p.returncode == 0 and p.stdout.strip() == ""
