@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_longlong, c_size_t, c_uint32, c_ulonglong, c_void_p
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblps_b200.so")

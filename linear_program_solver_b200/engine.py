@@ -6,9 +6,8 @@ stream; every arithmetic step of the path happens inside the CUDA library.
 """
 from __future__ import annotations
 
-import ctypes
 from ctypes import byref, c_int, c_longlong, c_void_p, c_double
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 

@@ -17,7 +17,6 @@ from __future__ import annotations
 import math
 from ctypes import byref, c_int, c_longlong, c_size_t, c_void_p
 from fractions import Fraction
-from functools import lru_cache
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np

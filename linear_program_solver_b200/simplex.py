@@ -8,7 +8,7 @@ switch all run on the device and only the status, basis, marks and pivot trace c
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple, Union
+from typing import Dict, List, Tuple, Union
 
 import numpy as np
 

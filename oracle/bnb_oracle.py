@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import math
 from fractions import Fraction as F
-from typing import Callable, Dict, List, Optional
+from typing import Callable, Dict
 
 from . import lpsol_oracle as O
 

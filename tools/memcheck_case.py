@@ -4,7 +4,6 @@ tool is allowed (it is closed on this round's GPU pool, so no sanitizer record e
 fp64 and exact single tableaux (phase 1, drive-out, phase switch, phase 2, whole-tableau rules, row operations) and a
 batch of node LPs.  Results are checked against the oracle so that a silent corruption cannot pass as a clean run."""
 import os
-import random
 import sys
 from fractions import Fraction
 
