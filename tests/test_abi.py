@@ -58,3 +58,27 @@ def test_no_cpu_fallback_and_no_oracle_import_in_the_product():
         pytest.skip("a GPU is present: the device path works here")
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
     assert "LOUD" in out.stdout, out.stdout + out.stderr
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: include/lps_b200.h must compile as C99 (no C++-isms, no torch types) and a C caller must
+    link against the shared library and reach it.  Only entry points that need no GPU are called."""
+    from linear_program_solver_b200 import _native
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "lps_b200.h"\n'
+        "int main(void) {\n"
+        "    lps_handle *h = NULL;\n"
+        "    int rc = lps_pivot(h, 0, 0);                 /* a null handle is refused, not dereferenced */\n"
+        '    printf("%d %d %d %s\\n", lps_version(), (int)lps_grid_ld(4000), rc < 0, lps_last_error() ? "msg" : "null");\n'
+        "    return 0;\n}\n")
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_native.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+           "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(_native.LIB_PATH), "-Wl,-rpath," + libdir]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    version, ld, refused, msg = out.stdout.split()
+    assert int(version) >= 100 and int(ld) % 16 == 0 and refused == "1" and msg == "msg"
