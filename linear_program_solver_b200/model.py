@@ -71,7 +71,7 @@ class LinExpr:
         # a scalar compares equal to a constant expression (linprog.py:64-68)
         if isinstance(other, LinExpr):
             return self.m == other.m and self.c == other.c
-        return not self.m and self.c == Fraction(other)
+        return self.c == Fraction(other) and not self.m      # the scalar is coerced FIRST: a bad one raises even then
 
     __hash__ = None
 

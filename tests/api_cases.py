@@ -59,6 +59,12 @@ f = LinExpr('2/4', 'w', 0.5, 'w')
     ("linexpr_ctor_errors", "", [
         "LinExpr(1, 2)", "LinExpr(1, '3x')", "LinExpr(1, 'x y')", "LinExpr(1, '')", "LinExpr('a', 'x')",
         "LinExpr(1, '_ok9')", "LinExpr(1, 'x', 2, None)"]),
+    # __eq__ coerces a scalar BEFORE looking at the variables (linprog.py:64-68): a bad scalar raises, it is not "unequal"
+    ("linexpr_eq_coerces_first", """
+a = LinExpr(2, 'x', 1)
+b = LinExpr(3)
+""", ["a == 'abc'", "a == None", "a == [1]", "b == 'abc'", "b == '6/2'", "b == 3.0", "a == 1", "a != 1", "b != 3",
+      "a == LinExpr(2, 'x', 1)", "a.constraintLeq(1) == 1", "LinVar('x') == 'x'"]),
     ("linexpr_str_signs", """
 a = LinExpr(-1, 'b', 1, 'a', -3)
 b = LinExpr(-2, 'a', -5, 'c')

@@ -98,6 +98,12 @@ def model_program(rng):
              "str(e + f)", "str(e - f)", "repr(-e)", "e.copy() == e",
              f"e.evaluate({gen_vars(rng)})", f"str(e.substitute({gen_vars(rng)}))",
              f"repr(f.substitute({gen_vars(rng)}))"]
+    # in-place arithmetic keeps the identity of the left operand (linprog.py:123-147); comparison with plain numbers
+    lines += [f"g = e.copy(); g_id = id(g); g {rng.choice(['+=', '-='])} {gen_expr(rng, 2)}",
+              f"h = f.copy(); h {rng.choice(['+=', '-='])} {src_num(rnum(rng))}"]
+    exprs += ["str(g)", "id(g) == g_id", "repr(h)", f"e == {src_num(rnum(rng))}", "e == e.getConstant()",
+              "(e - e) == 0", "str(e.copy() - e)", f"LinCon(e, {rng.choice(['<=', '>=', '==', '<', '=', 'le'])!r}, f)",
+              "e.evaluate({})", "e.substitute({}) == e"]
     comp = rng.choice(["constrantEq", "constraintLeq", "constraintGeq"])
     exprs += [f"str(e.{comp}(f))", f"repr(e.{comp}(f))", f"str(e.{comp}({src_num(rnum(rng))}))",
               f"str(e.{comp}(f).simplify())", f"repr(e.{comp}(f).reverse())",
