@@ -191,6 +191,11 @@ def tableau_program(rng):
             exprs.append(f"t.toggleVarMark({cc()})")
         elif k == 19:
             exprs.append("t.copy() == t")
+            exprs.append(f"(lambda u: (u.{rng.choice(['setCj(0, 99)', 'setBi(0, 99)', 'setAij(0, 0, 99)', 'setZ(99)', "setVarName(0, 'other')", 'toggleVarMark(0)', 'addVar()', 'addCon()'])}, u == t, t == u))(t.copy())[1:]")
+            exprs.append(f"(t == {rng.choice(['5', 'None', '[]', 'T(1, 1)'])}, t != t.copy())")
+            exprs.append(f"t.setVarNames({[rng.choice(NAMES) for _ in range(rng.randint(0, n + 1))]!r})")
+            exprs.append(f"t.setVarMarks({[rng.random() < 0.5 for _ in range(rng.randint(0, n + 1))]!r})")
+            exprs.append("(t.getVarNames(), t.getVarMarks())")
             exprs.append("T(1, 1).loadJson(t.saveJson())")
         elif k == 20:
             exprs.append(f"t.getAij({rr()}, {cc()})")
@@ -213,6 +218,10 @@ def tableau_program(rng):
               f"t.printText(labels={rng.random() < 0.5}, rownums={rng.random() < 0.5}, spacing={rng.randint(0, 4)}, "
               f"left={rng.random() < 0.5})", f"t.printGrid(labels={rng.random() < 0.5}, rownums={rng.random() < 0.5}, "
               f"mpre={mpre!r}, msuf={msuf!r})", "__import__('re').sub('0x[0-9a-f]+', '0x', repr(t))"]
+    # file round trip (tableau.py:312-320): the bytes on disk and what comes back
+    exprs.append("(lambda p: (t.saveFile(p), open(p).read(), (lambda u: (u.loadFile(p), u == t, u.saveJson() == t.saveJson()))(T(1, 1))[1:], "
+                 "__import__('os').remove(p))[1:3])(__import__('tempfile').mktemp(suffix='.json'))")
+    exprs.append("T(1, 1).loadFile('/nonexistent/dir/x.json')")
     exprs += ["t.saveJson()", "t.printCSV()", "t.printLatex()", "t.printText()", "t.printGrid()", "str(t)",
               "t.getVarNames()", "t.getVarMarks()", "t.printCSV(labels=False, rownums=True)",
               "t.printText(rownums=True, spacing=1, left=True)"]
