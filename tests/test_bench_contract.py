@@ -34,3 +34,17 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_is_silent_on_other_ranks():
     p = _run({"RANK": "1", "WORLD_SIZE": "2"})
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_algorithmic_bytes_are_the_surveys_figures():
+    """16(m+1)(n+1) + 8(m+1) + 8(n+1) bytes per fp64 pivot -- 128.1 MB at C2, 34.36 GB at C4
+    (5.26 ms at the measured 6531.9 GB/s: the 190 pivots/s ceiling the bench's roofline fraction is taken against)."""
+    code = ("import bench, os\n"
+            "os.write(bench._REAL_STDOUT, ('%d %d' % (bench.algorithmic_bytes(2000, 4000), "
+            "bench.algorithmic_bytes(32768, 65536))).encode())\n")
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-1500:]
+    c2, c4 = map(int, p.stdout.split())
+    assert c2 == 16 * 2001 * 4001 + 8 * 2001 + 8 * 4001 and round(c2 / 1e6, 1) == 128.1
+    assert c4 == 16 * 32769 * 65537 + 8 * 32769 + 8 * 65537 and round(c4 / 1e9, 2) == 34.36
+    assert 189.0 < 6531.9e9 / c4 < 191.0
