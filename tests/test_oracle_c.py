@@ -112,3 +112,17 @@ def test_c_solve_bit_identical_on_irregular_and_tie_heavy_tableaux(m, seed):
         assert st == want_status
         assert trace.tolist() == [list(p) for p in ptrace] and basis.tolist() == pb
         assert T.tobytes() == np.array(grid, dtype=np.float64).tobytes()
+
+
+@pytest.mark.parametrize("m,row0,ml,seed,lo,hi", [(16, 0, 16, 0, 1, 9), (31, 10, 11, 3, 1, 9), (64, 48, 16, 1, 1, 127),
+                                                  (40, 0, 13, 7, 2, 5)])
+def test_c_fill_equals_the_python_statement_of_the_hashed_family(m, row0, ml, seed, lo, hi):
+    """The synthetic C4 input exists three times -- `k_fill_dense_f64` on the device, `orc_fill_dense_f64` for the CPU
+    arm of bench.py, `problems.hashed_dense_grid` in Python -- and every rank generates only its own rows: the C and
+    the Python statement agree cell for cell on whole tableaux and on row slabs (the device one is compared with the
+    Python one in tests/test_api_fp64_gpu.py)."""
+    T = np.full((ml + 1, 2 * m + 1 + 3), -7.0)                  # padded rows: the fill must respect the leading dimension
+    C.fill_dense(T, m, row0, seed, lo, hi)
+    want = problems.hashed_dense_grid(m, seed, lo, hi, row0, ml).astype(np.float64)
+    assert T[:, :2 * m + 1].tobytes() == np.ascontiguousarray(want).tobytes()
+    assert (T[:, 2 * m + 1:] == -7.0).all() or (T[:, 2 * m + 1:] == 0.0).all()
