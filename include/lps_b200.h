@@ -180,6 +180,22 @@ int lps_p2p_block(lps_handle *h, void **block);
 int lps_p2p_attach_local(lps_handle *h, long long row0, long long m_total, int rank, int nranks,
                          void *const *blocks);
 int lps_step_update(lps_handle *h);
+/* Pivots in blocks (the loop lps_solve runs in fp64 mode; csrc/lps_f64_blk.cuh).  One lps_step_block = a look-ahead
+ * panel that DECIDES up to lps_block_size(h) consecutive pivots of Simplex.solve (simplex.py:110-148: pricing, ratio
+ * test, stuck counter, rule switch, Simplex._pivot's bookkeeping :192-197) from O(m+n) numbers -- the objective row
+ * and right-hand side kept current, the entering column and leaving row gathered from the stale grid and corrected
+ * with the block's earlier pivots -- followed by ONE pass over the grid that applies all of them to every cell in the
+ * reference's order and rounding (tableau.py:295-308).  Results are bit-identical to pivot-by-pivot updates; the grid
+ * is read and written once per block instead of once per pivot.  On a row-sharded handle (after lps_p2p_attach) the
+ * panel does the per-pivot argmin all-reduce and pivot-row broadcast with peer stores, like lps_step_select.
+ * lps_set_block_size: 1..16 pivots per block, 0 = lps_solve falls back to the rank-1 loop (default 16, or the
+ * environment variable LPS_F64_BLOCK). */
+int lps_step_block(lps_handle *h);
+int lps_block_size(lps_handle *h);
+int lps_set_block_size(lps_handle *h, int k);
+/* Launch shape of the panel (tuning / tests): 1 = one CTA of 1024 threads, >= 2 = that many CTAs of 256 threads
+ * (at most one per SM).  The default follows the size of the tableau. */
+int lps_set_panel_ctas(lps_handle *h, int ctas);
 int lps_solve_poll(lps_handle *h, int *status, long long *npiv);
 int lps_solve_end(lps_handle *h, int *basis, int *marks, int *trace, long long trace_cap,
                   long long *npiv);

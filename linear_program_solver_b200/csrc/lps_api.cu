@@ -92,6 +92,25 @@ static void plan(lps_handle* h) {
         h->sel_threads = kThreads;
         h->sel_blocks = std::max(1, std::min(std::max((h->m + kThreads - 1) / kThreads, (int)(h->ld / (8 * kThreads))), 148));
     }
+    // Pivots in blocks (lps_f64_blk.cuh).  The panel is a persistent grid that synchronises through memory: never
+    // more CTAs than SMs.  Small tableaux: one CTA of 1024 threads (barriers are __syncthreads).
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+    if (h->m <= 8 * kSelMaxThreads && h->ld <= 16 * kSelMaxThreads) { h->pan_blocks = 1; h->pan_threads = kSelMaxThreads; }
+    else {
+        h->pan_threads = kThreads;
+        h->pan_blocks = std::max(2, std::min(std::max((h->m + kThreads - 1) / kThreads, (int)((h->ld / 2 + kThreads - 1) / kThreads)), std::min(sms, 256)));
+    }
+    h->sel_blocks = std::min(h->sel_blocks, sms);
+    // fused update: 512-column tiles, as many rows per CTA as still leave a few waves of CTAs
+    const size_t blk_chunks = (h->ld + kBlkCW - 1) / kBlkCW;
+    h->blk_rows = 8;
+    for (int rb = kMaxRowBlock; rb >= 8; rb /= 2)
+        if (blk_chunks * (((size_t)h->m + 1 + rb - 1) / rb) >= (size_t)sms * 4) { h->blk_rows = rb; break; }
+    h->blk_k = kBlkMax;
+    if (const char* e = getenv("LPS_F64_BLOCK")) { const int v = atoi(e); if (v >= 0 && v <= kBlkMax) h->blk_k = v; }
+    if (const char* e = getenv("LPS_F64_BLOCK_ROWS")) { const int v = atoi(e); if (v >= 8 && v <= kMaxRowBlock && v % 8 == 0) h->blk_rows = v; }
+    if (const char* e = getenv("LPS_F64_PANEL_CTAS")) { const int v = atoi(e); if (v >= 2 && v <= sms && h->pan_blocks > 1) h->pan_blocks = v; }
 }
 
 extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* stream, lps_handle** out) {
@@ -119,6 +138,11 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
         CU(cudaMemsetAsync(h->T, 0, grid_bytes, h->stream));
     }
     plan(h);
+    {   // the fused update stages up to 16 pivot rows and columns in shared memory: beyond the 48 KB default
+        const size_t most = blk_update_smem(kBlkMax, kMaxRowBlock);
+        CU(cudaFuncSetAttribute(k_blk_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+        CU(cudaFuncSetAttribute(k_blk_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+    }
     const size_t ucol_n = ((size_t)m + 1 + kMaxRowBlock - 1) / kMaxRowBlock * kMaxRowBlock + kMaxRowBlock;
     const int maxchunks = (int)((h->ld + kNarrowChunk - 1) / kNarrowChunk);
     {   // the small buffers: one allocation (lps_internal.h, Slab)
@@ -134,17 +158,38 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
         sl.add(&h->marks, (size_t)n);
         h->cand_stride = lps_cand_bytes(n);
         sl.add(&h->cand_send, h->cand_stride);           // replaced, never freed, when lps_set_shard passes the caller's slots
+        // panel of the blocked pivot loop (lps_f64_blk.cuh)
+        h->blk.upitch = ucol_n;
+        sl.add(&h->blk.U, (size_t)kBlkMax * ucol_n);
+        sl.add(&h->blk.O[0], h->ld);
+        sl.add(&h->blk.O[1], h->ld);
+        sl.add(&h->blk.B[0], ucol_n);
+        sl.add(&h->blk.B[1], ucol_n);
+        sl.add(&h->blk.R, (size_t)kBlkMax);
+        sl.add(&h->blk.C, (size_t)kBlkMax);
+        sl.add(&h->blk.hdr, (size_t)4);
+        sl.add(&h->blk.p_val, (size_t)256);
+        sl.add(&h->blk.p_idx, (size_t)256);
+        sl.add(&h->blk.p_bidx, (size_t)256);
+        sl.add(&h->blk.rblk, (size_t)256);
+        sl.add(&h->blk.sync, (size_t)1);
         CU(sl.commit(&h->slab));
     }
+    CU(cudaMemsetAsync(h->blk.U, 0, (size_t)kBlkMax * ucol_n * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->blk.hdr, 0, 4 * sizeof(int), h->stream));
+    CU(cudaMemsetAsync(h->blk.sync, 0, sizeof(BlkSync), h->stream));
     CU(cudaMemsetAsync(h->ucol, 0, ucol_n * sizeof(double), h->stream));
     CU(cudaMemsetAsync(h->cand_send, 0, h->cand_stride, h->stream));
     h->cand_all = h->cand_send;
     h->own_cand = false;
     {
-        const size_t xb = sizeof(XchgBlock) + h->ld * sizeof(double);
+        // exchange block: headers and flags, then kBlkMax pivot rows (row 0 doubles as the rank-1 path's vrow)
+        const size_t xb = sizeof(XchgBlock) + (size_t)kBlkMax * h->ld * sizeof(double);
         CU(cudaMalloc(&h->xchg, xb));
         CU(cudaMemsetAsync(h->xchg, 0, xb, h->stream));
         CU(cudaMemcpyAsync(h->d_peers, &h->xchg, sizeof(XchgBlock*), cudaMemcpyHostToDevice, h->stream));
+        h->xchg_bytes = xb;
+        h->blk.V = xchg_vrow(h->xchg);
     }
     CU(cudaMemsetAsync(h->st, 0, sizeof(SolveState), h->stream));
     static_assert(sizeof(SolveState) <= 256, "pinned state blocks are 256 bytes");
@@ -284,9 +329,11 @@ static int launch_price(lps_handle* h) {
     else k_price_f64<kNarrowChunk><<<h->nchunks, kThreads, 0, h->stream>>>(grid_of(h), partials_of(h));
     h->launches_all++;
     CU(cudaGetLastError());
+    h->pp_valid = true;
     return LPS_OK;
 }
 static int launch_select(lps_handle* h) {
+    if (!h->pp_valid) TRY(launch_price(h));   // the blocked loop does not maintain the rank-1 path's pricing partials
     SelectArgs a;
     a.g = grid_of(h); a.pp = partials_of(h); a.nchunks = h->nchunks; a.st = h->st; a.ucol = h->ucol;
     a.blk = h->sel_blk; a.cand = (CandHeader*)h->cand_send;
@@ -319,6 +366,50 @@ static int launch_update(lps_handle* h, int commit) {
     CU(cudaGetLastError());
     return LPS_OK;
 }
+// ---- pivots in blocks (lps_f64_blk.cuh) ----------------------------------------------------------
+static int blk_sync_panel(lps_handle* h) {
+    // O / B / pricing partials of the panel from the grid (after anything but the blocked loop touched it)
+    if (h->blk_valid) return LPS_OK;
+    CU(cudaMemsetAsync(h->blk.sync, 0, sizeof(BlkSync), h->stream));
+    k_blk_init<<<h->pan_blocks, h->pan_threads, 0, h->stream>>>(grid_of(h), h->blk);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    h->blk_valid = true;
+    return LPS_OK;
+}
+static int launch_panel(lps_handle* h) {
+    BlkPanelArgs a;
+    a.g = grid_of(h); a.p = h->blk; a.st = h->st; a.kmax = h->blk_k;
+    a.xchg = h->xchg; a.peers = h->d_peers; a.rank = h->rank; a.nranks = h->use_xchg ? h->nranks : 1;
+    a.basis = h->basis; a.marks = h->use_marks ? h->marks : nullptr; a.trace = h->trace; a.trace_cap = h->trace_cap;
+    k_blk_panel<<<h->pan_blocks, h->pan_threads, 0, h->stream>>>(a);
+    h->launches_all++;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+static int launch_blk_update(lps_handle* h) {
+    BlkUpdateArgs a;
+    a.g = grid_of(h); a.p = h->blk; a.rows_per_cta = h->blk_rows; a.kcap = h->blk_k;
+    const size_t smem = blk_update_smem(h->blk_k, h->blk_rows);
+    const int which = h->stream_hint ? 1 : 0;
+    dim3 grid((unsigned)((h->ld + kBlkCW - 1) / kBlkCW), (unsigned)((h->m + 1 + h->blk_rows - 1) / h->blk_rows));
+    const bool timed = h->prof && h->ev_used + 2 <= h->ev.size();
+    if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
+    if (which) k_blk_update<true><<<grid, kThreads, smem, h->stream>>>(a);
+    else k_blk_update<false><<<grid, kThreads, smem, h->stream>>>(a);
+    if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
+    h->launches_update++;
+    h->launches_all++;
+    h->pp_valid = false;
+    CU(cudaGetLastError());
+    return LPS_OK;
+}
+static int launch_block(lps_handle* h) {
+    TRY(blk_sync_panel(h));
+    TRY(launch_panel(h));
+    return launch_blk_update(h);
+}
+
 static int read_state(lps_handle* h) {
     CU(cudaMemcpyAsync(h->st_host, h->st, sizeof(SolveState), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -583,7 +674,8 @@ extern "C" int lps_solve_begin(lps_handle* h, long long max_pivots, const int* b
     s.max_pivots = max_pivots; s.pending_zcheck = 0; s.ticket = 0; s.dry_run = 0; s.last_r = -1; s.last_c = -1;
     s.xseq = h->st_host->xseq;
     TRY(write_state(h, s));
-    TRY(launch_price(h));
+    h->pp_valid = false;              // both loops re-read the objective row on their first step
+    h->blk_valid = false;
     h->solving = true;
     return LPS_OK;
 }
@@ -598,6 +690,42 @@ extern "C" int lps_step_update(lps_handle* h) {
     NEED_MODE(h, 0);
     if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
     return launch_update(h, 1);
+}
+// One block of the blocked loop: the panel decides up to lps_block_size(h) pivots (fewer at optimality, at the end of
+// a pivot prefix, ...), the fused update applies them.  With the peer-store exchange attached the panel does the
+// per-pivot argmin all-reduce and pivot-row broadcast itself.
+extern "C" int lps_step_block(lps_handle* h) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (!h->solving) return fail(LPS_E_STATE, "no solve in progress");
+    if (h->blk_k < 1) return fail(LPS_E_STATE, "the blocked loop is switched off (LPS_F64_BLOCK=0)");
+    if (h->nranks > 1 && !h->use_xchg) return fail(LPS_E_STATE, "blocks on a sharded handle need the peer-store exchange (lps_p2p_attach)");
+    return launch_block(h);
+}
+extern "C" int lps_block_size(lps_handle* h) { return (h && h->mode == 0) ? h->blk_k : 0; }
+extern "C" int lps_set_block_size(lps_handle* h, int k) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (k < 0 || k > kBlkMax) return fail(LPS_E_INVALID, "block size %d outside 0..%d", k, kBlkMax);
+    if (h->solving) return fail(LPS_E_STATE, "solve in progress");
+    h->blk_k = k;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    return LPS_OK;
+}
+// Launch shape of the look-ahead panel: 1 = one CTA of 1024 threads (barriers are __syncthreads), >= 2 = that many
+// CTAs of 256 threads synchronising through memory (never more than SMs: they spin on each other).
+extern "C" int lps_set_panel_ctas(lps_handle* h, int ctas) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (h->solving) return fail(LPS_E_STATE, "solve in progress");
+    int sms = 148;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    if (ctas < 1 || ctas > std::min(sms, 256)) return fail(LPS_E_INVALID, "panel CTAs %d outside 1..%d", ctas, std::min(sms, 256));
+    h->pan_blocks = ctas;
+    h->pan_threads = (ctas == 1) ? kSelMaxThreads : kThreads;
+    h->blk_valid = false;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    return LPS_OK;
 }
 extern "C" int lps_solve_poll(lps_handle* h, int* status, long long* npiv) {
     USE(h);
@@ -634,15 +762,23 @@ static int ensure_burst_graph(lps_handle* h, long long burst) {
     mix((unsigned long long)(uintptr_t)h->basis); mix(h->use_xchg ? 1 : 0); mix((unsigned long long)h->chunk);
     mix((unsigned long long)h->rows_per_cta); mix((unsigned long long)h->sel_blocks); mix((unsigned long long)h->sel_threads);
     mix((unsigned long long)(uintptr_t)h->cand_send); mix((unsigned long long)(uintptr_t)h->cand_all); mix((unsigned long long)burst);
+    mix((unsigned long long)h->blk_k); mix((unsigned long long)h->blk_rows); mix((unsigned long long)h->pan_blocks);
+    mix((unsigned long long)h->n); mix((unsigned long long)(uintptr_t)h->T);
     if (h->gexec && h->gsig == sig && h->gburst == burst) return LPS_OK;
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    // the lazy re-reads of the objective row stay outside the captured burst
+    if (h->blk_k >= 1) TRY(blk_sync_panel(h));
+    else if (!h->pp_valid) TRY(launch_price(h));
     const long long la = h->launches_all, lu = h->launches_update;
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     int rc = LPS_OK;
     for (long long k = 0; k < burst && rc == LPS_OK; ++k) {
-        rc = launch_select(h);
-        if (rc == LPS_OK) rc = launch_update(h, 1);
+        if (h->blk_k >= 1) rc = launch_block(h);
+        else {
+            rc = launch_select(h);
+            if (rc == LPS_OK) rc = launch_update(h, 1);
+        }
     }
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
     h->launches_all = la; h->launches_update = lu;               // counted when the graph is launched
@@ -661,16 +797,41 @@ extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* m
     if (!basis) return fail(LPS_E_INVALID, "null basis");
     if (h->mode == 1) return lpsx_solve(h, max_pivots, basis, marks, trace, trace_cap, npiv);
     TRY(lps_solve_begin(h, max_pivots, basis, marks, trace ? trace_cap : 0));
-    // pivots enqueued per host check: about 2 ms of device work, between 4 and 256; a pivot
-    // prefix never enqueues more (select, update) pairs than it may commit
-    const double est_us = std::max(4.0, (double)(h->m + 1) * (double)h->ld * 16.0 / 5.0e6);
+    const double est_us = std::max(4.0, (double)(h->m + 1) * (double)h->ld * 16.0 / 5.0e6);   // one pass over the grid
+    // Launch-bound sizes: a burst is captured once as a CUDA graph and replayed.  Launches enqueued past optimality or
+    // past the pivot prefix are no-ops on the device (the kernels test the state first), so whole bursts are always
+    // safe.  Per-launch profiling events need the plain launches.
+    const bool graphed = !h->prof && est_us < 200.0;
+    if (h->blk_k >= 1) {
+        // blocked loop: one panel launch decides up to blk_k pivots, one pass over the grid applies them; about 2 ms of
+        // device work between two looks at the state
+        const double blk_us = est_us + 8.0 * h->blk_k;
+        const long long burst = (long long)std::max(1.0, std::min(64.0, 2000.0 / blk_us));
+        const long long gburst = std::min<long long>(burst, 8);
+        if (graphed) TRY(ensure_burst_graph(h, gburst));
+        long long enq_blocks = 0;
+        for (;;) {
+            if (graphed) {
+                for (long long k = 0; k < burst; k += gburst) CU(cudaGraphLaunch(h->gexec, h->stream));
+                const long long done = (burst + gburst - 1) / gburst * gburst;
+                h->launches_all += 2 * done;
+                h->launches_update += done;
+                enq_blocks += done;
+            } else {
+                long long now = burst;
+                if (max_pivots >= 0) now = std::max<long long>(1, std::min(burst, (max_pivots - enq_blocks * h->blk_k + h->blk_k - 1) / h->blk_k));
+                for (long long k = 0; k < now; ++k) TRY(launch_block(h));
+                enq_blocks += now;
+            }
+            TRY(read_state(h));
+            if (h->st_host->status != LPS_OK) break;
+        }
+        return lps_solve_end(h, basis, marks, trace, trace_cap, npiv);
+    }
+    // rank-1 loop (LPS_F64_BLOCK=0): pivots enqueued per host check: about 2 ms of device work, between 4 and 256; a
+    // pivot prefix never enqueues more (select, update) pairs than it may commit
     const long long burst = (long long)std::max(4.0, std::min(256.0, 2000.0 / est_us));
     long long enqueued = 0;
-    // Launch-bound sizes (a pivot is tens of microseconds of device work, two launches cost about as much on the
-    // host): the burst is captured once as a CUDA graph and replayed.  Pairs enqueued past optimality or past the
-    // pivot prefix are no-ops on the device (k_select_f64 / k_update_f64 test the state first), so whole bursts
-    // are always safe.  Per-launch profiling events need the plain launches.
-    const bool graphed = !h->prof && est_us < 200.0;
     const long long gburst = std::min<long long>(burst, 32);   // short graphs: capture stays cheap next to a short solve
     if (graphed) TRY(ensure_burst_graph(h, gburst));
     for (;;) {
@@ -712,6 +873,18 @@ extern "C" int lps_p2p_export(lps_handle* h, unsigned char* ipc_handle64) {
 
 static int attach_blocks(lps_handle* h, long long row0, long long m_total, int rank, int nranks, const std::vector<XchgBlock*>& peers) {
     CU(cudaMemcpy(h->d_peers, peers.data(), (size_t)nranks * sizeof(XchgBlock*), cudaMemcpyHostToDevice));
+    // The peer-store protocol counts select rounds from the same number on every rank, over zeroed headers: a
+    // (pooled) handle that already ran pivots or dry-run selects starts over.  The callers put a cross-rank barrier
+    // between attaching and the first pivot (sharded.py: the all-reduce of the "mapped" flags), so no peer can
+    // have stored into this block yet.
+    TRY(read_state(h));
+    SolveState s = *h->st_host;
+    s.xseq = 0; s.ticket = 0; s.ticket2 = 0;
+    TRY(write_state(h, s));
+    CU(cudaMemsetAsync(h->xchg, 0, sizeof(XchgBlock), h->stream));
+    CU(cudaMemsetAsync(h->blk.sync, 0, sizeof(BlkSync), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     h->row0 = row0; h->m_total = m_total; h->rank = rank; h->nranks = nranks;
     h->use_xchg = (nranks > 1);          // one rank: k_select writes the normalised row itself, no exchange
     CU(cudaFree(h->basis));

@@ -233,7 +233,16 @@ __global__ void __launch_bounds__(kSelMaxThreads, 1) k_select_f64(SelectArgs a) 
     // stuck counter and rule (simplex.py:123,132-137), recomputed identically by every block
     int rule = st->rule;
     long long stuck = st->stuck;
-    if (st->pending_zcheck) stuck = (g.T[(size_t)g.m * g.ld + g.n] == st->z_entry_cell) ? stuck + 1 : 0;
+    if (st->pending_zcheck) {
+        const double corner = g.T[(size_t)g.m * g.ld + g.n];
+        // simplex.py:133 `assert z <= obj_val`: the objective (minus the corner cell) may not rise above its value at
+        // entry; a float run can trip this on rounding noise, and the reference then stops with the pivot applied
+        if (!(corner >= st->z_entry_cell)) {
+            if (blockIdx.x == 0 && threadIdx.x == 0 && !dry) st->status = LPS_OBJ_INCREASED;
+            if (!dry) return;
+        }
+        stuck = (corner == st->z_entry_cell) ? stuck + 1 : 0;
+    }
     if (rule == LPS_RULE_DANTZIG && !(stuck < g.m_total + (long long)g.n)) rule = LPS_RULE_BLAND;
 
     // entering column

@@ -1,0 +1,540 @@
+// fp64 simplex pivots in BLOCKS: a look-ahead panel decides up to K consecutive pivots, then ONE pass over the
+// tableau applies all of them.
+//
+// Why: one pivot of the reference (tableau.py:295-308) is a rank-1 update T <- T - u (x) v that reads and writes
+// every cell -- 16 (m+1)(n+1) bytes of HBM traffic for 2 flops per cell.  k_update_f64 already moves those bytes at
+// the copy peak, so the only way to more pivots per second is fewer bytes per pivot.  The decisions of the NEXT
+// pivots do not need the updated tableau, only O(m+n) numbers of it:
+//
+//   * the objective row and the right-hand side column after each pivot (kept current in the panel: O, B),
+//   * column c_l (the entering column) and row r_l (the leaving row) of the tableau as it WOULD be after the
+//     first l pivots of the block: gathered from the stale tableau and corrected with the l rank-1 terms decided
+//     so far (U[lp] = column snapshot, V[lp] = normalised pivot row of pivot lp).
+//
+// Every corrected number goes through exactly the operations the reference applies to that cell, in the same order
+// (product rounded, then sum rounded; a zero multiplier leaves the cell alone, tableau.py:272/:285; the pivot row is
+// REPLACED by its normalised copy, tableau.py:262-267), so panel and tableau stay bit-identical to a run that
+// updates the whole tableau after every pivot.  k_blk_update then applies the K pivots to every cell with the same
+// per-cell sequence: one read and one write of the tableau per K pivots.
+//
+//   k_blk_init    O <- objective row, B <- right-hand side, pricing partials (at lps_solve_begin)
+//   k_blk_panel   persistent grid (<= one CTA per SM), two grid-wide synchronisations per pivot:
+//                   A  pricing from the partials (Dantzig simplex.py:262-267 / Bland :228-232), stuck counter and
+//                      rule switch (simplex.py:118-137), redundantly in every CTA
+//                   B  column c gathered + corrected -> U[l], ratio test (simplex.py:272-279) over the CTA's rows
+//                      -> the CTA that arrives last reduces the partials and -- row-sharded tableaux -- exchanges the
+//                      64-byte candidate header with every peer GPU by peer stores (the argmin all-reduce)
+//                   C  the owner of the leaving row gathers + corrects + normalises it -> V[l] (stored into every
+//                      peer GPU's panel: the pivot-row broadcast), objective row and right-hand side move on,
+//                      pricing partials of the new objective row, basis / marks / trace are committed
+//   k_blk_update  T <- T with the block's pivots applied, TMA-staged panel tiles, 128-bit streaming accesses
+#pragma once
+#include "lps_f64.cuh"
+
+namespace lps {
+
+constexpr int kBlkMax = 16;   // pivots per block (upper bound; the fp64 pipe saturates near 22 at the HBM rate)
+constexpr int kBlkCW = 512;   // columns per update tile: 256 threads x one double2
+constexpr int kBlkRU = 8;     // rows in flight per thread
+
+struct alignas(128) BlkSync {        // zeroed at lps_solve_begin; counters only ever grow
+    unsigned long long arrive1;      // phase B arrivals: the CTA that makes it a multiple of the grid size decides
+    unsigned long long pad1[15];
+    unsigned long long arrive2;      // end-of-pivot barrier
+    unsigned long long pad2[15];
+    unsigned long long dec_seq;      // decision of select round `seq` published
+    long long dec_row;
+    int dec_w, dec_pad;
+    unsigned long long pad3[13];
+    unsigned long long ticket2;      // V-row slices finished (owner of the leaving row)
+    unsigned long long exit_ticket;
+    unsigned long long pad4[14];
+};
+
+struct BlkPanel {
+    double* U;               // kBlkMax x upitch: U[l][i] = cell (i, c_l) just before pivot l (i = m: objective row)
+    size_t upitch;
+    double* V;               // kBlkMax x ld: normalised pivot rows (lives in the exchange block: peers store into it)
+    double* O[2];            // objective row, ping-pong by pivot parity (ld each)
+    double* B[2];            // right-hand side of the local rows, ping-pong (upitch each)
+    int* R;                  // kBlkMax: GLOBAL leaving row of pivot l
+    int* C;                  // kBlkMax: entering column
+    int* hdr;                // [0] pivots decided by the last panel launch, [1] current parity of O / B
+    double* p_val;           // pricing partials, one per panel CTA
+    int* p_idx;
+    int* p_bidx;
+    ArgMinF64* rblk;         // ratio-test partials, one per panel CTA
+    BlkSync* sync;
+};
+
+__device__ __forceinline__ double2 ldcg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void stcg2(double* p, double2 v) { __stcg(reinterpret_cast<double2*>(p), v); }
+// one cell through one pivot of the block: u = the cell of its row in the pivot column, v = the cell of its column
+// in the normalised pivot row (tableau.py:269-280: row += (-u) * pivot row, skipped when u == 0)
+__device__ __forceinline__ double blk_apply(double x, double u, double v) {
+    return (u == 0.0) ? x : __dadd_rn(x, __dmul_rn(-u, v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// init: panel state from the tableau
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSelMaxThreads) k_blk_init(F64Grid g, BlkPanel P) {
+    __shared__ ArgMinF64 s_arg[32];
+    __shared__ int s_int[32];
+    const int nt = (int)blockDim.x, G = (int)gridDim.x;
+    const double* obj = g.T + (size_t)g.m * g.ld;
+    ArgMinF64 best{0.0, INT_MAX};
+    int first_neg = INT_MAX;
+    for (int j = blockIdx.x * nt + threadIdx.x; j < (int)g.ld; j += G * nt) {
+        const double v = obj[j];
+        P.O[0][j] = v;
+        price_consider(v, j, g.n, best, first_neg);
+    }
+    for (int i = blockIdx.x * nt + threadIdx.x; i < g.m; i += G * nt) P.B[0][i] = g.T[(size_t)i * g.ld + g.n];
+    best = block_argmin(best, s_arg);
+    first_neg = block_min_int(first_neg, s_int);
+    if (threadIdx.x == 0) {
+        P.p_val[blockIdx.x] = best.key;
+        P.p_idx[blockIdx.x] = best.idx;
+        P.p_bidx[blockIdx.x] = first_neg;
+        if (blockIdx.x == 0) { P.hdr[0] = 0; P.hdr[1] = 0; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// panel: up to kmax pivot decisions in one launch
+// ------------------------------------------------------------------------------------------------
+struct BlkPanelArgs {
+    F64Grid g;
+    BlkPanel p;
+    SolveState* st;
+    int kmax;
+    XchgBlock* xchg;             // this rank's exchange block (headers, flags; V follows it)
+    XchgBlock* const* peers;     // every rank's exchange block
+    int rank, nranks;
+    int* basis;
+    int* marks;
+    int* trace;
+    long long trace_cap;
+};
+
+__device__ __forceinline__ int pick_winner_cg(const XchgBlock* x, int par, int nranks, long long* row_out) {
+    int w = -1;
+    double w_ratio = 0.0;
+    long long w_row = -1;
+    for (int k = 0; k < nranks; ++k) {
+        const CandHeader* h = &x->hdr[par][k];
+        const long long row = __ldcg(&h->row);
+        if (row < 0) continue;
+        const double ratio = __ldcg(&h->ratio);
+        if (w < 0 || ratio < w_ratio || (ratio == w_ratio && row < w_row)) { w = k; w_ratio = ratio; w_row = row; }
+    }
+    *row_out = w_row;
+    return w;
+}
+
+__global__ void __launch_bounds__(kSelMaxThreads, 1) k_blk_panel(BlkPanelArgs a) {
+    __shared__ ArgMinF64 s_arg[32];
+    __shared__ int s_int[32];
+    __shared__ double s_vc[kBlkMax];       // V[lp][c]: the entering column's cell in the earlier pivot rows
+    __shared__ double s_ur[kBlkMax];       // U[lp][r]: the leaving row's cell in the earlier pivot columns
+    __shared__ long long s_R[kBlkMax];     // global leaving rows decided so far in this block
+    __shared__ int s_w, s_flag;
+    __shared__ long long s_row;
+
+    const int nt = (int)blockDim.x, G = (int)gridDim.x, tid = (int)threadIdx.x, cta = (int)blockIdx.x;
+    const bool solo = (G == 1);
+    SolveState* st = a.st;
+    const F64Grid& g = a.g;
+    const BlkPanel& P = a.p;
+    BlkSync* sy = P.sync;
+
+    // The state is read here and written back by the CTA that leaves last: no CTA can see a half-updated state,
+    // and every CTA (every rank) walks through identical decisions.
+    int status = st->status;
+    if (status != LPS_OK) {
+        if (cta == 0 && tid == 0) P.hdr[0] = 0;
+        return;
+    }
+    int rule = st->rule;
+    long long stuck = st->stuck, npiv = st->npiv;
+    const long long maxp = st->max_pivots;
+    int pending = st->pending_zcheck;
+    const double z_entry = st->z_entry_cell;
+    unsigned long long seq = st->xseq;
+    int last_r = st->last_r, last_c = st->last_c;
+    int cur = P.hdr[1];
+
+    int l = 0;
+    for (; l < a.kmax; ++l) {
+        if (maxp >= 0 && npiv >= maxp) { status = LPS_MAX_PIVOTS; break; }
+        const double* Oc = P.O[cur];
+        double* On = P.O[cur ^ 1];
+        const double* Bc = P.B[cur];
+        double* Bn = P.B[cur ^ 1];
+
+        // ---- A: stuck counter and rule (simplex.py:123,132-137), entering column ----
+        long long stuck_now = stuck;
+        if (pending) {
+            const double corner = __ldcg(&Oc[g.n]);
+            // simplex.py:133 `assert z <= obj_val`: the objective (minus the corner cell) may not rise above its
+            // value at entry
+            if (!(corner >= z_entry)) { status = LPS_OBJ_INCREASED; break; }
+            stuck_now = (corner == z_entry) ? stuck + 1 : 0;
+        }
+        int rule_now = rule;
+        if (rule_now == LPS_RULE_DANTZIG && !(stuck_now < g.m_total + (long long)g.n)) rule_now = LPS_RULE_BLAND;
+        int c;
+        if (rule_now == LPS_RULE_DANTZIG) {
+            ArgMinF64 best{0.0, INT_MAX};
+            for (int k = tid; k < G; k += nt) best = argmin_pick(best, ArgMinF64{__ldcg(&P.p_val[k]), __ldcg(&P.p_idx[k])});
+            best = block_argmin(best, s_arg);
+            c = best.idx;
+        } else {
+            int first = INT_MAX;
+            for (int k = tid; k < G; k += nt) first = min(first, __ldcg(&P.p_bidx[k]));
+            c = block_min_int(first, s_int);
+        }
+        if (c == INT_MAX) { status = LPS_OPTIMAL; break; }
+
+        // ---- B: column c as it stands after the block's earlier pivots -> U[l]; ratio test ----
+        if (tid < l) s_vc[tid] = __ldcg(&P.V[(size_t)tid * g.ld + c]);
+        __syncthreads();
+        double* Ul = P.U + (size_t)l * P.upitch;
+        ArgMinF64 best{0.0, INT_MAX};
+        for (int i = cta * nt + tid; i < g.m; i += G * nt) {
+            double x = g.T[(size_t)i * g.ld + c];
+            const long long gi = g.row0 + i;
+            for (int lp = 0; lp < l; ++lp) {
+                if (s_R[lp] == gi) x = s_vc[lp];
+                else x = blk_apply(x, __ldcg(&P.U[(size_t)lp * P.upitch + i]), s_vc[lp]);
+            }
+            __stcg(&Ul[i], x);
+            if (x > 0.0) {
+                const double ratio = __ldcg(&Bc[i]) / x;
+                if (best.idx == INT_MAX || ratio < best.key) { best.key = ratio; best.idx = i; }
+            }
+        }
+        const double uobj = __ldcg(&Oc[c]);                    // the objective row's cell of the entering column
+        if (cta == 0 && tid == 0) __stcg(&Ul[g.m], uobj);
+        best = block_argmin(best, s_arg);
+        seq += 1;
+        if (tid == 0) {
+            if (solo) s_flag = 1;
+            else {
+                __stcg(&P.rblk[cta].key, best.key);
+                __stcg(&P.rblk[cta].idx, best.idx);
+                __threadfence();
+                const unsigned long long old = atomicAdd(&sy->arrive1, 1ull);
+                s_flag = ((old + 1) % (unsigned long long)G == 0);
+            }
+        }
+        __syncthreads();
+        if (s_flag) {
+            // the CTA that arrived last: this rank's best row, the exchange with the peers, the decision
+            if (!solo) {
+                __threadfence();
+                best = ArgMinF64{0.0, INT_MAX};
+                for (int k = tid; k < G; k += nt) best = argmin_pick(best, ArgMinF64{__ldcg(&P.rblk[k].key), __ldcg(&P.rblk[k].idx)});
+                best = block_argmin(best, s_arg);
+            }
+            const int r = best.idx;
+            int w;
+            long long w_row;
+            if (a.nranks > 1) {
+                CandHeader h{};
+                h.ratio = best.key; h.row = (r == INT_MAX) ? -1 : g.row0 + r; h.c = c; h.rule = rule_now; h.stuck = stuck_now;
+                publish_header(a.peers, a.rank, a.nranks, h, seq);
+                int ok = 1;
+                if (tid < a.nranks) ok = wait_seq(&a.xchg->hdr_seq[tid], seq) ? 1 : 0;
+                ok = __syncthreads_and(ok);
+                w = -2;
+                w_row = -1;
+                if (ok) w = pick_winner_cg(a.xchg, (int)(seq & 1), a.nranks, &w_row);
+            } else {
+                w = (r == INT_MAX) ? -1 : 0;
+                w_row = (r == INT_MAX) ? -1 : g.row0 + r;
+            }
+            if (tid == 0) {
+                if (solo) { s_w = w; s_row = w_row; }
+                else {
+                    sy->dec_w = w;
+                    sy->dec_row = w_row;
+                    __threadfence();
+                    st_release_gpu(&sy->dec_seq, seq);
+                }
+            }
+        }
+        if (!solo && tid == 0) {
+            if (wait_seq_gpu(&sy->dec_seq, seq)) {
+                s_w = *reinterpret_cast<volatile int*>(&sy->dec_w);
+                s_row = *reinterpret_cast<volatile long long*>(&sy->dec_row);
+            } else s_w = -3;
+        }
+        __syncthreads();
+        const int w = s_w;
+        const long long r_g = s_row;
+        if (w == -2 || w == -3) { status = LPS_E_PEER; break; }
+        if (w < 0) { status = LPS_UNBOUNDED; break; }
+
+        // ---- C: normalised pivot row -> V[l] (every rank's copy), objective row, right-hand side, pricing ----
+        double* Vl = P.V + (size_t)l * g.ld;
+        ArgMinF64 pb{0.0, INT_MAX};
+        int first_neg = INT_MAX;
+        double vn;                                              // the pivot row's right-hand side, normalised
+        if (w == a.rank) {
+            const int r_loc = (int)(r_g - g.row0);
+            if (tid < l) s_ur[tid] = __ldcg(&P.U[(size_t)tid * P.upitch + r_loc]);
+            __syncthreads();
+            const double inv = 1.0 / __ldcg(&Ul[r_loc]);      // rowDiv: ONE / d, then rowMult (tableau.py:262-267)
+            const double br = __ldcg(&Bc[r_loc]);
+            vn = (inv != 1.0) ? __dmul_rn(br, inv) : br;
+            const double* src = g.T + (size_t)r_loc * g.ld;
+            for (int j = 2 * (cta * nt + tid); j < (int)g.ld; j += 2 * G * nt) {
+                double2 y = *reinterpret_cast<const double2*>(src + j);
+                for (int lp = 0; lp < l; ++lp) {
+                    const double2 v = ldcg2(P.V + (size_t)lp * g.ld + j);
+                    if (s_R[lp] == r_g) y = v;
+                    else { y.x = blk_apply(y.x, s_ur[lp], v.x); y.y = blk_apply(y.y, s_ur[lp], v.y); }
+                }
+                if (inv != 1.0) { y.x = __dmul_rn(y.x, inv); y.y = __dmul_rn(y.y, inv); }   // rowMult skips a multiplier of 1
+                stcg2(Vl + j, y);
+                for (int k = 0; k < a.nranks; ++k)
+                    if (k != a.rank) *reinterpret_cast<double2*>(xchg_vrow(a.peers[k]) + (size_t)l * g.ld + j) = y;
+                double2 o = ldcg2(Oc + j);
+                o.x = blk_apply(o.x, uobj, y.x);
+                o.y = blk_apply(o.y, uobj, y.y);
+                stcg2(On + j, o);
+                price_consider(o.x, j, g.n, pb, first_neg);
+                price_consider(o.y, j + 1, g.n, pb, first_neg);
+            }
+            if (a.nranks > 1) {
+                __threadfence_system();
+                __syncthreads();
+                if (tid == 0) {
+                    const unsigned long long old = atomicAdd(&sy->ticket2, 1ull);
+                    s_flag = ((old + 1) % (unsigned long long)G == 0);
+                }
+                __syncthreads();
+                if (s_flag) {
+                    __threadfence_system();
+                    if (tid < a.nranks && tid != a.rank) st_release_sys(&a.peers[tid]->row_seq, seq);
+                }
+            }
+        } else {
+            if (tid == 0) s_flag = wait_seq(&a.xchg->row_seq, seq) ? 1 : 0;
+            __syncthreads();
+            if (!s_flag) { status = LPS_E_PEER; break; }
+            vn = __ldcg(&Vl[g.n]);
+            for (int j = 2 * (cta * nt + tid); j < (int)g.ld; j += 2 * G * nt) {
+                const double2 y = ldcg2(Vl + j);
+                double2 o = ldcg2(Oc + j);
+                o.x = blk_apply(o.x, uobj, y.x);
+                o.y = blk_apply(o.y, uobj, y.y);
+                stcg2(On + j, o);
+                price_consider(o.x, j, g.n, pb, first_neg);
+                price_consider(o.y, j + 1, g.n, pb, first_neg);
+            }
+        }
+        for (int i = cta * nt + tid; i < g.m; i += G * nt) {
+            double b;
+            if (g.row0 + i == r_g) b = vn;
+            else b = blk_apply(__ldcg(&Bc[i]), __ldcg(&Ul[i]), vn);
+            __stcg(&Bn[i], b);
+        }
+        pb = block_argmin(pb, s_arg);
+        first_neg = block_min_int(first_neg, s_int);
+        if (tid == 0) {
+            __stcg(&P.p_val[cta], pb.key);
+            __stcg(&P.p_idx[cta], pb.idx);
+            __stcg(&P.p_bidx[cta], first_neg);
+            s_R[l] = r_g;
+            if (cta == 0) {   // commit (Simplex._pivot simplex.py:192-197)
+                P.R[l] = (int)r_g;
+                P.C[l] = c;
+                if (a.trace && npiv < a.trace_cap) {
+                    a.trace[3 * npiv] = (int)r_g;
+                    a.trace[3 * npiv + 1] = c;
+                    a.trace[3 * npiv + 2] = rule_now;
+                }
+                if (a.marks) {
+                    const int old = a.basis[r_g];
+                    if (old >= 0 && old < g.n) a.marks[old] = 0;
+                    a.marks[c] = 1;
+                }
+                a.basis[r_g] = c;
+            }
+        }
+        npiv += 1;
+        rule = rule_now;
+        stuck = stuck_now;
+        pending = (rule_now == LPS_RULE_DANTZIG);
+        last_r = (int)r_g;
+        last_c = c;
+        cur ^= 1;
+
+        // ---- end of pivot: everything this pivot wrote is visible before the next one reads it ----
+        if (solo) __syncthreads();
+        else {
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                const unsigned long long old = atomicAdd(&sy->arrive2, 1ull);
+                const unsigned long long target = (old / (unsigned long long)G + 1) * (unsigned long long)G;
+                s_flag = wait_seq_gpu(&sy->arrive2, target) ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_flag) { status = LPS_E_PEER; break; }
+        }
+    }
+    if (status == LPS_OK && maxp >= 0 && npiv >= maxp) status = LPS_MAX_PIVOTS;
+
+    __syncthreads();
+    if (tid == 0) {
+        if (cta == 0) { P.hdr[0] = l; P.hdr[1] = cur; }
+        bool last = true;
+        if (!solo) last = ((atomicAdd(&sy->exit_ticket, 1ull) + 1) % (unsigned long long)G == 0);
+        if (last) {
+            st->status = status;
+            st->rule = rule;
+            st->stuck = stuck;
+            st->npiv = npiv;
+            st->pending_zcheck = pending;
+            st->xseq = seq;
+            st->last_r = last_r;
+            st->last_c = last_c;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// update: the block's pivots applied to every cell of the local rows in one pass
+// ------------------------------------------------------------------------------------------------
+struct BlkUpdateArgs {
+    F64Grid g;
+    BlkPanel p;
+    int rows_per_cta;   // multiple of kBlkRU, <= kMaxRowBlock
+    int kcap;           // pivots the shared-memory layout was sized for
+};
+
+__host__ __device__ inline size_t blk_update_smem(int kcap, int rows_per_cta) {
+    return (size_t)kcap * (kBlkCW + rows_per_cta) * sizeof(double) + 2 * (size_t)rows_per_cta * sizeof(unsigned) +
+           (size_t)(rows_per_cta / kBlkRU) * sizeof(unsigned) + 16;
+}
+
+template <bool STREAM>
+__global__ void __launch_bounds__(kThreads, 2) k_blk_update(BlkUpdateArgs a) {
+    extern __shared__ __align__(128) unsigned char blk_smem[];
+    const BlkPanel& P = a.p;
+    const F64Grid& g = a.g;
+    const int kk = P.hdr[0];
+    if (kk <= 0) return;
+    const int RB = a.rows_per_cta;
+    double* s_v = reinterpret_cast<double*>(blk_smem);                 // kk x kBlkCW
+    double* s_u = s_v + (size_t)a.kcap * kBlkCW;                        // kk x RB
+    unsigned* s_spec = reinterpret_cast<unsigned*>(s_u + (size_t)a.kcap * RB);   // per row: bit l = this row is pivot l's row
+    unsigned* s_zero = s_spec + RB;                                     // per row: bit l = multiplier of pivot l is 0
+    unsigned* s_grp = s_zero + RB;                                      // per group of kBlkRU rows: any special / zero bit
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + RB / kBlkRU + ((RB / kBlkRU) & 1));
+
+    const int tid = (int)threadIdx.x;
+    const int col0 = blockIdx.x * kBlkCW;
+    const int row0 = blockIdx.y * RB;
+    const int mrows = g.m + 1;
+    const int ncols = min(kBlkCW, (int)g.ld - col0);
+    const int nrows = min(RB, mrows - row0);
+
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        mbar_fence_init();
+        const uint32_t vb = (uint32_t)ncols * 8u, ub = (uint32_t)RB * 8u;
+        mbar_expect_tx(s_bar, (uint32_t)kk * (vb + ub));
+        for (int l = 0; l < kk; ++l) {
+            tma_load_1d(s_v + (size_t)l * kBlkCW, P.V + (size_t)l * g.ld + col0, vb, s_bar);
+            tma_load_1d(s_u + (size_t)l * RB, P.U + (size_t)l * P.upitch + row0, ub, s_bar);
+        }
+    }
+    __syncthreads();
+    mbar_wait(s_bar, 0);
+
+    // per-row masks: which pivots replace the row (it is their pivot row), which leave it alone (zero multiplier)
+    for (int il = tid; il < RB; il += kThreads) {
+        unsigned spec = 0, zero = 0;
+        if (il < nrows) {
+            const long long gi = (row0 + il < g.m) ? g.row0 + row0 + il : -1;   // the objective row is nobody's pivot row
+            for (int l = 0; l < kk; ++l) {
+                if (gi >= 0 && (long long)P.R[l] == gi) spec |= 1u << l;
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(s_u[(size_t)l * RB + il]);
+                if ((bits << 1) == 0ull) zero |= 1u << l;
+            }
+        }
+        s_spec[il] = spec;
+        s_zero[il] = zero;
+    }
+    __syncthreads();
+    for (int gq = tid; gq < RB / kBlkRU; gq += kThreads) {
+        unsigned f = 0;
+        for (int q = 0; q < kBlkRU; ++q) f |= s_spec[gq * kBlkRU + q] | s_zero[gq * kBlkRU + q];
+        s_grp[gq] = f;
+    }
+    __syncthreads();
+
+    const int jl = 2 * tid;
+    if (jl >= ncols) return;
+    double* base = g.T + (size_t)row0 * g.ld + col0 + jl;
+    const double* sv = s_v + jl;
+
+    double2 ta[kBlkRU], tb[kBlkRU];
+    auto load = [&](double2 (&t)[kBlkRU], int rg) {
+#pragma unroll
+        for (int q = 0; q < kBlkRU; ++q)
+            if (rg + q < nrows) t[q] = ld_f64x2<STREAM>(base + (size_t)(rg + q) * g.ld);
+    };
+    auto work = [&](double2 (&t)[kBlkRU], int rg) {
+        if (s_grp[rg / kBlkRU] == 0) {
+            // the common case: every pivot of the block touches every row of the group
+            for (int l = 0; l < kk; ++l) {
+                const double2 v = *reinterpret_cast<const double2*>(sv + (size_t)l * kBlkCW);
+                const double2* up = reinterpret_cast<const double2*>(s_u + (size_t)l * RB + rg);
+#pragma unroll
+                for (int q2 = 0; q2 < kBlkRU / 2; ++q2) {
+                    const double2 u = up[q2];
+                    t[2 * q2].x = __dadd_rn(t[2 * q2].x, __dmul_rn(-u.x, v.x));
+                    t[2 * q2].y = __dadd_rn(t[2 * q2].y, __dmul_rn(-u.x, v.y));
+                    t[2 * q2 + 1].x = __dadd_rn(t[2 * q2 + 1].x, __dmul_rn(-u.y, v.x));
+                    t[2 * q2 + 1].y = __dadd_rn(t[2 * q2 + 1].y, __dmul_rn(-u.y, v.y));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kBlkRU; ++q)
+                if (rg + q < nrows) st_f64x2<STREAM>(base + (size_t)(rg + q) * g.ld, t[q]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < kBlkRU; ++q) {
+                if (rg + q >= nrows) continue;
+                const unsigned spec = s_spec[rg + q], zero = s_zero[rg + q];
+                bool dirty = false;
+                for (int l = 0; l < kk; ++l) {
+                    const double2 v = *reinterpret_cast<const double2*>(sv + (size_t)l * kBlkCW);
+                    if ((spec >> l) & 1u) { t[q] = v; dirty = true; }
+                    else if (!((zero >> l) & 1u)) {
+                        const double u = s_u[(size_t)l * RB + rg + q];
+                        t[q].x = __dadd_rn(t[q].x, __dmul_rn(-u, v.x));
+                        t[q].y = __dadd_rn(t[q].y, __dmul_rn(-u, v.y));
+                        dirty = true;
+                    }
+                }
+                if (dirty) st_f64x2<STREAM>(base + (size_t)(rg + q) * g.ld, t[q]);
+            }
+        }
+    };
+    load(ta, 0);
+    for (int rg = 0; rg < nrows; rg += 2 * kBlkRU) {
+        if (rg + kBlkRU < nrows) load(tb, rg + kBlkRU);
+        work(ta, rg);
+        if (rg + 2 * kBlkRU < nrows) load(ta, rg + 2 * kBlkRU);
+        if (rg + kBlkRU < nrows) work(tb, rg + kBlkRU);
+    }
+}
+
+}  // namespace lps

@@ -6,6 +6,7 @@
 
 #include "../../include/lps_b200.h"
 #include "lps_f64.cuh"
+#include "lps_f64_blk.cuh"
 
 int lps_fail(int code, const char* fmt, ...);
 #define fail lps_fail
@@ -68,6 +69,15 @@ struct lps_handle {
     int* scratch_i = nullptr;        // n + 8 ints (isCanonical)
     void* slab = nullptr;            // the one allocation the small device buffers are carved from
     bool solving = false;
+
+    // pivots in blocks (lps_f64_blk.cuh): the look-ahead panel and the fused update
+    int blk_k = kBlkMax;             // pivots decided per panel launch (1..kBlkMax); 0: rank-1 path only
+    int blk_rows = 128;              // rows per CTA of the fused update
+    int pan_blocks = 1, pan_threads = 256;
+    BlkPanel blk{};
+    bool blk_valid = false;          // O / B / pricing partials of the panel describe the grid
+    bool pp_valid = false;           // pd_val / pd_idx / pb_idx (rank-1 path) describe the grid's objective row
+    size_t xchg_bytes = 0;
 
     // a burst of (select, update) pairs captured once as a CUDA graph: small tableaux are launch bound on the host
     cudaGraphExec_t gexec = nullptr;

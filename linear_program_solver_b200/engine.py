@@ -273,6 +273,22 @@ class F64Engine:
     def step_update(self):
         N.check(self.L.lps_step_update(self.h))
 
+    def step_block(self):
+        """One block of the blocked loop (`lps_step_block`): up to `block_size()` pivots decided by the look-ahead
+        panel, applied to the grid in one pass."""
+        N.check(self.L.lps_step_block(self.h))
+
+    def block_size(self) -> int:
+        return int(self.L.lps_block_size(self.h))
+
+    def set_block_size(self, k: int):
+        self._pool_key = None                            # a tuned handle does not go back to the pool
+        N.check(self.L.lps_set_block_size(self.h, int(k)))
+
+    def set_panel_ctas(self, ctas: int):
+        self._pool_key = None
+        N.check(self.L.lps_set_panel_ctas(self.h, int(ctas)))
+
     def poll(self) -> Tuple[int, int]:
         st, k = c_int(0), c_longlong(0)
         N.check(self.L.lps_solve_poll(self.h, byref(st), byref(k)))

@@ -6,12 +6,15 @@ pivot: every rank prices the (identical) objective row and ratio-tests its own r
 ratio, then lowest global row: simplex.py:277) and applies the rank-1 update to its rows
 (`lps_step_update`).  No host round trip inside a burst of pivots.  Two exchanges:
 
-  exchange="p2p"   (default on GPUs) the select kernel does it itself with peer stores over NVLink: each
-                   rank writes a 64-byte header into every peer's exchange block and waits for theirs, the
-                   owner of the winning row writes the normalised row into every peer.  The argmin
-                   all-reduce and the pivot-row broadcast are fused into `lps_step_select`: two launches
-                   per pivot, no collective call; torch.distributed is used once, to pass the CUDA IPC
-                   handles around.
+  exchange="p2p"   (default on GPUs) the kernels do it themselves with peer stores over NVLink: each rank
+                   writes a 64-byte header into every peer's exchange block and waits for theirs, the
+                   owner of the winning row writes the normalised row into every peer.  No collective
+                   call; torch.distributed is used once, to pass the CUDA IPC handles around.  Pivots
+                   run in BLOCKS (`lps_step_block`, csrc/lps_f64_blk.cuh): a look-ahead panel decides
+                   up to 16 pivots -- one exchange per pivot, on O(m+n) numbers -- and one pass over
+                   the local rows applies them all, so the tableau is read and written once per block
+                   instead of once per pivot.  `block=0` keeps the rank-1 loop (`lps_step_select` +
+                   `lps_step_update` per pivot), the previous round's path.
   exchange="nccl"  the candidates -- header followed by the normalised candidate row -- are all-gathered
                    with one NCCL collective per pivot (the baseline the p2p path is measured against, and
                    the protocol the CPU/gloo test exercises).
@@ -38,7 +41,7 @@ def shard_rows(m_total: int, rank: int, nranks: int) -> Tuple[int, int]:
 class ShardedF64Solver:
     def __init__(self, m_total: int, n: int, rank: int = 0, nranks: int = 1, device: Optional[int] = None,
                  group=None, engine_factory: Optional[Callable] = None, burst: Optional[int] = None,
-                 exchange: Optional[str] = None):
+                 exchange: Optional[str] = None, block: Optional[int] = None):
         self.m_total, self.n, self.rank, self.nranks, self.group = int(m_total), int(n), rank, nranks, group
         self.row0, self.m_local = shard_rows(m_total, rank, nranks)
         if self.m_local <= 0:
@@ -59,9 +62,21 @@ class ShardedF64Solver:
                 self.exchange = "nccl"
             if self.exchange == "nccl":
                 self.eng.set_shard(self.row0, self.m_total, rank, nranks)
-        # pivots enqueued between two host checks: ~2 ms of device work, between 4 and 256
-        est_us = max(4.0, (self.m_local + 1) * (self.n + 1) * 16.0 / 5.0e6)
+        # pivots per block of the blocked loop (peer-store exchange only; the collective exchange is per pivot)
+        self.block = 0
+        if self.exchange == "p2p" and hasattr(self.eng, "block_size"):
+            if block is not None:
+                self.eng.set_block_size(block)
+            self.block = self.eng.block_size()
+        # pivots enqueued between two host checks: ~2 ms of device work, between 4 and 256.  The same number on every
+        # rank -- every enqueued pivot is a collective with exchange="nccl" -- so it is derived from the LARGEST
+        # shard, not from this rank's own (uneven shards differ by a row).
+        rows_max = -(-self.m_total // nranks)
+        est_us = max(4.0, (rows_max + 1) * (self.n + 1) * 16.0 / 5.0e6)
         self.burst = burst or int(max(4, min(256, 2000.0 / est_us)))
+        if self.block:
+            blocks = max(1, min(64, int(2000.0 / (est_us + 10.0 * self.block))))
+            self.burst = burst or blocks * self.block
         self._active = False
 
     def close(self):
@@ -97,8 +112,13 @@ class ShardedF64Solver:
                 dist.all_gather_into_tensor(self.eng.cand_all, self.eng.cand_send, group=self.group)
 
     def enqueue(self, pivots: int):
-        """Enqueue `pivots` (select, exchange, update) triples without waiting for the device."""
+        """Enqueue `pivots` pivots without waiting for the device: blocks of `self.block` pivots (the last one of a
+        pivot prefix stops early on the device), or (select, exchange, update) triples."""
         eng = self.eng
+        if self.block:
+            for _ in range(-(-pivots // self.block)):
+                eng.step_block()
+            return
         for _ in range(pivots):
             eng.step_select()
             self._exchange()
@@ -126,7 +146,8 @@ class ShardedF64Solver:
             self.enqueue(now)
             done += now
             if now == 0:
-                self.eng.step_select()      # lets the device report LPS_MAX_PIVOTS (or optimality)
+                # lets the device report LPS_MAX_PIVOTS (or optimality)
+                self.eng.step_block() if self.block else self.eng.step_select()
             status, _ = self.poll()
             if status != N.OK:
                 break

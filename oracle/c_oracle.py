@@ -12,6 +12,7 @@ _SO = os.path.join(_HERE, "_build", "libpivot_oracle.so")
 _lib = None
 
 OK, OPTIMAL, UNBOUNDED, ZERO_PIVOT, MAX_PIVOTS = 0, 1, 2, 3, 4
+OBJ_INCREASED = 6
 
 
 def build(force: bool = False) -> str:

@@ -34,6 +34,7 @@
 #define ORC_UNBOUNDED 2
 #define ORC_ZERO_PIVOT 3
 #define ORC_MAX_PIVOTS 4
+#define ORC_OBJ_INCREASED 6   /* simplex.py:133 assert z <= obj_val */
 
 /* ---- a minimal fork-join over row ranges (libgomp's spec file is not in the image) ---- */
 static int g_threads = 0;
@@ -128,8 +129,10 @@ int orc_ratio_f64(const double *T, int m, int n, size_t ld, int c) {
 
 /*
  * simplex.py:110-148.  basis[m] is updated in place; trace (may be NULL) gets
- * 3 ints per pivot (row, column, rule).  Returns ORC_OPTIMAL, ORC_UNBOUNDED or
- * ORC_MAX_PIVOTS (prefix stop, not in the reference).
+ * 3 ints per pivot (row, column, rule).  Returns ORC_OPTIMAL, ORC_UNBOUNDED,
+ * ORC_OBJ_INCREASED (the reference's `assert z <= obj_val` after a Dantzig pivot,
+ * simplex.py:133: a float run can trip it on rounding noise; the pivot stays applied)
+ * or ORC_MAX_PIVOTS (prefix stop, not in the reference).
  */
 int orc_solve_f64(double *T, int m, int n, size_t ld, int *basis, int *trace,
                   long max_pivots, long *npiv_out) {
@@ -150,6 +153,7 @@ int orc_solve_f64(double *T, int m, int n, size_t ld, int *basis, int *trace,
         ++done;
         if (rule == 0) {
             double z = -T[(size_t)m * ld + n];
+            if (!(z <= z_entry)) { status = ORC_OBJ_INCREASED; break; }
             stuck = (z == z_entry) ? stuck + 1 : 0;
         }
     }

@@ -58,6 +58,9 @@ class OracleShardEngine:
             return
         stuck, rule = self.stuck, self.rule
         if self.pending:
+            if not (self.T[self.m, self.n] >= self.z_entry):      # simplex.py:133 assert z <= obj_val
+                self.status = 6
+                return
             stuck = stuck + 1 if self.T[self.m, self.n] == self.z_entry else 0
         if rule == 0 and not stuck < self.m_total + self.n:
             rule = 1
@@ -169,6 +172,23 @@ def test_sharded_protocol_equals_single_process_oracle(world, m, seed, max_pivot
         ml = shard.shape[0] - 1
         assert shard[:ml].tobytes() == T[row0:row0 + ml].tobytes()       # the rank's rows
         assert shard[ml].tobytes() == T[m].tobytes()                      # its replica of the objective row
+
+
+def test_default_burst_is_the_same_on_every_rank_with_uneven_shards():
+    """Every enqueued pivot is a collective with exchange="nccl": ranks whose shards differ by a row must not round
+    their default burst differently (round-1 advisor finding)."""
+    from linear_program_solver_b200.sharded import ShardedF64Solver, shard_rows
+    differing = 0
+    for m_total, n, world in [(142, 49999, 3), (1001, 3000, 3), (32769, 65538, 8), (233, 49999, 3), (12345, 24690, 7)]:
+        bursts, old = set(), set()
+        for rank in range(world):
+            sv = ShardedF64Solver(m_total, n, rank, world, engine_factory=OracleShardEngine, exchange="nccl")
+            bursts.add(sv.burst)
+            ml = shard_rows(m_total, rank, world)[1]
+            old.add(int(max(4, min(256, 2000.0 / max(4.0, (ml + 1) * (n + 1) * 16.0 / 5.0e6)))))
+        assert len(bursts) == 1, (m_total, n, world, bursts)
+        differing += len(old) > 1
+    assert differing >= 1          # the per-rank formula really did disagree on one of these shapes
 
 
 def test_node_lps_shard_by_lp_without_overlap():
