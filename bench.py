@@ -8,14 +8,22 @@
 Workload (config.workload): C4 of BASELINE.json -- the fp64 32768 x 65536 tableau of the seeded dense
 family (17.2 GB, far larger than L2, so no flush is needed between iterations), generated on the
 device, row-sharded over the N GPUs (strong scaling: the tableau is fixed, each rank holds m/N rows).
-A step is `--pivots-per-step` consecutive simplex pivots (Dantzig pricing + ratio test + rank-1
-update, the reference's Simplex.solve loop); value = pivots/s over all ranks, device-timed with CUDA
-events on the launching stream, max over ranks.
+A step is `--pivots-per-step` consecutive simplex pivots (Dantzig pricing + ratio test + update, the
+reference's Simplex.solve loop); value = pivots/s over all ranks, device-timed with CUDA events on the
+launching stream, max over ranks.
+
+The loop runs pivots in BLOCKS (csrc/lps_f64_blk.cuh): a look-ahead panel decides up to 16 pivots from
+O(m+n) numbers, one pass over the tableau applies them all, bit-identical to pivot-by-pivot updates.
+The dominant kernel is that fused pass, k_blk_update: it reads and writes every cell ONCE per block.
 
 Extra objects on the JSON line:
-  roofline      the rank-1 update kernel: algorithmic bytes per launch (16(m_loc+1)(n+1) + 8(m_loc+1)
-                + 8(n+1)) / its mean CUDA-event duration in the timed region,
-                against MEASURED_PEAKS.json's hbm_gbs
+  roofline      k_blk_update: the bytes one launch has to move -- 16(m_loc+1)(n+1) for the cells plus the
+                block's pivot rows and columns, K(8(m_loc+1) + 8(n+1)) -- / its mean CUDA-event duration in
+                the timed region, against MEASURED_PEAKS.json's hbm_gbs.  `rank1_equivalent_gbs` restates
+                the same time in SURVEY.md section 8(d)'s per-pivot bytes (what a pivot-at-a-time loop
+                would have had to move for the pivots this launch applied); `rank1` is the rank-1 kernel
+                k_update_f64 itself (north star: >= 70 % of the HBM peak), timed over a short leg of the
+                pivot-at-a-time loop before the main measurement
   e2e           the same metric through the public API with HOST buffers: every step uploads the
                 tableau from pinned host memory, runs the pivots, reads back basis, objective and
                 basic solution
@@ -56,6 +64,21 @@ def algorithmic_bytes(m_rows: int, n: int) -> int:
     return 16 * (m_rows + 1) * (n + 1) + 8 * (m_rows + 1) + 8 * (n + 1)
 
 
+def block_bytes(m_rows: int, n: int, k: int) -> int:
+    """fp64 bytes ONE fused launch applying k pivots must move: every cell read and written once, plus the k pivot
+    columns and normalised pivot rows of the panel."""
+    return 16 * (m_rows + 1) * (n + 1) + k * (8 * (m_rows + 1) + 8 * (n + 1))
+
+
+def base_config(a) -> dict:
+    """The workload, named identically by both arms."""
+    m, n = a.m, 2 * a.m
+    return {"workload": f"C4 fp64 {m}x{n} dense tableau, seed {a.seed}", "m": m, "n": n,
+            "pivots_per_step": a.pivots_per_step,
+            "l2": f"tableau ({(m + 1) * (n + 1) * 8 / 1e9:.1f} GB total) is larger than L2; no flush needed"
+                  if (m + 1) * (n + 1) * 8 > (256 << 20) else "tableau fits L2: a cache-resident workload by construction"}
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -64,11 +87,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic():
-    """dram bytes per launch of the update kernel from the committed `ncu --set full` capture, or None."""
+def recorded_traffic(kernel: str):
+    """dram bytes per launch of a kernel at C4 on one GPU from the committed `ncu --set full` capture, or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "update_traffic.json")) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            d = json.load(f)
+        return d.get(kernel, {}).get("dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -168,15 +192,16 @@ def run_reference(a):
         if s >= a.warmup:
             times.append(dt)
     sec = float(np.mean(times)) / scale
-    sample = f"1 pivot per step (pricing + ratio test + rank-1 update) of the {rows} x {n} " \
-             + ("full tableau" if rows == m else f"row slab of the {m} x {n} tableau, time scaled by rows") \
-             + f", {a.steps} steps"
+    B = a.pivots_per_step
+    sample = f"bounded sample: 1 pivot (pricing + ratio test + rank-1 update) timed per step instead of {B}, on the " \
+             f"{rows} x {n} " + ("full tableau" if rows == m else f"row slab of the {m} x {n} tableau, time scaled by rows") \
+             + f", {a.steps} steps; ms_per_step = that pivot's time x {B}"
     val = 1.0 / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3 * B, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C4 fp64 {m}x{n} dense tableau, seed {a.seed}", "m": m, "n": n, "pivots_per_step": 1},
+        "config": base_config(a),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": C.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -219,11 +244,37 @@ def run_ours(a):
 
     m, n, B = a.m, 2 * a.m, a.pivots_per_step
     row0, m_loc = shard_rows(m, rank, world)
-    solver = ShardedF64Solver(m, n, rank, world, device=local, exchange=a.exchange)
+    solver = ShardedF64Solver(m, n, rank, world, device=local, exchange=a.exchange, block=a.block)
     solver_exchange = solver.exchange            # "nccl" when the peers' exchange blocks could not be mapped
     eng = solver.eng
-    eng.fill_dense(a.seed, 1, 9)
+    K = solver.block                             # pivots per block; 0: the pivot-at-a-time loop
     basis = np.arange(m, 2 * m, dtype=np.int32)
+    peak, peak_src = measured_peak()
+
+    # ---- short leg of the pivot-at-a-time loop: the rank-1 kernel k_update_f64 against the roofline ----
+    rank1 = None
+    if K and a.rank1_pivots > 0:
+        eng.fill_dense(a.seed, 1, 9)
+        eng.set_block_size(0)
+        solver.block = 0
+        solver.begin(basis.copy(), None, -1, 0)
+        solver.enqueue(3)
+        solver.poll()
+        eng.prof_reset()
+        barrier()
+        solver.enqueue(a.rank1_pivots)
+        solver.poll()
+        r1_ms, r1_n, _ = eng.prof_read()
+        solver.end(basis.copy(), None, 0)
+        r1_avg = max_over_ranks(r1_ms / max(r1_n, 1))
+        r1_bytes = algorithmic_bytes(m_loc, n)
+        r1_ach = r1_bytes / (r1_avg * 1e-3) / 1e9
+        rank1 = {"kernel": "k_update_f64", "achieved": r1_ach, "frac": r1_ach / peak, "bytes_per_launch": r1_bytes,
+                 "ms_per_launch": r1_avg, "launches_timed": int(r1_n), "traffic": recorded_traffic("k_update_f64")}
+        eng.set_block_size(K)
+        solver.block = K
+
+    eng.fill_dense(a.seed, 1, 9)
     solver.begin(basis, None, -1, 0)
 
     def step():
@@ -247,9 +298,10 @@ def run_ours(a):
     upd_ms, upd_launches, all_launches = eng.prof_read()
     pivots = piv1 - piv0
     value = pivots / (ms * 1e-3)
-    bytes_launch = algorithmic_bytes(m_loc, n)
+    kernel = "k_blk_update" if K else "k_update_f64"
+    per_launch = pivots / max(upd_launches, 1)   # pivots one launch applied (K, fewer only at the end of a solve)
+    bytes_launch = block_bytes(m_loc, n, K) if K else algorithmic_bytes(m_loc, n)
     upd_avg_ms = max_over_ranks(upd_ms / max(upd_launches, 1))
-    peak, peak_src = measured_peak()
     achieved = bytes_launch / (upd_avg_ms * 1e-3) / 1e9 if upd_launches else None
     solver.end(basis, None, 0)
 
@@ -323,18 +375,25 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C4 fp64 {m}x{n} dense tableau, seed {a.seed}", "m": m, "n": n,
-                       "pivots_per_step": B, "sharding": f"rows/{world}", "rows_per_gpu": m_loc,
-                       "exchange": ("none (one rank)" if world == 1 else
-                                    "peer stores over NVLink inside the pivot kernels" if solver_exchange == "p2p" else
-                                    "one NCCL all-gather per pivot"),
-                       "l2": "tableau (17.2 GB total) is larger than L2; no flush needed",
-                       "status_after": int(status), "pivots_timed": int(pivots)},
+            "config": dict(base_config(a), sharding=f"rows/{world}", rows_per_gpu=m_loc,
+                           loop=(f"blocks of {K} pivots: look-ahead panel + one fused pass over the tableau" if K
+                                 else "one rank-1 update per pivot"),
+                           exchange=("none (one rank)" if world == 1 else
+                                     "peer stores over NVLink inside the pivot kernels" if solver_exchange == "p2p" else
+                                     "one NCCL all-gather per pivot"),
+                           status_after=int(status), pivots_timed=int(pivots)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": recorded_traffic(),
-                         "kernel": "k_update_f64", "bytes_per_launch": bytes_launch, "ms_per_launch": upd_avg_ms,
-                         "launches_timed": int(upd_launches), "peak_source": peak_src,
-                         "loop_frac": bytes_launch * pivots / (ms * 1e-3) / 1e9 / peak},
+                         "frac": (achieved / peak) if achieved else None, "traffic": recorded_traffic(kernel) if world == 1 else None,
+                         "kernel": kernel, "bytes_per_launch": bytes_launch, "ms_per_launch": upd_avg_ms,
+                         "launches_timed": int(upd_launches), "pivots_per_launch": per_launch,
+                         "peak_source": peak_src,
+                         # the same launch time in SURVEY 8(d)'s per-pivot bytes: what a pivot-at-a-time loop would
+                         # have had to move for the pivots one launch applies (exceeds the HBM peak by construction:
+                         # the block reads and writes the tableau once for all of them)
+                         "rank1_equivalent_gbs": (algorithmic_bytes(m_loc, n) * per_launch / (upd_avg_ms * 1e-3) / 1e9)
+                         if upd_launches else None,
+                         "loop_frac": bytes_launch * upd_launches / (ms * 1e-3) / 1e9 / peak,
+                         "rank1": rank1},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world if world > 1 else h2d,
                     "d2h_bytes_per_step": d2h_box[0], "steps": e2e_steps, "pivots_per_step": B,
                     "seconds_per_step": {"upload_and_setup": float(np.mean([p[0] for p in parts])),
@@ -360,8 +419,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--m", type=int, default=32768, help="constraint rows (n = 2m); default is config C4")
-    ap.add_argument("--pivots-per-step", type=int, default=512,
+    ap.add_argument("--pivots-per-step", type=int, default=1024,
                     help="consecutive simplex pivots per step (a solve of this size runs tens of thousands)")
+    ap.add_argument("--block", type=int, default=None, help="pivots per block (default: the library's, 16; 0 = one rank-1 update per pivot)")
+    ap.add_argument("--rank1-pivots", type=int, default=24, help="length of the pivot-at-a-time leg that times k_update_f64 (0: skip)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

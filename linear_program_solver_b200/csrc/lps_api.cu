@@ -102,14 +102,9 @@ static void plan(lps_handle* h) {
         h->pan_blocks = std::max(2, std::min(std::max((h->m + kThreads - 1) / kThreads, (int)((h->ld / 2 + kThreads - 1) / kThreads)), std::min(sms, 256)));
     }
     h->sel_blocks = std::min(h->sel_blocks, sms);
-    // fused update: 512-column tiles, as many rows per CTA as still leave a few waves of CTAs
-    const size_t blk_chunks = (h->ld + kBlkCW - 1) / kBlkCW;
-    h->blk_rows = 8;
-    for (int rb = kMaxRowBlock; rb >= 8; rb /= 2)
-        if (blk_chunks * (((size_t)h->m + 1 + rb - 1) / rb) >= (size_t)sms * 4) { h->blk_rows = rb; break; }
+    h->sms = sms;
     h->blk_k = kBlkMax;
     if (const char* e = getenv("LPS_F64_BLOCK")) { const int v = atoi(e); if (v >= 0 && v <= kBlkMax) h->blk_k = v; }
-    if (const char* e = getenv("LPS_F64_BLOCK_ROWS")) { const int v = atoi(e); if (v >= 8 && v <= kMaxRowBlock && v % 8 == 0) h->blk_rows = v; }
     if (const char* e = getenv("LPS_F64_PANEL_CTAS")) { const int v = atoi(e); if (v >= 2 && v <= sms && h->pan_blocks > 1) h->pan_blocks = v; }
 }
 
@@ -138,11 +133,8 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
         CU(cudaMemsetAsync(h->T, 0, grid_bytes, h->stream));
     }
     plan(h);
-    {   // the fused update stages up to 16 pivot rows and columns in shared memory: beyond the 48 KB default
-        const size_t most = blk_update_smem(kBlkMax, kMaxRowBlock);
-        CU(cudaFuncSetAttribute(k_blk_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
-        CU(cudaFuncSetAttribute(k_blk_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
-    }
+    // the fused update's shared-memory ring (stages of the grid, pivot rows): far beyond the 48 KB default
+    CU(cudaFuncSetAttribute(k_blk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkRing)));
     const size_t ucol_n = ((size_t)m + 1 + kMaxRowBlock - 1) / kMaxRowBlock * kMaxRowBlock + kMaxRowBlock;
     const int maxchunks = (int)((h->ld + kNarrowChunk - 1) / kNarrowChunk);
     {   // the small buffers: one allocation (lps_internal.h, Slab)
@@ -160,7 +152,7 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
         sl.add(&h->cand_send, h->cand_stride);           // replaced, never freed, when lps_set_shard passes the caller's slots
         // panel of the blocked pivot loop (lps_f64_blk.cuh)
         h->blk.upitch = ucol_n;
-        sl.add(&h->blk.U, (size_t)kBlkMax * ucol_n);
+        sl.add(&h->blk.U, (size_t)kBlkRec * ucol_n);
         sl.add(&h->blk.O[0], h->ld);
         sl.add(&h->blk.O[1], h->ld);
         sl.add(&h->blk.B[0], ucol_n);
@@ -175,7 +167,7 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
         sl.add(&h->blk.sync, (size_t)1);
         CU(sl.commit(&h->slab));
     }
-    CU(cudaMemsetAsync(h->blk.U, 0, (size_t)kBlkMax * ucol_n * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->blk.U, 0, (size_t)kBlkRec * ucol_n * sizeof(double), h->stream));
     CU(cudaMemsetAsync(h->blk.hdr, 0, 4 * sizeof(int), h->stream));
     CU(cudaMemsetAsync(h->blk.sync, 0, sizeof(BlkSync), h->stream));
     CU(cudaMemsetAsync(h->ucol, 0, ucol_n * sizeof(double), h->stream));
@@ -363,6 +355,7 @@ static int launch_update(lps_handle* h, int commit) {
     if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
     h->launches_update++;
     h->launches_all++;
+    h->blk_valid = false;             // the panel's copy of the objective row / right-hand side is stale now
     CU(cudaGetLastError());
     return LPS_OK;
 }
@@ -382,21 +375,21 @@ static int launch_panel(lps_handle* h) {
     a.g = grid_of(h); a.p = h->blk; a.st = h->st; a.kmax = h->blk_k;
     a.xchg = h->xchg; a.peers = h->d_peers; a.rank = h->rank; a.nranks = h->use_xchg ? h->nranks : 1;
     a.basis = h->basis; a.marks = h->use_marks ? h->marks : nullptr; a.trace = h->trace; a.trace_cap = h->trace_cap;
-    k_blk_panel<<<h->pan_blocks, h->pan_threads, 0, h->stream>>>(a);
+    if (h->pan_threads == kSelMaxThreads) k_blk_panel<kSelMaxThreads><<<h->pan_blocks, kSelMaxThreads, 0, h->stream>>>(a);
+    else k_blk_panel<kThreads><<<h->pan_blocks, kThreads, 0, h->stream>>>(a);
     h->launches_all++;
     CU(cudaGetLastError());
     return LPS_OK;
 }
 static int launch_blk_update(lps_handle* h) {
     BlkUpdateArgs a;
-    a.g = grid_of(h); a.p = h->blk; a.rows_per_cta = h->blk_rows; a.kcap = h->blk_k;
-    const size_t smem = blk_update_smem(h->blk_k, h->blk_rows);
-    const int which = h->stream_hint ? 1 : 0;
-    dim3 grid((unsigned)((h->ld + kBlkCW - 1) / kBlkCW), (unsigned)((h->m + 1 + h->blk_rows - 1) / h->blk_rows));
+    a.g = grid_of(h); a.p = h->blk;
+    // persistent: one CTA per SM, each walks its share of the (512-column chunk, 8-row stage) items
+    const long long items = (long long)((h->ld + kBlkCW - 1) / kBlkCW) * (((long long)h->m + 1 + kBlkRU - 1) / kBlkRU);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(h->sms, items));
     const bool timed = h->prof && h->ev_used + 2 <= h->ev.size();
     if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
-    if (which) k_blk_update<true><<<grid, kThreads, smem, h->stream>>>(a);
-    else k_blk_update<false><<<grid, kThreads, smem, h->stream>>>(a);
+    k_blk_update<<<grid, kBlkConsumers + 32, sizeof(BlkRing), h->stream>>>(a);
     if (timed) CU(cudaEventRecord(h->ev[h->ev_used++], h->stream));
     h->launches_update++;
     h->launches_all++;
@@ -762,13 +755,10 @@ static int ensure_burst_graph(lps_handle* h, long long burst) {
     mix((unsigned long long)(uintptr_t)h->basis); mix(h->use_xchg ? 1 : 0); mix((unsigned long long)h->chunk);
     mix((unsigned long long)h->rows_per_cta); mix((unsigned long long)h->sel_blocks); mix((unsigned long long)h->sel_threads);
     mix((unsigned long long)(uintptr_t)h->cand_send); mix((unsigned long long)(uintptr_t)h->cand_all); mix((unsigned long long)burst);
-    mix((unsigned long long)h->blk_k); mix((unsigned long long)h->blk_rows); mix((unsigned long long)h->pan_blocks);
+    mix((unsigned long long)h->blk_k); mix((unsigned long long)h->pan_blocks);
     mix((unsigned long long)h->n); mix((unsigned long long)(uintptr_t)h->T);
     if (h->gexec && h->gsig == sig && h->gburst == burst) return LPS_OK;
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
-    // the lazy re-reads of the objective row stay outside the captured burst
-    if (h->blk_k >= 1) TRY(blk_sync_panel(h));
-    else if (!h->pp_valid) TRY(launch_price(h));
     const long long la = h->launches_all, lu = h->launches_update;
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -808,6 +798,7 @@ extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* m
         const double blk_us = est_us + 8.0 * h->blk_k;
         const long long burst = (long long)std::max(1.0, std::min(64.0, 2000.0 / blk_us));
         const long long gburst = std::min<long long>(burst, 8);
+        TRY(blk_sync_panel(h));           // the lazy re-read of the objective row stays outside the captured burst
         if (graphed) TRY(ensure_burst_graph(h, gburst));
         long long enq_blocks = 0;
         for (;;) {
@@ -833,6 +824,7 @@ extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* m
     const long long burst = (long long)std::max(4.0, std::min(256.0, 2000.0 / est_us));
     long long enqueued = 0;
     const long long gburst = std::min<long long>(burst, 32);   // short graphs: capture stays cheap next to a short solve
+    if (!h->pp_valid) TRY(launch_price(h));   // (outside the captured burst)
     if (graphed) TRY(ensure_burst_graph(h, gburst));
     for (;;) {
         if (graphed) {

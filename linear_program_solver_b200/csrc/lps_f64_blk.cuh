@@ -35,7 +35,10 @@ namespace lps {
 
 constexpr int kBlkMax = 16;   // pivots per block (upper bound; the fp64 pipe saturates near 22 at the HBM rate)
 constexpr int kBlkCW = 512;   // columns per update tile: 256 threads x one double2
-constexpr int kBlkRU = 8;     // rows in flight per thread
+constexpr int kBlkRU = 8;     // rows per stage of the fused update
+constexpr int kBlkRec = kBlkMax + 2;   // doubles per row record of the panel's U (16-byte multiple: TMA source)
+constexpr int kBlkStages = 4;          // stages of the update's shared-memory ring
+constexpr int kBlkConsumers = 256;     // consumer threads of the fused update (one double2 column each)
 
 struct alignas(128) BlkSync {        // zeroed at lps_solve_begin; counters only ever grow
     unsigned long long arrive1;      // phase B arrivals: the CTA that makes it a multiple of the grid size decides
@@ -52,7 +55,10 @@ struct alignas(128) BlkSync {        // zeroed at lps_solve_begin; counters only
 };
 
 struct BlkPanel {
-    double* U;               // kBlkMax x upitch: U[l][i] = cell (i, c_l) just before pivot l (i = m: objective row)
+    double* U;               // upitch records of kBlkRec doubles, one per local row (record m: the objective row):
+                             //   [l] for l < kBlkMax = cell (row, c_l) just before pivot l, the row's multiplier in pivot l
+                             //   [kBlkMax] = two 32-bit masks: low, bit l = that multiplier is zero (the reference leaves
+                             //   the row alone, tableau.py:272); high, bit l = the row IS pivot l's row (replaced)
     size_t upitch;
     double* V;               // kBlkMax x ld: normalised pivot rows (lives in the exchange block: peers store into it)
     double* O[2];            // objective row, ping-pong by pivot parity (ld each)
@@ -133,7 +139,9 @@ __device__ __forceinline__ int pick_winner_cg(const XchgBlock* x, int par, int n
     return w;
 }
 
-__global__ void __launch_bounds__(kSelMaxThreads, 1) k_blk_panel(BlkPanelArgs a) {
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
+    constexpr int kBlkBatch = (NT > 512) ? 4 : 8;   // loads of earlier pivots' multipliers issued together (register budget)
     __shared__ ArgMinF64 s_arg[32];
     __shared__ int s_int[32];
     __shared__ double s_vc[kBlkMax];       // V[lp][c]: the entering column's cell in the earlier pivot rows
@@ -200,23 +208,44 @@ __global__ void __launch_bounds__(kSelMaxThreads, 1) k_blk_panel(BlkPanelArgs a)
         // ---- B: column c as it stands after the block's earlier pivots -> U[l]; ratio test ----
         if (tid < l) s_vc[tid] = __ldcg(&P.V[(size_t)tid * g.ld + c]);
         __syncthreads();
-        double* Ul = P.U + (size_t)l * P.upitch;
         ArgMinF64 best{0.0, INT_MAX};
         for (int i = cta * nt + tid; i < g.m; i += G * nt) {
             double x = g.T[(size_t)i * g.ld + c];
             const long long gi = g.row0 + i;
-            for (int lp = 0; lp < l; ++lp) {
-                if (s_R[lp] == gi) x = s_vc[lp];
-                else x = blk_apply(x, __ldcg(&P.U[(size_t)lp * P.upitch + i]), s_vc[lp]);
+            // the multipliers of the earlier pivots are independent loads: issued in batches, applied in order
+            for (int l0 = 0; l0 < l; l0 += kBlkBatch) {
+                double u[kBlkBatch];
+#pragma unroll
+                for (int q = 0; q < kBlkBatch; q += 2)
+                    if (l0 + q < l) {
+                        const double2 uu = ldcg2(P.U + (size_t)i * kBlkRec + l0 + q);
+                        u[q] = uu.x;
+                        u[q + 1] = uu.y;
+                    }
+#pragma unroll
+                for (int q = 0; q < kBlkBatch; ++q)
+                    if (l0 + q < l) x = (s_R[l0 + q] == gi) ? s_vc[l0 + q] : blk_apply(x, u[q], s_vc[l0 + q]);
             }
-            __stcg(&Ul[i], x);
+            {   // the row's record: multiplier of pivot l, zero-multiplier mask (a new block starts new masks)
+                double* rec = P.U + (size_t)i * kBlkRec;
+                __stcg(&rec[l], x);
+                uint2 mk = (l == 0) ? make_uint2(0u, 0u) : __ldcg(reinterpret_cast<const uint2*>(rec + kBlkMax));
+                if (x == 0.0) mk.x |= 1u << l;
+                if (l == 0 || x == 0.0) __stcg(reinterpret_cast<uint2*>(rec + kBlkMax), mk);
+            }
             if (x > 0.0) {
                 const double ratio = __ldcg(&Bc[i]) / x;
                 if (best.idx == INT_MAX || ratio < best.key) { best.key = ratio; best.idx = i; }
             }
         }
         const double uobj = __ldcg(&Oc[c]);                    // the objective row's cell of the entering column
-        if (cta == 0 && tid == 0) __stcg(&Ul[g.m], uobj);
+        if (cta == 0 && tid == 0) {
+            double* rec = P.U + (size_t)g.m * kBlkRec;
+            __stcg(&rec[l], uobj);
+            uint2 mk = (l == 0) ? make_uint2(0u, 0u) : __ldcg(reinterpret_cast<const uint2*>(rec + kBlkMax));
+            if (uobj == 0.0) mk.x |= 1u << l;
+            if (l == 0 || uobj == 0.0) __stcg(reinterpret_cast<uint2*>(rec + kBlkMax), mk);
+        }
         best = block_argmin(best, s_arg);
         seq += 1;
         if (tid == 0) {
@@ -284,24 +313,32 @@ __global__ void __launch_bounds__(kSelMaxThreads, 1) k_blk_panel(BlkPanelArgs a)
         double vn;                                              // the pivot row's right-hand side, normalised
         if (w == a.rank) {
             const int r_loc = (int)(r_g - g.row0);
-            if (tid < l) s_ur[tid] = __ldcg(&P.U[(size_t)tid * P.upitch + r_loc]);
+            if (tid < l) s_ur[tid] = __ldcg(&P.U[(size_t)r_loc * kBlkRec + tid]);
             __syncthreads();
-            const double inv = 1.0 / __ldcg(&Ul[r_loc]);      // rowDiv: ONE / d, then rowMult (tableau.py:262-267)
+            const double inv = 1.0 / __ldcg(&P.U[(size_t)r_loc * kBlkRec + l]);      // rowDiv: ONE / d, then rowMult (tableau.py:262-267)
             const double br = __ldcg(&Bc[r_loc]);
             vn = (inv != 1.0) ? __dmul_rn(br, inv) : br;
             const double* src = g.T + (size_t)r_loc * g.ld;
             for (int j = 2 * (cta * nt + tid); j < (int)g.ld; j += 2 * G * nt) {
                 double2 y = *reinterpret_cast<const double2*>(src + j);
-                for (int lp = 0; lp < l; ++lp) {
-                    const double2 v = ldcg2(P.V + (size_t)lp * g.ld + j);
-                    if (s_R[lp] == r_g) y = v;
-                    else { y.x = blk_apply(y.x, s_ur[lp], v.x); y.y = blk_apply(y.y, s_ur[lp], v.y); }
+                const double2 o_old = ldcg2(Oc + j);
+                for (int l0 = 0; l0 < l; l0 += kBlkBatch / 2) {
+                    double2 v[kBlkBatch / 2];
+#pragma unroll
+                    for (int q = 0; q < kBlkBatch / 2; ++q)
+                        if (l0 + q < l) v[q] = ldcg2(P.V + (size_t)(l0 + q) * g.ld + j);
+#pragma unroll
+                    for (int q = 0; q < kBlkBatch / 2; ++q) {
+                        if (l0 + q >= l) continue;
+                        if (s_R[l0 + q] == r_g) y = v[q];
+                        else { y.x = blk_apply(y.x, s_ur[l0 + q], v[q].x); y.y = blk_apply(y.y, s_ur[l0 + q], v[q].y); }
+                    }
                 }
                 if (inv != 1.0) { y.x = __dmul_rn(y.x, inv); y.y = __dmul_rn(y.y, inv); }   // rowMult skips a multiplier of 1
                 stcg2(Vl + j, y);
                 for (int k = 0; k < a.nranks; ++k)
                     if (k != a.rank) *reinterpret_cast<double2*>(xchg_vrow(a.peers[k]) + (size_t)l * g.ld + j) = y;
-                double2 o = ldcg2(Oc + j);
+                double2 o = o_old;
                 o.x = blk_apply(o.x, uobj, y.x);
                 o.y = blk_apply(o.y, uobj, y.y);
                 stcg2(On + j, o);
@@ -338,8 +375,13 @@ __global__ void __launch_bounds__(kSelMaxThreads, 1) k_blk_panel(BlkPanelArgs a)
         }
         for (int i = cta * nt + tid; i < g.m; i += G * nt) {
             double b;
-            if (g.row0 + i == r_g) b = vn;
-            else b = blk_apply(__ldcg(&Bc[i]), __ldcg(&Ul[i]), vn);
+            double* rec = P.U + (size_t)i * kBlkRec;
+            if (g.row0 + i == r_g) {
+                b = vn;
+                uint2 mk = __ldcg(reinterpret_cast<const uint2*>(rec + kBlkMax));   // this row is pivot l's row
+                mk.y |= 1u << l;
+                __stcg(reinterpret_cast<uint2*>(rec + kBlkMax), mk);
+            } else b = blk_apply(__ldcg(&Bc[i]), __ldcg(&rec[l]), vn);
             __stcg(&Bn[i], b);
         }
         pb = block_argmin(pb, s_arg);
@@ -410,130 +452,199 @@ __global__ void __launch_bounds__(kSelMaxThreads, 1) k_blk_panel(BlkPanelArgs a)
 // ------------------------------------------------------------------------------------------------
 // update: the block's pivots applied to every cell of the local rows in one pass
 // ------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised, one CTA per SM.  Work item = (512-column chunk, stage of 8 rows); every CTA owns a
+// contiguous range of the chunk-major item list.  One producer thread moves the items through a shared-memory ring
+// with TMA bulk copies: 8 row segments of the grid + the 8 rows' panel records in, 8 row segments out; 256 consumer
+// threads (one double2 column each, the chunk's 16 normalised pivot-row cells in registers) apply the block's pivots
+// to the stage in place.  HBM reads and writes never wait for the arithmetic and the fp64 pipe never waits for HBM
+// as long as the ring is deep enough: the grid is read once and written once per block.
 struct BlkUpdateArgs {
     F64Grid g;
     BlkPanel p;
-    int rows_per_cta;   // multiple of kBlkRU, <= kMaxRowBlock
-    int kcap;           // pivots the shared-memory layout was sized for
 };
 
-__host__ __device__ inline size_t blk_update_smem(int kcap, int rows_per_cta) {
-    return (size_t)kcap * (kBlkCW + rows_per_cta) * sizeof(double) + 2 * (size_t)rows_per_cta * sizeof(unsigned) +
-           (size_t)(rows_per_cta / kBlkRU) * sizeof(unsigned) + 16;
-}
+struct BlkRing {                                  // dynamic shared memory of k_blk_update
+    double t[kBlkStages][kBlkRU][kBlkCW];         // ring: stage rows of the grid
+    double u[kBlkStages][kBlkRU * kBlkRec];       // ring: the rows' panel records
+    double v[kBlkMax][kBlkCW];                    // the chunk's cells of the block's normalised pivot rows
+    uint64_t full[kBlkStages];                    // producer -> consumers: stage landed (TMA transaction bytes)
+    uint64_t done[kBlkStages];                    // consumers -> producer: stage updated in place (one arrival per warp)
+    uint64_t vfull;                               // producer -> consumers: v holds the next chunk
+    uint64_t vdone;                               // consumers -> producer: v is no longer needed (chunk finished)
+};
 
-template <bool STREAM>
-__global__ void __launch_bounds__(kThreads, 2) k_blk_update(BlkUpdateArgs a) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared -> global bulk copy, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kBlkConsumers + 32, 1) k_blk_update(BlkUpdateArgs a) {
     extern __shared__ __align__(128) unsigned char blk_smem[];
+    BlkRing& S = *reinterpret_cast<BlkRing*>(blk_smem);
     const BlkPanel& P = a.p;
     const F64Grid& g = a.g;
     const int kk = P.hdr[0];
     if (kk <= 0) return;
-    const int RB = a.rows_per_cta;
-    double* s_v = reinterpret_cast<double*>(blk_smem);                 // kk x kBlkCW
-    double* s_u = s_v + (size_t)a.kcap * kBlkCW;                        // kk x RB
-    unsigned* s_spec = reinterpret_cast<unsigned*>(s_u + (size_t)a.kcap * RB);   // per row: bit l = this row is pivot l's row
-    unsigned* s_zero = s_spec + RB;                                     // per row: bit l = multiplier of pivot l is 0
-    unsigned* s_grp = s_zero + RB;                                      // per group of kBlkRU rows: any special / zero bit
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + RB / kBlkRU + ((RB / kBlkRU) & 1));
-
     const int tid = (int)threadIdx.x;
-    const int col0 = blockIdx.x * kBlkCW;
-    const int row0 = blockIdx.y * RB;
     const int mrows = g.m + 1;
-    const int ncols = min(kBlkCW, (int)g.ld - col0);
-    const int nrows = min(RB, mrows - row0);
+    const long long nst = (mrows + kBlkRU - 1) / kBlkRU;                    // stages per chunk
+    const long long nchunk = ((long long)g.ld + kBlkCW - 1) / kBlkCW;
+    const long long W = nst * nchunk;
+    const long long it0 = W * blockIdx.x / gridDim.x, it1 = W * (blockIdx.x + 1) / gridDim.x;
+    if (it0 >= it1) return;
 
     if (tid == 0) {
-        mbar_init(s_bar, 1);
+        for (int s = 0; s < kBlkStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.done[s], kBlkConsumers / 32); }
+        mbar_init(&S.vfull, 1);
+        mbar_init(&S.vdone, kBlkConsumers / 32);
         mbar_fence_init();
-        const uint32_t vb = (uint32_t)ncols * 8u, ub = (uint32_t)RB * 8u;
-        mbar_expect_tx(s_bar, (uint32_t)kk * (vb + ub));
-        for (int l = 0; l < kk; ++l) {
-            tma_load_1d(s_v + (size_t)l * kBlkCW, P.V + (size_t)l * g.ld + col0, vb, s_bar);
-            tma_load_1d(s_u + (size_t)l * RB, P.U + (size_t)l * P.upitch + row0, ub, s_bar);
-        }
     }
     __syncthreads();
-    mbar_wait(s_bar, 0);
 
-    // per-row masks: which pivots replace the row (it is their pivot row), which leave it alone (zero multiplier)
-    for (int il = tid; il < RB; il += kThreads) {
-        unsigned spec = 0, zero = 0;
-        if (il < nrows) {
-            const long long gi = (row0 + il < g.m) ? g.row0 + row0 + il : -1;   // the objective row is nobody's pivot row
-            for (int l = 0; l < kk; ++l) {
-                if (gi >= 0 && (long long)P.R[l] == gi) spec |= 1u << l;
-                const unsigned long long bits = (unsigned long long)__double_as_longlong(s_u[(size_t)l * RB + il]);
-                if ((bits << 1) == 0ull) zero |= 1u << l;
+    if (tid >= kBlkConsumers) {
+        // ---------------- producer: one thread ----------------
+        if (tid != kBlkConsumers) return;
+        long long chunk_loaded = -1;
+        int vphase = 0;                       // chunks loaded so far (parity of vfull / vdone)
+        auto load_item = [&](long long it, long long q) {
+            const long long chunk = it / nst, st = it - chunk * nst;
+            const int slot = (int)(q % kBlkStages);
+            const int col0 = (int)(chunk * kBlkCW);
+            const int ncols = min(kBlkCW, (int)g.ld - col0);
+            const int r0 = (int)(st * kBlkRU);
+            const int nr = min(kBlkRU, mrows - r0);
+            if (chunk != chunk_loaded) {
+                // a new chunk: the consumers must be through with the old pivot-row cells (they hold them in registers
+                // after reading v once, and say so on vdone)
+                if (chunk_loaded >= 0) mbar_spin(&S.vdone, (uint32_t)((vphase - 1) & 1));
+                mbar_expect_tx(&S.vfull, (uint32_t)kk * (uint32_t)ncols * 8u);
+                for (int l = 0; l < kk; ++l) tma_load_1d(&S.v[l][0], P.V + (size_t)l * g.ld + col0, (uint32_t)ncols * 8u, &S.vfull);
+                chunk_loaded = chunk;
+                ++vphase;
+            }
+            mbar_expect_tx(&S.full[slot], (uint32_t)nr * (uint32_t)ncols * 8u + (uint32_t)(kBlkRU * kBlkRec * 8));
+            tma_load_1d(&S.u[slot][0], P.U + (size_t)r0 * kBlkRec, (uint32_t)(kBlkRU * kBlkRec * 8), &S.full[slot]);
+            for (int r = 0; r < nr; ++r)
+                tma_load_1d(&S.t[slot][r][0], g.T + (size_t)(r0 + r) * g.ld + col0, (uint32_t)ncols * 8u, &S.full[slot]);
+        };
+        auto store_item = [&](long long it, long long q) {
+            const long long chunk = it / nst, st = it - chunk * nst;
+            const int slot = (int)(q % kBlkStages);
+            const int col0 = (int)(chunk * kBlkCW);
+            const int ncols = min(kBlkCW, (int)g.ld - col0);
+            const int r0 = (int)(st * kBlkRU);
+            const int nr = min(kBlkRU, mrows - r0);
+            for (int r = 0; r < nr; ++r)
+                tma_store_1d(g.T + (size_t)(r0 + r) * g.ld + col0, &S.t[slot][r][0], (uint32_t)ncols * 8u);
+            tma_commit();
+        };
+        const long long n = it1 - it0;
+        for (long long q = 0; q < n && q < kBlkStages; ++q) load_item(it0 + q, q);
+        for (long long q = 0; q < n; ++q) {
+            const int slot = (int)(q % kBlkStages);
+            mbar_spin(&S.done[slot], (uint32_t)((q / kBlkStages) & 1));
+            store_item(it0 + q, q);
+            // refill the slot of the PREVIOUS item: its store (one bulk group older) has finished reading shared memory
+            if (q >= 1 && q - 1 + kBlkStages < n) {
+                tma_wait_read<1>();
+                load_item(it0 + q - 1 + kBlkStages, q - 1 + kBlkStages);
             }
         }
-        s_spec[il] = spec;
-        s_zero[il] = zero;
+        tma_wait_all<0>();
+        return;
     }
-    __syncthreads();
-    for (int gq = tid; gq < RB / kBlkRU; gq += kThreads) {
-        unsigned f = 0;
-        for (int q = 0; q < kBlkRU; ++q) f |= s_spec[gq * kBlkRU + q] | s_zero[gq * kBlkRU + q];
-        s_grp[gq] = f;
-    }
-    __syncthreads();
 
+    // ---------------- consumers: 8 warps, thread = one double2 column of the chunk ----------------
     const int jl = 2 * tid;
-    if (jl >= ncols) return;
-    double* base = g.T + (size_t)row0 * g.ld + col0 + jl;
-    const double* sv = s_v + jl;
-
-    double2 ta[kBlkRU], tb[kBlkRU];
-    auto load = [&](double2 (&t)[kBlkRU], int rg) {
+    double2 v[kBlkMax];
+    long long chunk_have = -1;
+    int vphase = 0;
+    const long long n = it1 - it0;
+    for (long long q = 0; q < n; ++q) {
+        const long long it = it0 + q;
+        const long long chunk = it / nst;
+        const int slot = (int)(q % kBlkStages);
+        if (chunk != chunk_have) {
+            mbar_spin(&S.vfull, (uint32_t)(vphase & 1));
+            ++vphase;
 #pragma unroll
-        for (int q = 0; q < kBlkRU; ++q)
-            if (rg + q < nrows) t[q] = ld_f64x2<STREAM>(base + (size_t)(rg + q) * g.ld);
-    };
-    auto work = [&](double2 (&t)[kBlkRU], int rg) {
-        if (s_grp[rg / kBlkRU] == 0) {
-            // the common case: every pivot of the block touches every row of the group
-            for (int l = 0; l < kk; ++l) {
-                const double2 v = *reinterpret_cast<const double2*>(sv + (size_t)l * kBlkCW);
-                const double2* up = reinterpret_cast<const double2*>(s_u + (size_t)l * RB + rg);
+            for (int l = 0; l < kBlkMax; ++l) v[l] = (l < kk) ? *reinterpret_cast<const double2*>(&S.v[l][jl]) : make_double2(0.0, 0.0);
+            chunk_have = chunk;
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&S.vdone);
+        }
+        mbar_spin(&S.full[slot], (uint32_t)((q / kBlkStages) & 1));
+        const double* rec = &S.u[slot][0];
+        unsigned any = 0;
 #pragma unroll
-                for (int q2 = 0; q2 < kBlkRU / 2; ++q2) {
-                    const double2 u = up[q2];
-                    t[2 * q2].x = __dadd_rn(t[2 * q2].x, __dmul_rn(-u.x, v.x));
-                    t[2 * q2].y = __dadd_rn(t[2 * q2].y, __dmul_rn(-u.x, v.y));
-                    t[2 * q2 + 1].x = __dadd_rn(t[2 * q2 + 1].x, __dmul_rn(-u.y, v.x));
-                    t[2 * q2 + 1].y = __dadd_rn(t[2 * q2 + 1].y, __dmul_rn(-u.y, v.y));
-                }
-            }
+        for (int r = 0; r < kBlkRU; ++r) {
+            const uint2 mk = *reinterpret_cast<const uint2*>(rec + r * kBlkRec + kBlkMax);
+            any |= mk.x | mk.y;
+        }
+        double2 t[kBlkRU];
 #pragma unroll
-            for (int q = 0; q < kBlkRU; ++q)
-                if (rg + q < nrows) st_f64x2<STREAM>(base + (size_t)(rg + q) * g.ld, t[q]);
-        } else {
+        for (int r = 0; r < kBlkRU; ++r) t[r] = *reinterpret_cast<const double2*>(&S.t[slot][r][jl]);
+        if ((any & ((kk >= 32) ? 0xffffffffu : ((1u << kk) - 1u))) == 0) {
+            // the common case: every pivot of the block touches every row of the stage
 #pragma unroll
-            for (int q = 0; q < kBlkRU; ++q) {
-                if (rg + q >= nrows) continue;
-                const unsigned spec = s_spec[rg + q], zero = s_zero[rg + q];
-                bool dirty = false;
-                for (int l = 0; l < kk; ++l) {
-                    const double2 v = *reinterpret_cast<const double2*>(sv + (size_t)l * kBlkCW);
-                    if ((spec >> l) & 1u) { t[q] = v; dirty = true; }
-                    else if (!((zero >> l) & 1u)) {
-                        const double u = s_u[(size_t)l * RB + rg + q];
-                        t[q].x = __dadd_rn(t[q].x, __dmul_rn(-u, v.x));
-                        t[q].y = __dadd_rn(t[q].y, __dmul_rn(-u, v.y));
-                        dirty = true;
+            for (int l = 0; l < kBlkMax; ++l) {
+                if (l < kk) {
+#pragma unroll
+                    for (int r = 0; r < kBlkRU; ++r) {
+                        const double u = rec[r * kBlkRec + l];
+                        t[r].x = __dadd_rn(t[r].x, __dmul_rn(-u, v[l].x));
+                        t[r].y = __dadd_rn(t[r].y, __dmul_rn(-u, v[l].y));
                     }
                 }
-                if (dirty) st_f64x2<STREAM>(base + (size_t)(rg + q) * g.ld, t[q]);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kBlkRU; ++r) {
+                const uint2 mk = *reinterpret_cast<const uint2*>(rec + r * kBlkRec + kBlkMax);
+#pragma unroll
+                for (int l = 0; l < kBlkMax; ++l) {
+                    if (l < kk) {
+                        if ((mk.y >> l) & 1u) t[r] = v[l];
+                        else if (!((mk.x >> l) & 1u)) {
+                            const double u = rec[r * kBlkRec + l];
+                            t[r].x = __dadd_rn(t[r].x, __dmul_rn(-u, v[l].x));
+                            t[r].y = __dadd_rn(t[r].y, __dmul_rn(-u, v[l].y));
+                        }
+                    }
+                }
             }
         }
-    };
-    load(ta, 0);
-    for (int rg = 0; rg < nrows; rg += 2 * kBlkRU) {
-        if (rg + kBlkRU < nrows) load(tb, rg + kBlkRU);
-        work(ta, rg);
-        if (rg + 2 * kBlkRU < nrows) load(ta, rg + 2 * kBlkRU);
-        if (rg + kBlkRU < nrows) work(tb, rg + kBlkRU);
+#pragma unroll
+        for (int r = 0; r < kBlkRU; ++r) *reinterpret_cast<double2*>(&S.t[slot][r][jl]) = t[r];
+        fence_proxy_async();                  // the TMA store (async proxy) must see these writes
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&S.done[slot]);
     }
 }
 

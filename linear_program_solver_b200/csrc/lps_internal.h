@@ -72,7 +72,7 @@ struct lps_handle {
 
     // pivots in blocks (lps_f64_blk.cuh): the look-ahead panel and the fused update
     int blk_k = kBlkMax;             // pivots decided per panel launch (1..kBlkMax); 0: rank-1 path only
-    int blk_rows = 128;              // rows per CTA of the fused update
+    int sms = 148;                   // SMs of the device: size of the persistent grids
     int pan_blocks = 1, pan_threads = 256;
     BlkPanel blk{};
     bool blk_valid = false;          // O / B / pricing partials of the panel describe the grid

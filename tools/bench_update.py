@@ -56,10 +56,13 @@ def main():
     wall = time.perf_counter() - t0
     ms, nu, na = eng.prof_read() if not a.no_prof else (0.0, 0, 0)
     bytes_per = 16 * (m + 1) * (n + 1) + 8 * (m + 1) + 8 * (n + 1)
-    out = {"m": m, "n": n, "status": st, "pivots": k, "wall_s": wall, "pivots_per_s": k / wall,
+    kb = eng.block_size()
+    # one update launch applies up to kb pivots (kb = 0: the rank-1 loop): bytes the launch has to move
+    bytes_launch = 16 * (m + 1) * (n + 1) + max(kb, 1) * (8 * (m + 1) + 8 * (n + 1))
+    out = {"m": m, "n": n, "block": kb, "status": st, "pivots": k, "wall_s": wall, "pivots_per_s": k / wall,
            "update_ms_avg": ms / max(nu, 1), "update_launches_timed": nu, "launches": na,
-           "update_GBps": bytes_per / (ms / max(nu, 1) * 1e-3) / 1e9 if nu else None,
-           "loop_GBps": bytes_per * k / wall / 1e9}
+           "update_GBps": bytes_launch / (ms / max(nu, 1) * 1e-3) / 1e9 if nu else None,
+           "rank1_equivalent_GBps": bytes_per * k / wall / 1e9}
     print(json.dumps(out))
 
 
