@@ -37,7 +37,7 @@ constexpr int kBlkMax = 16;   // pivots per block (upper bound; the fp64 pipe sa
 constexpr int kBlkCW = 512;   // columns per update tile: 256 threads x one double2
 constexpr int kBlkRU = 8;     // rows per stage of the fused update
 constexpr int kBlkRec = kBlkMax + 2;   // doubles per row record of the panel's U (16-byte multiple: TMA source)
-constexpr int kBlkStages = 4;          // stages of the update's shared-memory ring
+constexpr int kBlkStages = 6;          // stages of the update's shared-memory ring
 constexpr int kBlkConsumers = 256;     // consumer threads of the fused update (one double2 column each)
 
 struct alignas(128) BlkSync {        // zeroed at lps_solve_begin; counters only ever grow
@@ -466,11 +466,8 @@ struct BlkUpdateArgs {
 struct BlkRing {                                  // dynamic shared memory of k_blk_update
     double t[kBlkStages][kBlkRU][kBlkCW];         // ring: stage rows of the grid
     double u[kBlkStages][kBlkRU * kBlkRec];       // ring: the rows' panel records
-    double v[kBlkMax][kBlkCW];                    // the chunk's cells of the block's normalised pivot rows
     uint64_t full[kBlkStages];                    // producer -> consumers: stage landed (TMA transaction bytes)
     uint64_t done[kBlkStages];                    // consumers -> producer: stage updated in place (one arrival per warp)
-    uint64_t vfull;                               // producer -> consumers: v holds the next chunk
-    uint64_t vdone;                               // consumers -> producer: v is no longer needed (chunk finished)
 };
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
@@ -521,8 +518,6 @@ __global__ void __launch_bounds__(kBlkConsumers + 32, 1) k_blk_update(BlkUpdateA
 
     if (tid == 0) {
         for (int s = 0; s < kBlkStages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.done[s], kBlkConsumers / 32); }
-        mbar_init(&S.vfull, 1);
-        mbar_init(&S.vdone, kBlkConsumers / 32);
         mbar_fence_init();
     }
     __syncthreads();
@@ -530,8 +525,6 @@ __global__ void __launch_bounds__(kBlkConsumers + 32, 1) k_blk_update(BlkUpdateA
     if (tid >= kBlkConsumers) {
         // ---------------- producer: one thread ----------------
         if (tid != kBlkConsumers) return;
-        long long chunk_loaded = -1;
-        int vphase = 0;                       // chunks loaded so far (parity of vfull / vdone)
         auto load_item = [&](long long it, long long q) {
             const long long chunk = it / nst, st = it - chunk * nst;
             const int slot = (int)(q % kBlkStages);
@@ -539,15 +532,6 @@ __global__ void __launch_bounds__(kBlkConsumers + 32, 1) k_blk_update(BlkUpdateA
             const int ncols = min(kBlkCW, (int)g.ld - col0);
             const int r0 = (int)(st * kBlkRU);
             const int nr = min(kBlkRU, mrows - r0);
-            if (chunk != chunk_loaded) {
-                // a new chunk: the consumers must be through with the old pivot-row cells (they hold them in registers
-                // after reading v once, and say so on vdone)
-                if (chunk_loaded >= 0) mbar_spin(&S.vdone, (uint32_t)((vphase - 1) & 1));
-                mbar_expect_tx(&S.vfull, (uint32_t)kk * (uint32_t)ncols * 8u);
-                for (int l = 0; l < kk; ++l) tma_load_1d(&S.v[l][0], P.V + (size_t)l * g.ld + col0, (uint32_t)ncols * 8u, &S.vfull);
-                chunk_loaded = chunk;
-                ++vphase;
-            }
             mbar_expect_tx(&S.full[slot], (uint32_t)nr * (uint32_t)ncols * 8u + (uint32_t)(kBlkRU * kBlkRec * 8));
             tma_load_1d(&S.u[slot][0], P.U + (size_t)r0 * kBlkRec, (uint32_t)(kBlkRU * kBlkRec * 8), &S.full[slot]);
             for (int r = 0; r < nr; ++r)
@@ -582,22 +566,20 @@ __global__ void __launch_bounds__(kBlkConsumers + 32, 1) k_blk_update(BlkUpdateA
 
     // ---------------- consumers: 8 warps, thread = one double2 column of the chunk ----------------
     const int jl = 2 * tid;
-    double2 v[kBlkMax];
+    double2 v[kBlkMax];                       // this column's cells of the block's normalised pivot rows
     long long chunk_have = -1;
-    int vphase = 0;
     const long long n = it1 - it0;
+    const unsigned kmask = (1u << kk) - 1u;   // kk <= 16
     for (long long q = 0; q < n; ++q) {
         const long long it = it0 + q;
         const long long chunk = it / nst;
         const int slot = (int)(q % kBlkStages);
         if (chunk != chunk_have) {
-            mbar_spin(&S.vfull, (uint32_t)(vphase & 1));
-            ++vphase;
+            const int col = (int)(chunk * kBlkCW) + jl;
 #pragma unroll
-            for (int l = 0; l < kBlkMax; ++l) v[l] = (l < kk) ? *reinterpret_cast<const double2*>(&S.v[l][jl]) : make_double2(0.0, 0.0);
+            for (int l = 0; l < kBlkMax; ++l)
+                v[l] = (l < kk && col < (int)g.ld) ? ldcg2(P.V + (size_t)l * g.ld + col) : make_double2(0.0, 0.0);
             chunk_have = chunk;
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&S.vdone);
         }
         mbar_spin(&S.full[slot], (uint32_t)((q / kBlkStages) & 1));
         const double* rec = &S.u[slot][0];
@@ -610,8 +592,33 @@ __global__ void __launch_bounds__(kBlkConsumers + 32, 1) k_blk_update(BlkUpdateA
         double2 t[kBlkRU];
 #pragma unroll
         for (int r = 0; r < kBlkRU; ++r) t[r] = *reinterpret_cast<const double2*>(&S.t[slot][r][jl]);
-        if ((any & ((kk >= 32) ? 0xffffffffu : ((1u << kk) - 1u))) == 0) {
-            // the common case: every pivot of the block touches every row of the stage
+        if (kk == kBlkMax && (any & kmask) == 0) {
+            // the common case: a full block, and every pivot of it touches every row of the stage.  Branch free; the
+            // multipliers of the next two pivots are fetched while the current two are applied.
+            double2 ua[kBlkRU], ub[kBlkRU];
+#pragma unroll
+            for (int r = 0; r < kBlkRU; ++r) ua[r] = *reinterpret_cast<const double2*>(rec + r * kBlkRec);
+#pragma unroll
+            for (int l = 0; l < kBlkMax; l += 2) {
+                if (l + 2 < kBlkMax) {
+#pragma unroll
+                    for (int r = 0; r < kBlkRU; ++r) ub[r] = *reinterpret_cast<const double2*>(rec + r * kBlkRec + l + 2);
+                }
+#pragma unroll
+                for (int r = 0; r < kBlkRU; ++r) {
+                    t[r].x = __dadd_rn(t[r].x, __dmul_rn(-ua[r].x, v[l].x));
+                    t[r].y = __dadd_rn(t[r].y, __dmul_rn(-ua[r].x, v[l].y));
+                }
+#pragma unroll
+                for (int r = 0; r < kBlkRU; ++r) {
+                    t[r].x = __dadd_rn(t[r].x, __dmul_rn(-ua[r].y, v[l + 1].x));
+                    t[r].y = __dadd_rn(t[r].y, __dmul_rn(-ua[r].y, v[l + 1].y));
+                }
+#pragma unroll
+                for (int r = 0; r < kBlkRU; ++r) ua[r] = ub[r];
+            }
+        } else if ((any & kmask) == 0) {
+            // a short block (the end of a solve or of a pivot prefix): the uniform test on the block length only
 #pragma unroll
             for (int l = 0; l < kBlkMax; ++l) {
                 if (l < kk) {
@@ -624,18 +631,26 @@ __global__ void __launch_bounds__(kBlkConsumers + 32, 1) k_blk_update(BlkUpdateA
                 }
             }
         } else {
+            // rows with a zero multiplier (left alone, tableau.py:272) / pivot rows (replaced by the normalised row): the
+            // same arithmetic, its result selected per row and pivot from the masks -- no divergent control flow
+            unsigned mz[kBlkRU], ms[kBlkRU];
 #pragma unroll
             for (int r = 0; r < kBlkRU; ++r) {
                 const uint2 mk = *reinterpret_cast<const uint2*>(rec + r * kBlkRec + kBlkMax);
+                mz[r] = mk.x;
+                ms[r] = mk.y;
+            }
 #pragma unroll
-                for (int l = 0; l < kBlkMax; ++l) {
-                    if (l < kk) {
-                        if ((mk.y >> l) & 1u) t[r] = v[l];
-                        else if (!((mk.x >> l) & 1u)) {
-                            const double u = rec[r * kBlkRec + l];
-                            t[r].x = __dadd_rn(t[r].x, __dmul_rn(-u, v[l].x));
-                            t[r].y = __dadd_rn(t[r].y, __dmul_rn(-u, v[l].y));
-                        }
+            for (int l = 0; l < kBlkMax; ++l) {
+                if (l < kk) {
+#pragma unroll
+                    for (int r = 0; r < kBlkRU; ++r) {
+                        const double u = rec[r * kBlkRec + l];
+                        const double nx = __dadd_rn(t[r].x, __dmul_rn(-u, v[l].x));
+                        const double ny = __dadd_rn(t[r].y, __dmul_rn(-u, v[l].y));
+                        const bool spec = (ms[r] >> l) & 1u, zero = (mz[r] >> l) & 1u;
+                        t[r].x = spec ? v[l].x : (zero ? t[r].x : nx);
+                        t[r].y = spec ? v[l].y : (zero ? t[r].y : ny);
                     }
                 }
             }
