@@ -188,7 +188,7 @@ int lps_step_update(lps_handle *h);
  * reference's order and rounding (tableau.py:295-308).  Results are bit-identical to pivot-by-pivot updates; the grid
  * is read and written once per block instead of once per pivot.  On a row-sharded handle (after lps_p2p_attach) the
  * panel does the per-pivot argmin all-reduce and pivot-row broadcast with peer stores, like lps_step_select.
- * lps_set_block_size: 1..16 pivots per block, 0 = lps_solve falls back to the rank-1 loop (default 16, or the
+ * lps_set_block_size: 1..16 pivots per block, 0 = lps_solve runs the rank-1 loop (default: 16 from 1.5 M cells on, 0 below; or the
  * environment variable LPS_F64_BLOCK). */
 int lps_step_block(lps_handle *h);
 int lps_block_size(lps_handle *h);

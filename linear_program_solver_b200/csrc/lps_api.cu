@@ -96,16 +96,25 @@ static void plan(lps_handle* h) {
     // more CTAs than SMs.  Small tableaux: one CTA of 1024 threads (barriers are __syncthreads).
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
-    if (h->m <= 8 * kSelMaxThreads && h->ld <= 16 * kSelMaxThreads) { h->pan_blocks = 1; h->pan_threads = kSelMaxThreads; }
+    // (measured, profiles/r02d_panel_shapes.txt: at 2000 x 4000 eight CTAs of 256 threads decide a pivot in 15 us, the
+    // one-CTA panel in 25 us; at 500 x 1000 and below the one-CTA panel is the faster one)
+    if (h->m < 1024 && h->ld < 2048) { h->pan_blocks = 1; h->pan_threads = kSelMaxThreads; }
     else {
         h->pan_threads = kThreads;
         h->pan_blocks = std::max(2, std::min(std::max((h->m + kThreads - 1) / kThreads, (int)((h->ld / 2 + kThreads - 1) / kThreads)), std::min(sms, 256)));
     }
     h->sel_blocks = std::min(h->sel_blocks, sms);
     h->sms = sms;
-    h->blk_k = kBlkMax;
+    // Blocks pay once a pass over the grid costs more than the panel's latency per pivot (~15 us): from about a
+    // million cells on.  Below that the rank-1 loop (two short launches per pivot, replayed as a graph) is faster
+    // (500 x 1000: 82 k pivots/s against 68 k in blocks) and stays the default.
+    h->blk_k = ((size_t)(h->m + 1) * h->ld >= (size_t)1500000) ? kBlkMax : 0;
     if (const char* e = getenv("LPS_F64_BLOCK")) { const int v = atoi(e); if (v >= 0 && v <= kBlkMax) h->blk_k = v; }
-    if (const char* e = getenv("LPS_F64_PANEL_CTAS")) { const int v = atoi(e); if (v >= 2 && v <= sms && h->pan_blocks > 1) h->pan_blocks = v; }
+    if (const char* e = getenv("LPS_F64_PANEL_CTAS")) {   // tuning: 1 = one CTA of 1024 threads, >= 2 = that many CTAs of 256
+        const int v = atoi(e);
+        if (v == 1) { h->pan_blocks = 1; h->pan_threads = kSelMaxThreads; }
+        else if (v >= 2 && v <= std::min(sms, 256)) { h->pan_blocks = v; h->pan_threads = kThreads; }
+    }
 }
 
 extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* stream, lps_handle** out) {

@@ -77,24 +77,37 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
 __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// spin until *p >= want; false after ten seconds (a peer died or never enqueued this pivot: do not hang the GPU)
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *p >= want; false after ten seconds (a peer died or never enqueued this pivot: do not hang the GPU).
+// The polls are relaxed loads (an acquire load invalidates L1 on every poll); one acquire fence follows the hit.
 __device__ __forceinline__ bool wait_seq(const unsigned long long* p, unsigned long long want) {
     if (ld_acquire_sys(p) >= want) return true;
     const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(p) < want) {
-        if (global_ns() - t0 > 10000000000ull) return false;
-        __nanosleep(32);
+    unsigned int polls = 0;
+    while (ld_relaxed_sys(p) < want) {
+        if ((++polls & 1023u) == 0 && global_ns() - t0 > 10000000000ull) return false;
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
     return true;
 }
 // same on a flag raised by another CTA of this kernel (twenty seconds: outlasts wait_seq)
 __device__ __forceinline__ bool wait_seq_gpu(const unsigned long long* p, unsigned long long want) {
     if (ld_acquire_gpu(p) >= want) return true;
     const unsigned long long t0 = global_ns();
-    while (ld_acquire_gpu(p) < want) {
-        if (global_ns() - t0 > 20000000000ull) return false;
-        __nanosleep(20);
+    unsigned int polls = 0;
+    while (ld_relaxed_gpu(p) < want) {
+        if ((++polls & 1023u) == 0 && global_ns() - t0 > 20000000000ull) return false;
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     return true;
 }
 

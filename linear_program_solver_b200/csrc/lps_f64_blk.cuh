@@ -206,11 +206,17 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
         if (c == INT_MAX) { status = LPS_OPTIMAL; break; }
 
         // ---- B: column c as it stands after the block's earlier pivots -> U[l]; ratio test ----
+        // (the first row's loads are issued before the block waits for the column's cells of the earlier pivot rows)
+        const int i_first = cta * nt + tid;
+        double x_first = 0.0, b_first = 0.0;
+        if (i_first < g.m) { x_first = g.T[(size_t)i_first * g.ld + c]; b_first = __ldcg(&Bc[i_first]); }
         if (tid < l) s_vc[tid] = __ldcg(&P.V[(size_t)tid * g.ld + c]);
+        const double uobj = __ldcg(&Oc[c]);                    // the objective row's cell of the entering column
         __syncthreads();
         ArgMinF64 best{0.0, INT_MAX};
-        for (int i = cta * nt + tid; i < g.m; i += G * nt) {
-            double x = g.T[(size_t)i * g.ld + c];
+        for (int i = i_first; i < g.m; i += G * nt) {
+            double x = (i == i_first) ? x_first : g.T[(size_t)i * g.ld + c];
+            const double bi = (i == i_first) ? b_first : __ldcg(&Bc[i]);
             const long long gi = g.row0 + i;
             // the multipliers of the earlier pivots are independent loads: issued in batches, applied in order
             for (int l0 = 0; l0 < l; l0 += kBlkBatch) {
@@ -234,11 +240,10 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
                 if (l == 0 || x == 0.0) __stcg(reinterpret_cast<uint2*>(rec + kBlkMax), mk);
             }
             if (x > 0.0) {
-                const double ratio = __ldcg(&Bc[i]) / x;
+                const double ratio = bi / x;
                 if (best.idx == INT_MAX || ratio < best.key) { best.key = ratio; best.idx = i; }
             }
         }
-        const double uobj = __ldcg(&Oc[c]);                    // the objective row's cell of the entering column
         if (cta == 0 && tid == 0) {
             double* rec = P.U + (size_t)g.m * kBlkRec;
             __stcg(&rec[l], uobj);
@@ -313,15 +318,19 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
         double vn;                                              // the pivot row's right-hand side, normalised
         if (w == a.rank) {
             const int r_loc = (int)(r_g - g.row0);
-            if (tid < l) s_ur[tid] = __ldcg(&P.U[(size_t)r_loc * kBlkRec + tid]);
-            __syncthreads();
-            const double inv = 1.0 / __ldcg(&P.U[(size_t)r_loc * kBlkRec + l]);      // rowDiv: ONE / d, then rowMult (tableau.py:262-267)
-            const double br = __ldcg(&Bc[r_loc]);
-            vn = (inv != 1.0) ? __dmul_rn(br, inv) : br;
             const double* src = g.T + (size_t)r_loc * g.ld;
-            for (int j = 2 * (cta * nt + tid); j < (int)g.ld; j += 2 * G * nt) {
-                double2 y = *reinterpret_cast<const double2*>(src + j);
-                const double2 o_old = ldcg2(Oc + j);
+            const int j_first = 2 * (cta * nt + tid);
+            double2 y_first = make_double2(0.0, 0.0), o_first = make_double2(0.0, 0.0);
+            if (j_first < (int)g.ld) { y_first = *reinterpret_cast<const double2*>(src + j_first); o_first = ldcg2(Oc + j_first); }
+            if (tid < l) s_ur[tid] = __ldcg(&P.U[(size_t)r_loc * kBlkRec + tid]);
+            const double pv = __ldcg(&P.U[(size_t)r_loc * kBlkRec + l]);
+            const double br = __ldcg(&Bc[r_loc]);
+            __syncthreads();
+            const double inv = 1.0 / pv;                        // rowDiv: ONE / d, then rowMult (tableau.py:262-267)
+            vn = (inv != 1.0) ? __dmul_rn(br, inv) : br;
+            for (int j = j_first; j < (int)g.ld; j += 2 * G * nt) {
+                double2 y = (j == j_first) ? y_first : *reinterpret_cast<const double2*>(src + j);
+                const double2 o_old = (j == j_first) ? o_first : ldcg2(Oc + j);
                 for (int l0 = 0; l0 < l; l0 += kBlkBatch / 2) {
                     double2 v[kBlkBatch / 2];
 #pragma unroll

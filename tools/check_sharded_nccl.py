@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--rows", type=int, default=512)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p")
+    ap.add_argument("--block", type=int, default=None, help="pivots per block with the peer-store exchange (0: rank-1 loop)")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -28,7 +29,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m, n = a.rows, 2 * a.rows
-    sv = ShardedF64Solver(m, n, rank, world, device=local, exchange=a.exchange)
+    sv = ShardedF64Solver(m, n, rank, world, device=local, exchange=a.exchange, block=a.block)
     sv.eng.fill_dense(a.seed, 1, 9)
     basis = np.arange(m, n, dtype=np.int32)
     st, k, trace = sv.solve(basis, None, trace_cap=1 << 20)
@@ -41,7 +42,7 @@ def main():
     flag = torch.tensor([1 if good else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"sharded check ({a.exchange} exchange): world={world} m={m} pivots={k} status={st} -> {'OK' if flag.item() else 'MISMATCH'}", flush=True)
+        print(f"sharded check ({a.exchange} exchange, block {sv.block}): world={world} m={m} pivots={k} status={st} -> {'OK' if flag.item() else 'MISMATCH'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
 

@@ -1,16 +1,18 @@
 #!/bin/bash
-# Multi-GPU pass (gpurun --gpus N): parity of the row-sharded solver with both exchanges, then the C4 bench at N
-# with the peer-store exchange and with the NCCL all-gather.  Everything lands in gpurun_out/.
+# Multi-GPU pass (gpurun --gpus N): parity of the row-sharded solver (blocked loop with peer stores, rank-1 loop with
+# peer stores, rank-1 loop with the NCCL all-gather), then the C4 bench at N.  Everything lands in gpurun_out/.
 set -u
 N=${1:-2}
+TAG=${2:-r02}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 600 python -m pytest tests/test_f64_engine_gpu.py tests/test_api_fp64_gpu.py tests/test_sharded_gpu.py -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_f64_multi.log
-for X in p2p nccl; do
-  timeout 300 $TR --master-port 29511 tools/check_sharded_nccl.py --rows 512 --exchange $X 2>&1 | grep -v "^W\|^\*\*\*" | tail -4 | tee gpurun_out/check_${X}_n$N.log
-  timeout 300 $TR --master-port 29512 tools/check_sharded_nccl.py --rows 1000 --seed 3 --exchange $X 2>&1 | grep -v "^W\|^\*\*\*" | tail -4 | tee -a gpurun_out/check_${X}_n$N.log
+for ARGS in "--exchange p2p" "--exchange p2p --block 0" "--exchange nccl" "--exchange p2p --block 5"; do
+  timeout 300 $TR --master-port 29511 tools/check_sharded_nccl.py --rows 512 $ARGS 2>&1 | grep "sharded check" | tee -a gpurun_out/${TAG}_check_n$N.log
+  timeout 300 $TR --master-port 29512 tools/check_sharded_nccl.py --rows 1001 --seed 3 $ARGS 2>&1 | grep "sharded check" | tee -a gpurun_out/${TAG}_check_n$N.log
 done
-for X in p2p nccl; do
-  timeout 900 $TR --master-port 29513 bench.py --gpus $N --exchange $X > gpurun_out/bench_n${N}_$X.json 2> gpurun_out/bench_n${N}_$X.err
-  tail -2 gpurun_out/bench_n${N}_$X.err; cat gpurun_out/bench_n${N}_$X.json
-done
+timeout 900 $TR --master-port 29513 bench.py --gpus $N --e2e-steps 2 > gpurun_out/${TAG}_bench_n${N}.json 2> gpurun_out/${TAG}_bench_n${N}.err
+tail -2 gpurun_out/${TAG}_bench_n${N}.err | cut -c1-300; cat gpurun_out/${TAG}_bench_n${N}.json
+if [ "${3:-}" = "legacy" ]; then
+  timeout 900 $TR --master-port 29514 bench.py --gpus $N --block 0 --pivots-per-step 256 --e2e-steps 1 > gpurun_out/${TAG}_bench_n${N}_rank1.json 2> gpurun_out/${TAG}_bench_n${N}_rank1.err
+  cat gpurun_out/${TAG}_bench_n${N}_rank1.json
+fi
