@@ -270,7 +270,7 @@ def run_ours(a):
         r1_bytes = algorithmic_bytes(m_loc, n)
         r1_ach = r1_bytes / (r1_avg * 1e-3) / 1e9
         rank1 = {"kernel": "k_update_f64", "achieved": r1_ach, "frac": r1_ach / peak, "bytes_per_launch": r1_bytes,
-                 "ms_per_launch": r1_avg, "launches_timed": int(r1_n), "traffic": recorded_traffic("k_update_f64")}
+                 "ms_per_launch": r1_avg, "launches_timed": int(r1_n), "traffic": recorded_traffic("k_update_f64") if world == 1 else None}
         eng.set_block_size(K)
         solver.block = K
 
@@ -419,8 +419,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--m", type=int, default=32768, help="constraint rows (n = 2m); default is config C4")
-    ap.add_argument("--pivots-per-step", type=int, default=1024,
-                    help="consecutive simplex pivots per step (a solve of this size runs tens of thousands)")
+    ap.add_argument("--pivots-per-step", type=int, default=4096,
+                    help="consecutive simplex pivots per step (C4 takes 193 374 pivots to optimality: profiles/r02d_c4_time_to_optimal.json)")
     ap.add_argument("--block", type=int, default=None, help="pivots per block (default: the library's, 16; 0 = one rank-1 update per pivot)")
     ap.add_argument("--rank1-pivots", type=int, default=24, help="length of the pivot-at-a-time leg that times k_update_f64 (0: skip)")
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -306,6 +306,26 @@ static int launch_extend(lps_handle* h, int Pnew, uint32_t* vec, long long count
 
 // LPS_NEED_PRIMES was reported (nothing modified): extend the working set so that the pending pivot fits, with
 // head-room, and clear the status.  The residues modulo the new primes are computed on the device.
+// The working prime set grows from x->P to Pnew primes: the common denominator D first -- a new prime that divides D
+// has no D^-1 and cannot join (the pivot checks only see the primes that were in the set when the pivot was made) --
+// then the grid.  LPS_BAD_PRIME with *bad = index of such a prime, nothing modified inside the working set.
+static int extend_working(lps_handle* h, int Pnew, int* bad) {
+    ExactData* x = h->x;
+    const int Pold = x->P;
+    *bad = -1;
+    TRY(ensure_planes(h, Pnew, Pold));
+    TRY(launch_extend<4>(h, Pnew, x->Dres, 1));
+    std::vector<uint32_t> dres((size_t)(Pnew - Pold));
+    CU(cudaMemcpyAsync(dres.data(), x->Dres + Pold, dres.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < Pnew - Pold; ++k)
+        if (dres[(size_t)k] == 0) { *bad = Pold + k; return LPS_BAD_PRIME; }
+    TRY(launch_extend<4>(h, Pnew, nullptr, (long long)(h->m + 1) * (h->n + 1)));
+    TRY(set_working(h, Pnew));
+    x->grows++;
+    return LPS_OK;
+}
+
 static int grow_working(lps_handle* h) {
     ExactData* x = h->x;
     TRY(xread_state(h));
@@ -313,11 +333,15 @@ static int grow_working(lps_handle* h) {
     const long long need = s.wnext + 2 * x->wmax256 + x->guard256;
     const int Pnew = pick_working(x, need, x->P + 1);
     if (Pnew > x->P) {
-        TRY(ensure_planes(h, Pnew, x->P));
-        TRY(launch_extend<4>(h, Pnew, nullptr, (long long)(h->m + 1) * (h->n + 1)));
-        TRY(launch_extend<4>(h, Pnew, x->Dres, 1));
-        TRY(set_working(h, Pnew));
-        x->grows++;
+        int bad = -1;
+        const int rc = extend_working(h, Pnew, &bad);
+        if (rc < 0) return rc;
+        if (rc == LPS_BAD_PRIME) {                       // reported like a prime dividing the next pivot: the host
+            s.status = LPS_BAD_PRIME;                    // re-encodes without it and resumes
+            s.bad_prime = bad;
+            TRY(xwrite_state(h));
+            return LPS_BAD_PRIME;
+        }
     }
     s.wlimit = wlimit_of(x, x->P);
     if (s.wnext > s.wlimit) return LPS_NEED_PRIMES;      // every prime of the handle is in use and the bound (grown by row
@@ -458,11 +482,10 @@ extern "C" int lps_row_combine_exact(lps_handle* h, int rd, int rs, const uint32
     if (s.wsum > wlimit_of(x, x->P)) {
         const int Pnew = pick_working(x, need, x->P + 1);
         if (Pnew > x->P) {
-            TRY(ensure_planes(h, Pnew, x->P));
-            TRY(launch_extend<4>(h, Pnew, nullptr, (long long)(h->m + 1) * (h->n + 1)));
-            TRY(launch_extend<4>(h, Pnew, x->Dres, 1));
-            TRY(set_working(h, Pnew));
-            x->grows++;
+            int bad = -1;
+            const int rc = extend_working(h, Pnew, &bad);
+            if (rc < 0) return rc;
+            if (rc == LPS_BAD_PRIME) return LPS_NEED_PRIMES;   // a new prime divides D: refused, nothing modified (host copy)
         }
     }
     s.wlimit = wlimit_of(x, x->P);
@@ -550,11 +573,13 @@ extern "C" int lps_phase2_exact(lps_handle* h, int n_new, const uint32_t* cost_l
         if (wsum > wlimit_of(x, x->P)) {                 // the restored objective row may not fit the working set
             const int Pnew = pick_working(x, wsum + 2 * wmax + x->guard256, x->P + 1);
             if (Pnew > x->P) {
-                TRY(ensure_planes(h, Pnew, x->P));
-                TRY(launch_extend<4>(h, Pnew, nullptr, (long long)(h->m + 1) * (h->n + 1)));
-                TRY(launch_extend<4>(h, Pnew, x->Dres, 1));
-                TRY(set_working(h, Pnew));
-                x->grows++;
+                int bad = -1;
+                const int rc = extend_working(h, Pnew, &bad);
+                if (rc < 0) return rc;
+                // a new prime divides D (about 2^-31 per prime): the columns are already cut, so this call cannot be
+                // refused cleanly -- fail loudly rather than carry a prime without D^-1
+                if (rc == LPS_BAD_PRIME)
+                    return fail(LPS_E_STATE, "prime %d of the handle divides the common denominator: re-encode the tableau without it", bad);
             }
         }
         XState& s = *x->st_host;
@@ -877,7 +902,7 @@ int lpsx_pivot(lps_handle* h, int r, int c) {
         if (x->st_host->status != LPS_NEED_PRIMES || attempt > 0) break;
         const int grc = grow_working(h);                 // nothing was modified: extend the working set, try again
         if (grc < 0) return grc;
-        if (grc == LPS_NEED_PRIMES) break;
+        if (grc == LPS_NEED_PRIMES || grc == LPS_BAD_PRIME) break;
     }
     const int st = x->st_host->status;
     return (st == LPS_ZERO_PIVOT || st == LPS_BAD_PRIME || st == LPS_NEED_PRIMES) ? st : LPS_OK;
@@ -1048,7 +1073,7 @@ int lpsx_solve(lps_handle* h, long long max_pivots, int* basis, int* marks, int*
             enqueued = x->st_host->npiv;                 // the launches behind it were no-ops
             const int grc = grow_working(h);
             if (grc < 0) return grc;
-            if (grc == LPS_NEED_PRIMES) break;           // reported: the host re-encodes and resumes (like LPS_BAD_PRIME)
+            if (grc == LPS_NEED_PRIMES || grc == LPS_BAD_PRIME) break;   // reported: the host re-encodes and resumes
             continue;
         }
         if (x->st_host->status != LPS_OK) break;
