@@ -171,6 +171,9 @@ int lps_step_select(lps_handle *h);
  * all-reduce + pivot-row broadcast of SURVEY.md section 8e fused into the select kernel.  lps_p2p_export returns the
  * 64-byte CUDA IPC handle of this handle's exchange block; the caller gathers the handles of all ranks (any
  * transport) and passes them, in rank order, to lps_p2p_attach on every rank. */
+/* lps_p2p_prepare sizes the exchange block for nranks ranks (in the blocked loop every rank stores its candidate rows
+ * into every rank's block); call it before lps_p2p_export / lps_p2p_block -- it may move the block. */
+int lps_p2p_prepare(lps_handle *h, int nranks);
 int lps_p2p_export(lps_handle *h, unsigned char *ipc_handle64);
 int lps_p2p_attach(lps_handle *h, long long row0, long long m_total, int rank, int nranks,
                    const unsigned char *ipc_handles);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "lps_block_size": (c_int, [c_void_p]),
     "lps_set_block_size": (c_int, [c_void_p, c_int]),
     "lps_set_panel_ctas": (c_int, [c_void_p, c_int]),
+    "lps_p2p_prepare": (c_int, [c_void_p, c_int]),
     "lps_p2p_export": (c_int, [c_void_p, c_void_p]),
     "lps_p2p_attach": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_void_p]),
     "lps_p2p_block": (c_int, [c_void_p, POINTER(c_void_p)]),

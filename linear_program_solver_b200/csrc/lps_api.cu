@@ -117,6 +117,24 @@ static void plan(lps_handle* h) {
     }
 }
 
+// Exchange block: headers and flags, then the row area -- two sets of kBlkMax candidate rows per rank (the rank-1 loop
+// uses the first row as its vrow).  Sized for the number of ranks that will store into it.
+static int alloc_xchg(lps_handle* h, int nranks) {
+    if (h->xchg && h->blk.nr == nranks) return LPS_OK;
+    if (h->xchg) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(h->xchg)); h->xchg = nullptr; }
+    const size_t xb = sizeof(XchgBlock) + 2 * (size_t)nranks * kBlkMax * h->ld * sizeof(double);
+    cudaError_t e = cudaMalloc(&h->xchg, xb);
+    if (e != cudaSuccess) return fail(LPS_E_NOMEM, "cudaMalloc of the %zu-byte exchange block failed: %s", xb, cudaGetErrorString(e));
+    CU(cudaMemsetAsync(h->xchg, 0, xb, h->stream));
+    CU(cudaMemcpyAsync(h->d_peers, &h->xchg, sizeof(XchgBlock*), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));           // (&h->xchg is read by the copy)
+    h->xchg_bytes = xb;
+    h->blk.V = xchg_vrow(h->xchg);
+    h->blk.nr = nranks;
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    return LPS_OK;
+}
+
 extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* stream, lps_handle** out) {
     if (!out) return fail(LPS_E_INVALID, "null out");
     *out = nullptr;
@@ -168,6 +186,7 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
         sl.add(&h->blk.B[1], ucol_n);
         sl.add(&h->blk.R, (size_t)kBlkMax);
         sl.add(&h->blk.C, (size_t)kBlkMax);
+        sl.add(&h->blk.W, (size_t)kBlkMax);
         sl.add(&h->blk.hdr, (size_t)4);
         sl.add(&h->blk.p_val, (size_t)256);
         sl.add(&h->blk.p_idx, (size_t)256);
@@ -183,15 +202,7 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
     CU(cudaMemsetAsync(h->cand_send, 0, h->cand_stride, h->stream));
     h->cand_all = h->cand_send;
     h->own_cand = false;
-    {
-        // exchange block: headers and flags, then kBlkMax pivot rows (row 0 doubles as the rank-1 path's vrow)
-        const size_t xb = sizeof(XchgBlock) + (size_t)kBlkMax * h->ld * sizeof(double);
-        CU(cudaMalloc(&h->xchg, xb));
-        CU(cudaMemsetAsync(h->xchg, 0, xb, h->stream));
-        CU(cudaMemcpyAsync(h->d_peers, &h->xchg, sizeof(XchgBlock*), cudaMemcpyHostToDevice, h->stream));
-        h->xchg_bytes = xb;
-        h->blk.V = xchg_vrow(h->xchg);
-    }
+    TRY(alloc_xchg(h, 1));
     CU(cudaMemsetAsync(h->st, 0, sizeof(SolveState), h->stream));
     static_assert(sizeof(SolveState) <= 256, "pinned state blocks are 256 bytes");
     h->st_host = (SolveState*)lps_pinned_get(sizeof(SolveState));
@@ -861,6 +872,17 @@ extern "C" int lps_solve(lps_handle* h, long long max_pivots, int* basis, int* m
 // ------------------------------------------------------------------------------------------------
 // peer-store exchange over CUDA IPC
 // ------------------------------------------------------------------------------------------------
+// Sizes this handle's exchange block for `nranks` ranks (every rank stores its candidate rows into every block).
+// Call it before lps_p2p_export / lps_p2p_block: it may move the block.
+extern "C" int lps_p2p_prepare(lps_handle* h, int nranks) {
+    USE(h);
+    NEED_MODE(h, 0);
+    if (nranks < 1 || nranks > kMaxRanks) return fail(LPS_E_INVALID, "bad rank count %d", nranks);
+    if (h->solving) return fail(LPS_E_STATE, "solve in progress");
+    if (!h->ipc_open.empty()) return fail(LPS_E_STATE, "peers are already attached to this handle");
+    return alloc_xchg(h, nranks);
+}
+
 extern "C" int lps_p2p_export(lps_handle* h, unsigned char* ipc_handle64) {
     USE(h);
     NEED_MODE(h, 0);
@@ -896,6 +918,7 @@ static int attach_blocks(lps_handle* h, long long row0, long long m_total, int r
 
 static int check_shard(lps_handle* h, long long row0, long long m_total, int rank, int nranks) {
     if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(LPS_E_INVALID, "bad rank %d of %d", rank, nranks);
+    if (h->blk.nr != nranks) return fail(LPS_E_STATE, "exchange block sized for %d ranks, not %d: call lps_p2p_prepare first", h->blk.nr, nranks);
     if (row0 < 0 || row0 + h->m > m_total) return fail(LPS_E_INVALID, "rows [%lld,%lld) outside 0..%lld", row0, row0 + h->m, m_total);
     return LPS_OK;
 }

@@ -184,7 +184,11 @@ extern "C" int lps_batch_create(int count, int m, int n, int art_cap, int nprime
     CUB(cudaEventCreate(&b->ev1));
 
     cudaError_t e = cudaSuccess;
-    BATCH_DISPATCH(P, e = cudaFuncSetAttribute(k_bnb_nodes<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    // The attribute belongs to the kernel instantiation, not to this batch: batches of the same prime count but other
+    // shapes live next to each other (the host pools them), so it is raised to the most any of them can ask for --
+    // setting it to THIS batch's size let a later, smaller batch lower it under an earlier one ("invalid argument"
+    // at that one's next launch).
+    BATCH_DISPATCH(P, e = cudaFuncSetAttribute(k_bnb_nodes<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBatchSmemMax));
     CUB(e);
     CUB(cudaStreamSynchronize(b->stream));
     *out = b;

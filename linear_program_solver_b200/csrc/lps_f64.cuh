@@ -45,12 +45,20 @@ static_assert(sizeof(CandHeader) == 64, "candidate header must stay 64 bytes");
 // themselves -- no collective call, no host step.  Headers are double buffered by sequence parity (a rank can be at
 // most one pivot ahead of a peer), vrow is single buffered (it is rewritten only after every rank has published
 // the next header, i.e. finished the previous update).
+constexpr int kMaxPanelCtas = 256;
 struct XchgBlock {
     CandHeader hdr[2][kMaxRanks];
     unsigned long long hdr_seq[kMaxRanks];
     unsigned long long row_seq;
     unsigned long long pad[15];
-    // followed by vrow: ld doubles (128-byte aligned)
+    // blocked loop (lps_f64_blk.cuh): ONE exchange per pivot.  Every rank stores a 32-byte self-validating candidate
+    // record (ratio bits, row | sequence number << 32, check word) into slot `rank` of every rank's hdr2 -- no fence,
+    // no flag: a reader takes a record only when its sequence number and check word agree -- and its own normalised
+    // candidate row into every rank's row area, slice by slice, each slice followed by rowflag[rank][cta] = sequence.
+    unsigned long long hdr2[2][kMaxRanks][4];
+    unsigned long long rowflag[kMaxRanks][kMaxPanelCtas];
+    // followed by the row area (128-byte aligned): the rank-1 loop uses its first ld doubles (vrow); the blocked loop
+    // [set 2][rank nranks][pivot kBlkMax][ld]
 };
 static_assert(sizeof(XchgBlock) % 128 == 0, "vrow must stay 128-byte aligned");
 __host__ __device__ __forceinline__ double* xchg_vrow(XchgBlock* x) { return reinterpret_cast<double*>(x + 1); }
@@ -63,6 +71,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;

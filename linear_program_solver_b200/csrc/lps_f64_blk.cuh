@@ -60,12 +60,18 @@ struct BlkPanel {
                              //   [kBlkMax] = two 32-bit masks: low, bit l = that multiplier is zero (the reference leaves
                              //   the row alone, tableau.py:272); high, bit l = the row IS pivot l's row (replaced)
     size_t upitch;
-    double* V;               // kBlkMax x ld: normalised pivot rows (lives in the exchange block: peers store into it)
+    double* V;               // the exchange block's row area [set 2][rank nr][pivot kBlkMax][ld]: normalised candidate rows.
+                             // Pivot l's row is the one of the rank that won its ratio test, W[l]; blocks alternate
+                             // between the two sets (a peer may already store its first candidate of the next block
+                             // while this rank's update still reads the current one)
+    int nr;                  // rank slots of the row area
+    int* W;                  // kBlkMax: winning rank of pivot l
     double* O[2];            // objective row, ping-pong by pivot parity (ld each)
     double* B[2];            // right-hand side of the local rows, ping-pong (upitch each)
     int* R;                  // kBlkMax: GLOBAL leaving row of pivot l
     int* C;                  // kBlkMax: entering column
-    int* hdr;                // [0] pivots decided by the last panel launch, [1] current parity of O / B
+    int* hdr;                // [0] pivots decided by the last panel launch, [1] current parity of O / B,
+                             // [2] non-empty blocks since lps_solve_begin, [3] row-area set of the last panel launch
     double* p_val;           // pricing partials, one per panel CTA
     int* p_idx;
     int* p_bidx;
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(kSelMaxThreads) k_blk_init(F64Grid g, BlkPanel
         P.p_val[blockIdx.x] = best.key;
         P.p_idx[blockIdx.x] = best.idx;
         P.p_bidx[blockIdx.x] = first_neg;
-        if (blockIdx.x == 0) { P.hdr[0] = 0; P.hdr[1] = 0; }
+        if (blockIdx.x == 0) { P.hdr[0] = 0; P.hdr[1] = 0; P.hdr[2] = 0; P.hdr[3] = 0; }
     }
 }
 
@@ -124,19 +130,31 @@ struct BlkPanelArgs {
     long long trace_cap;
 };
 
-__device__ __forceinline__ int pick_winner_cg(const XchgBlock* x, int par, int nranks, long long* row_out) {
-    int w = -1;
-    double w_ratio = 0.0;
-    long long w_row = -1;
-    for (int k = 0; k < nranks; ++k) {
-        const CandHeader* h = &x->hdr[par][k];
-        const long long row = __ldcg(&h->row);
-        if (row < 0) continue;
-        const double ratio = __ldcg(&h->ratio);
-        if (w < 0 || ratio < w_ratio || (ratio == w_ratio && row < w_row)) { w = k; w_ratio = ratio; w_row = row; }
+// ---- candidate records of the one-exchange protocol (XchgBlock::hdr2) ----
+constexpr unsigned long long kHdrMagic = 0x5bd1e995a5a5a5a5ull;
+__device__ __forceinline__ void hdr2_store(unsigned long long* slot, double ratio, long long row, unsigned long long seq) {
+    const unsigned long long w0 = (unsigned long long)__double_as_longlong(ratio);
+    const unsigned long long w1 = (unsigned long long)(unsigned int)(row < 0 ? 0xffffffffu : (unsigned int)row) | (seq << 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(slot + 2), "l"(w0 ^ w1 ^ kHdrMagic), "l"(0ull) : "memory");
+}
+// true once the record of sequence number seq has landed whole; ten-second time-out like wait_seq
+__device__ __forceinline__ bool hdr2_wait(const unsigned long long* slot, unsigned long long seq, double* ratio, long long* row) {
+    const unsigned long long t0 = global_ns();
+    unsigned int polls = 0;
+    for (;;) {
+        const unsigned long long w1 = ld_relaxed_sys(slot + 1);
+        if ((w1 >> 32) == (seq & 0xffffffffull)) {
+            const unsigned long long w0 = ld_relaxed_sys(slot), w2 = ld_relaxed_sys(slot + 2);
+            if ((w0 ^ w1 ^ kHdrMagic) == w2) {
+                *ratio = __longlong_as_double((long long)w0);
+                const unsigned int r32 = (unsigned int)(w1 & 0xffffffffull);
+                *row = (r32 == 0xffffffffu) ? -1 : (long long)r32;
+                return true;
+            }
+        }
+        if ((++polls & 1023u) == 0 && global_ns() - t0 > 10000000000ull) return false;
     }
-    *row_out = w_row;
-    return w;
 }
 
 template <int NT>
@@ -147,6 +165,9 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
     __shared__ double s_vc[kBlkMax];       // V[lp][c]: the entering column's cell in the earlier pivot rows
     __shared__ double s_ur[kBlkMax];       // U[lp][r]: the leaving row's cell in the earlier pivot columns
     __shared__ long long s_R[kBlkMax];     // global leaving rows decided so far in this block
+    __shared__ int s_W[kBlkMax];           // ranks that owned them
+    __shared__ double s_hratio[kMaxRanks]; // this pivot's candidates of all ranks
+    __shared__ long long s_hrow[kMaxRanks];
     __shared__ int s_w, s_flag;
     __shared__ long long s_row;
 
@@ -172,6 +193,9 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
     unsigned long long seq = st->xseq;
     int last_r = st->last_r, last_c = st->last_c;
     int cur = P.hdr[1];
+    const int set = P.hdr[2] & 1;                              // row-area set of this block
+    const size_t vset = (size_t)set * P.nr;
+    auto Vrow = [&](int lp, int w) { return P.V + ((vset + w) * kBlkMax + lp) * g.ld; };   // rank w's candidate row of pivot lp
 
     int l = 0;
     for (; l < a.kmax; ++l) {
@@ -210,7 +234,7 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
         const int i_first = cta * nt + tid;
         double x_first = 0.0, b_first = 0.0;
         if (i_first < g.m) { x_first = g.T[(size_t)i_first * g.ld + c]; b_first = __ldcg(&Bc[i_first]); }
-        if (tid < l) s_vc[tid] = __ldcg(&P.V[(size_t)tid * g.ld + c]);
+        if (tid < l) s_vc[tid] = __ldcg(Vrow(tid, s_W[tid]) + c);
         const double uobj = __ldcg(&Oc[c]);                    // the objective row's cell of the entering column
         __syncthreads();
         ArgMinF64 best{0.0, INT_MAX};
@@ -265,7 +289,7 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
         }
         __syncthreads();
         if (s_flag) {
-            // the CTA that arrived last: this rank's best row, the exchange with the peers, the decision
+            // the CTA that arrived last: this rank's best row.  Row-sharded: its candidate record goes to every rank.
             if (!solo) {
                 __threadfence();
                 best = ArgMinF64{0.0, INT_MAX};
@@ -273,51 +297,39 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
                 best = block_argmin(best, s_arg);
             }
             const int r = best.idx;
-            int w;
-            long long w_row;
-            if (a.nranks > 1) {
-                CandHeader h{};
-                h.ratio = best.key; h.row = (r == INT_MAX) ? -1 : g.row0 + r; h.c = c; h.rule = rule_now; h.stuck = stuck_now;
-                publish_header(a.peers, a.rank, a.nranks, h, seq);
-                int ok = 1;
-                if (tid < a.nranks) ok = wait_seq(&a.xchg->hdr_seq[tid], seq) ? 1 : 0;
-                ok = __syncthreads_and(ok);
-                w = -2;
-                w_row = -1;
-                if (ok) w = pick_winner_cg(a.xchg, (int)(seq & 1), a.nranks, &w_row);
-            } else {
-                w = (r == INT_MAX) ? -1 : 0;
-                w_row = (r == INT_MAX) ? -1 : g.row0 + r;
-            }
+            const long long cand = (r == INT_MAX) ? -1 : g.row0 + r;
+            if (a.nranks > 1 && tid < a.nranks) hdr2_store(&a.peers[tid]->hdr2[seq & 1][a.rank][0], best.key, cand, seq);
             if (tid == 0) {
-                if (solo) { s_w = w; s_row = w_row; }
+                if (solo) s_row = cand;
                 else {
-                    sy->dec_w = w;
-                    sy->dec_row = w_row;
+                    sy->dec_row = cand;
                     __threadfence();
                     st_release_gpu(&sy->dec_seq, seq);
                 }
             }
         }
         if (!solo && tid == 0) {
-            if (wait_seq_gpu(&sy->dec_seq, seq)) {
-                s_w = *reinterpret_cast<volatile int*>(&sy->dec_w);
-                s_row = *reinterpret_cast<volatile long long*>(&sy->dec_row);
-            } else s_w = -3;
-        }
+            if (wait_seq_gpu(&sy->dec_seq, seq)) { s_row = *reinterpret_cast<volatile long long*>(&sy->dec_row); s_w = 0; }
+            else s_w = -3;
+        } else if (solo && tid == 0) s_w = 0;
         __syncthreads();
-        const int w = s_w;
-        const long long r_g = s_row;
-        if (w == -2 || w == -3) { status = LPS_E_PEER; break; }
-        if (w < 0) { status = LPS_UNBOUNDED; break; }
+        if (s_w == -3) { status = LPS_E_PEER; break; }
+        const long long cand_g = s_row;                         // this rank's candidate (global row), -1: none
 
-        // ---- C: normalised pivot row -> V[l] (every rank's copy), objective row, right-hand side, pricing ----
-        double* Vl = P.V + (size_t)l * g.ld;
+        // ---- C: normalised candidate row -> the row area (every rank's copy); winner; objective row, right-hand
+        //         side, pricing ----
         ArgMinF64 pb{0.0, INT_MAX};
         int first_neg = INT_MAX;
         double vn;                                              // the pivot row's right-hand side, normalised
-        if (w == a.rank) {
-            const int r_loc = (int)(r_g - g.row0);
+        int w;
+        long long r_g;
+        if (a.nranks == 1) {
+            if (cand_g < 0) { status = LPS_UNBOUNDED; break; }
+            w = 0;
+            r_g = cand_g;
+        } else { w = -1; r_g = -1; }
+        if (cand_g >= 0) {
+            const int r_loc = (int)(cand_g - g.row0);
             const double* src = g.T + (size_t)r_loc * g.ld;
             const int j_first = 2 * (cta * nt + tid);
             double2 y_first = make_double2(0.0, 0.0), o_first = make_double2(0.0, 0.0);
@@ -328,52 +340,75 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
             __syncthreads();
             const double inv = 1.0 / pv;                        // rowDiv: ONE / d, then rowMult (tableau.py:262-267)
             vn = (inv != 1.0) ? __dmul_rn(br, inv) : br;
+            double* Vl = Vrow(l, a.rank);
+            const size_t peer_off = (size_t)(Vl - P.V);
             for (int j = j_first; j < (int)g.ld; j += 2 * G * nt) {
                 double2 y = (j == j_first) ? y_first : *reinterpret_cast<const double2*>(src + j);
-                const double2 o_old = (j == j_first) ? o_first : ldcg2(Oc + j);
                 for (int l0 = 0; l0 < l; l0 += kBlkBatch / 2) {
                     double2 v[kBlkBatch / 2];
 #pragma unroll
                     for (int q = 0; q < kBlkBatch / 2; ++q)
-                        if (l0 + q < l) v[q] = ldcg2(P.V + (size_t)(l0 + q) * g.ld + j);
+                        if (l0 + q < l) v[q] = ldcg2(Vrow(l0 + q, s_W[l0 + q]) + j);
 #pragma unroll
                     for (int q = 0; q < kBlkBatch / 2; ++q) {
                         if (l0 + q >= l) continue;
-                        if (s_R[l0 + q] == r_g) y = v[q];
+                        if (s_R[l0 + q] == cand_g) y = v[q];
                         else { y.x = blk_apply(y.x, s_ur[l0 + q], v[q].x); y.y = blk_apply(y.y, s_ur[l0 + q], v[q].y); }
                     }
                 }
                 if (inv != 1.0) { y.x = __dmul_rn(y.x, inv); y.y = __dmul_rn(y.y, inv); }   // rowMult skips a multiplier of 1
                 stcg2(Vl + j, y);
-                for (int k = 0; k < a.nranks; ++k)
-                    if (k != a.rank) *reinterpret_cast<double2*>(xchg_vrow(a.peers[k]) + (size_t)l * g.ld + j) = y;
-                double2 o = o_old;
-                o.x = blk_apply(o.x, uobj, y.x);
-                o.y = blk_apply(o.y, uobj, y.y);
-                stcg2(On + j, o);
-                price_consider(o.x, j, g.n, pb, first_neg);
-                price_consider(o.y, j + 1, g.n, pb, first_neg);
+                if (a.nranks == 1) {                            // one rank: the candidate is the pivot row
+                    double2 o = (j == j_first) ? o_first : ldcg2(Oc + j);
+                    o.x = blk_apply(o.x, uobj, y.x);
+                    o.y = blk_apply(o.y, uobj, y.y);
+                    stcg2(On + j, o);
+                    price_consider(o.x, j, g.n, pb, first_neg);
+                    price_consider(o.y, j + 1, g.n, pb, first_neg);
+                } else {
+                    for (int k = 0; k < a.nranks; ++k)
+                        if (k != a.rank) *reinterpret_cast<double2*>(xchg_vrow(a.peers[k]) + peer_off + j) = y;
+                }
             }
             if (a.nranks > 1) {
-                __threadfence_system();
+                // this CTA's slice is out: one system-scope fence by one thread (the block barrier orders the other
+                // threads' stores before it), then the slice's flag on every rank
                 __syncthreads();
-                if (tid == 0) {
-                    const unsigned long long old = atomicAdd(&sy->ticket2, 1ull);
-                    s_flag = ((old + 1) % (unsigned long long)G == 0);
-                }
+                if (tid == 0) __threadfence_system();
                 __syncthreads();
-                if (s_flag) {
-                    __threadfence_system();
-                    if (tid < a.nranks && tid != a.rank) st_release_sys(&a.peers[tid]->row_seq, seq);
-                }
+                if (tid < a.nranks) st_relaxed_sys(&a.peers[tid]->rowflag[a.rank][cta], seq);
             }
-        } else {
-            if (tid == 0) s_flag = wait_seq(&a.xchg->row_seq, seq) ? 1 : 0;
+        }
+        if (a.nranks > 1) {
+            // every CTA reads all candidates and picks the same winner: lowest ratio, then lowest global row
+            // (simplex.py:277); then it needs the winner's row only where it works: its own slice, and the slice
+            // that holds the right-hand side
+            if (tid < a.nranks) {
+                double hr = 0.0;
+                long long hrow = -1;
+                const bool ok = hdr2_wait(&a.xchg->hdr2[seq & 1][tid][0], seq, &hr, &hrow);
+                s_hratio[tid] = hr;
+                s_hrow[tid] = ok ? hrow : -2;
+            }
+            __syncthreads();
+            bool dead = false;
+            for (int k = 0; k < a.nranks; ++k) {
+                const long long row = s_hrow[k];
+                if (row == -2) dead = true;
+                if (row < 0) continue;
+                if (w < 0 || s_hratio[k] < s_hratio[w] || (s_hratio[k] == s_hratio[w] && row < r_g)) { w = k; r_g = row; }
+            }
+            if (dead) { status = LPS_E_PEER; break; }
+            if (w < 0) { status = LPS_UNBOUNDED; break; }
+            const int pair_n = g.n / 2;                         // the column pair that holds the right-hand side
+            const int cta_n = (pair_n % (G * nt)) / nt;
+            if (tid == 0) s_flag = (wait_seq(&a.xchg->rowflag[w][cta], seq) && wait_seq(&a.xchg->rowflag[w][cta_n], seq)) ? 1 : 0;
             __syncthreads();
             if (!s_flag) { status = LPS_E_PEER; break; }
-            vn = __ldcg(&Vl[g.n]);
+            const double* Vw = Vrow(l, w);
+            vn = __ldcg(&Vw[g.n]);
             for (int j = 2 * (cta * nt + tid); j < (int)g.ld; j += 2 * G * nt) {
-                const double2 y = ldcg2(Vl + j);
+                const double2 y = ldcg2(Vw + j);
                 double2 o = ldcg2(Oc + j);
                 o.x = blk_apply(o.x, uobj, y.x);
                 o.y = blk_apply(o.y, uobj, y.y);
@@ -400,9 +435,11 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
             __stcg(&P.p_idx[cta], pb.idx);
             __stcg(&P.p_bidx[cta], first_neg);
             s_R[l] = r_g;
+            s_W[l] = w;
             if (cta == 0) {   // commit (Simplex._pivot simplex.py:192-197)
                 P.R[l] = (int)r_g;
                 P.C[l] = c;
+                P.W[l] = w;
                 if (a.trace && npiv < a.trace_cap) {
                     a.trace[3 * npiv] = (int)r_g;
                     a.trace[3 * npiv + 1] = c;
@@ -442,7 +479,12 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
 
     __syncthreads();
     if (tid == 0) {
-        if (cta == 0) { P.hdr[0] = l; P.hdr[1] = cur; }
+        if (cta == 0) {
+            P.hdr[0] = l;
+            P.hdr[1] = cur;
+            P.hdr[3] = set;
+            if (l > 0) P.hdr[2] = P.hdr[2] + 1;
+        }
         bool last = true;
         if (!solo) last = ((atomicAdd(&sy->exit_ticket, 1ull) + 1) % (unsigned long long)G == 0);
         if (last) {
@@ -587,7 +629,9 @@ __global__ void __launch_bounds__(kBlkConsumers + 32, 1) k_blk_update(BlkUpdateA
             const int col = (int)(chunk * kBlkCW) + jl;
 #pragma unroll
             for (int l = 0; l < kBlkMax; ++l)
-                v[l] = (l < kk && col < (int)g.ld) ? ldcg2(P.V + (size_t)l * g.ld + col) : make_double2(0.0, 0.0);
+                v[l] = (l < kk && col < (int)g.ld)
+                           ? ldcg2(P.V + (((size_t)P.hdr[3] * P.nr + P.W[l]) * kBlkMax + l) * g.ld + col)
+                           : make_double2(0.0, 0.0);
             chunk_have = chunk;
         }
         mbar_spin(&S.full[slot], (uint32_t)((q / kBlkStages) & 1));

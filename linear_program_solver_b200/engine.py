@@ -117,8 +117,11 @@ class F64Engine:
         N.check(self.L.lps_set_shard(self.h, row0, m_total, rank, nranks, self.cand_send.data_ptr(), self.cand_all.data_ptr()))
         self.row0, self.m_total, self.rank, self.nranks = row0, m_total, rank, nranks
 
-    def p2p_export(self) -> np.ndarray:
-        """64-byte CUDA IPC handle of this engine's exchange block (peer-store exchange, include/lps_b200.h)."""
+    def p2p_export(self, nranks: int) -> np.ndarray:
+        """64-byte CUDA IPC handle of this engine's exchange block, sized for `nranks` ranks (peer-store exchange,
+        include/lps_b200.h)."""
+        self._pool_key = None
+        N.check(self.L.lps_p2p_prepare(self.h, int(nranks)))
         out = np.zeros(64, dtype=np.uint8)
         N.check(self.L.lps_p2p_export(self.h, out.ctypes.data))
         return out
@@ -131,9 +134,12 @@ class F64Engine:
         N.check(self.L.lps_p2p_attach(self.h, row0, m_total, rank, nranks, handles.ctypes.data))
         self.row0, self.m_total, self.rank, self.nranks = row0, m_total, rank, nranks
 
-    def p2p_block(self) -> int:
-        """Device address of this engine's exchange block (ranks of one process: `p2p_attach_local`)."""
+    def p2p_block(self, nranks: int) -> int:
+        """Device address of this engine's exchange block, sized for `nranks` ranks (ranks of one process:
+        `p2p_attach_local`)."""
         from ctypes import c_void_p
+        self._pool_key = None
+        N.check(self.L.lps_p2p_prepare(self.h, int(nranks)))
         out = c_void_p()
         N.check(self.L.lps_p2p_block(self.h, byref(out)))
         return int(out.value)

@@ -229,8 +229,11 @@ class LinProg:
                         out[i] = ("infeasible", None, None)
                     elif st == N.UNBOUNDED:
                         out[i] = ("unbounded", None, None)
-                    elif st == N.BAD_PRIME:
-                        out[i] = None                                # solved alone below
+                    elif st in (N.BAD_PRIME, N.REDUNDANT_ROW, N.MAX_PIVOTS, N.NEED_PRIMES, N.NEED_ARTIFICIALS):
+                        # solved alone below: the single-LP engine re-encodes around a bad prime, has no pivot cap,
+                        # and drops dependent equality rows instead of reproducing the reference constructor's crash
+                        # (this layer has no reference behaviour to mirror)
+                        out[i] = None
                     else:
                         res.raise_for_status(k)
             for i in idxs:
@@ -247,7 +250,7 @@ class LinProg:
         from .tableau import Tableau
         t = Tableau.from_grid(form.grid, mode="exact", device=device)
         try:
-            s = Simplex(t)
+            s = Simplex(t, drop_redundant=True)
         except ValueError as e:
             if str(e).startswith("infeasible problem"):
                 return ("infeasible", None, None)

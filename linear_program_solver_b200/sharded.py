@@ -87,7 +87,7 @@ class ShardedF64Solver:
         rank succeeded."""
         import torch
         import torch.distributed as dist
-        mine = torch.from_numpy(self.eng.p2p_export()).to(f"cuda:{self.eng.device}")
+        mine = torch.from_numpy(self.eng.p2p_export(self.nranks)).to(f"cuda:{self.eng.device}")
         everyone = torch.empty(64 * self.nranks, dtype=torch.uint8, device=mine.device)
         dist.all_gather_into_tensor(everyone, mine, group=self.group)
         ok = 1

@@ -26,7 +26,14 @@ class Simplex:
     problem.  The tableau is not copied.
     """
 
-    def __init__(self, tab: Tableau):
+    #: `pivot_log` keeps at most this many pivots of ONE `solve()` call (the device trace buffer is sized up front);
+    #: `last_pivots` is always exact.  Raise it before a solve whose whole pivot sequence is wanted.
+    log_cap: int = 1 << 16
+
+    def __init__(self, tab: Tableau, drop_redundant: bool = False):
+        #: not in the reference: when phase 1 finds dependent constraint rows, drop them and go on instead of
+        #: reproducing the reference's crash (simplex.py:93 re-installs the stale row count).  `LinProg` sets it.
+        self._drop_redundant = bool(drop_redundant)
         self._tab: Tableau = tab
         self._bfs: List[int] = [-1] * tab.getNumCons()
         #: (row, column, rule) of every pivot made through this object; rule 0 = Dantzig,
@@ -87,7 +94,7 @@ class Simplex:
             tab.setC(orig_c)
             for i, j in enumerate(self._bfs):
                 tab.rowSubFromObj(i, tab.getCj(j))
-        if not all(rowkeep):
+        if not all(rowkeep) and not self._drop_redundant:
             self._fail_like_stale_row_count()
         assert tab.isCanonical(), "tableau not canonical (internal error)"
         for j in self._bfs:
@@ -119,13 +126,14 @@ class Simplex:
         pivots when the objective seems stuck (simplex.py:110-148).
 
         `max_pivots` (not in the reference) stops after a prefix of pivots; the default runs to
-        optimality.  Returns None like the reference; the number of pivots made is `self.last_pivots`."""
+        optimality.  Returns None like the reference; the number of pivots made is `self.last_pivots`
+        (`pivot_log` records the first `log_cap` of them)."""
         tab = self._tab
         eng = tab._touch_dev()
         m, n = tab.getTableauSize()
         basis = np.asarray(self._bfs, dtype=np.int32)
         marks = np.asarray(tab._cm, dtype=np.int32)
-        cap = max_pivots if max_pivots >= 0 else 1 << 16
+        cap = max_pivots if max_pivots >= 0 else int(self.log_cap)
         status, npiv, trace = eng.solve(basis, marks, max_pivots=max_pivots, trace_cap=cap)
         self.last_pivots = int(npiv)
         self._bfs[:] = [int(j) for j in basis]

@@ -204,7 +204,7 @@ def test_blocks_with_the_peer_store_exchange_between_engines_of_one_process(m, p
     for g in range(parts):
         row0, ml = shard_rows(m, g, parts)
         engs.append(F64Engine(ml, n, device=g % ndev))
-    blocks = [e.p2p_block() for e in engs]
+    blocks = [e.p2p_block(parts) for e in engs]
     for g, e in enumerate(engs):
         row0, ml = shard_rows(m, g, parts)
         e.set_block_size(block)

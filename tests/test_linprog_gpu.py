@@ -86,3 +86,26 @@ def test_unbounded_relaxation_raises():
     lp.setObjective(LinExpr(-1, "x"))
     with pytest.raises(ValueError):
         lp.solve()
+
+
+def test_dependent_equality_rows_are_dropped_instead_of_crashing():
+    """x + y = 4 stated twice (once scaled): phase 1 ends with an artificial variable on a zero row.  The reference
+    constructor crashes there (simplex.py:93, reproduced by `Simplex`); the MILP layer -- new design, SURVEY F1 --
+    drops the dependent row and goes on (round-1 advisor finding)."""
+    from linear_program_solver_b200 import LinExpr, LinProg, LinVar, Simplex, Tableau
+    lp = LinProg()
+    lp.addVar(LinVar("x", True, 0, 3))
+    lp.addVar(LinVar("y", True, 0, None))
+    lp.addConstraint(LinExpr(1, "x", 1, "y").constrantEq(4))
+    lp.addConstraint(LinExpr(2, "x", 2, "y").constrantEq(8))
+    lp.addConstraint(LinExpr(1, "x", -1, "y").constraintLeq(1))
+    lp.setObjective(LinExpr(3, "x", 1, "y"), "max")
+    res = lp.solve()
+    assert res.status == "optimal" and res.objective == 8 and res.values == {"x": 2, "y": 2}
+    # the class surface keeps the reference's behaviour unless asked otherwise
+    grid = [[1, 1, 0, 2], [2, 2, 0, 4], [0, 1, 1, 3], [1, 1, 1, 0]]
+    with pytest.raises((IndexError, AssertionError)):
+        Simplex(Tableau.from_grid(grid, mode="exact"))
+    s = Simplex(Tableau.from_grid(grid, mode="exact"), drop_redundant=True)
+    s.solve()
+    assert s._tab.getNumCons() == 2 and s.getObjValue() == 3      # x2 = 2, x3 = 1

@@ -69,7 +69,7 @@ def test_peer_store_exchange_between_engines_of_one_process(m, parts, seed):
     for g in range(parts):
         row0, ml = shard_rows(m, g, parts)
         engs.append(F64Engine(ml, n, device=g % ndev))
-    blocks = [e.p2p_block() for e in engs]
+    blocks = [e.p2p_block(parts) for e in engs]
     for g, e in enumerate(engs):
         row0, ml = shard_rows(m, g, parts)
         e.p2p_attach_local(row0, m, g, parts, blocks)
@@ -117,7 +117,7 @@ def test_ties_across_shards_pick_the_lowest_global_row(m, parts, seed):
     for g in range(parts):
         row0, ml = shard_rows(m, g, parts)
         engs.append(F64Engine(ml, n, device=g % ndev))
-    blocks = [e.p2p_block() for e in engs]
+    blocks = [e.p2p_block(parts) for e in engs]
     for g, e in enumerate(engs):
         row0, ml = shard_rows(m, g, parts)
         e.p2p_attach_local(row0, m, g, parts, blocks)

@@ -6,7 +6,7 @@ N=${1:-2}
 TAG=${2:-r02}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-for ARGS in "--exchange p2p" "--exchange p2p --block 0" "--exchange nccl" "--exchange p2p --block 5"; do
+for ARGS in "--exchange p2p --block 16" "--exchange p2p --block 0" "--exchange nccl" "--exchange p2p --block 5"; do
   timeout 300 $TR --master-port 29511 tools/check_sharded_nccl.py --rows 512 $ARGS 2>&1 | grep "sharded check" | tee -a gpurun_out/${TAG}_check_n$N.log
   timeout 300 $TR --master-port 29512 tools/check_sharded_nccl.py --rows 1001 --seed 3 $ARGS 2>&1 | grep "sharded check" | tee -a gpurun_out/${TAG}_check_n$N.log
 done
