@@ -159,7 +159,7 @@ __device__ __forceinline__ bool hdr2_wait(const unsigned long long* slot, unsign
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
-    constexpr int kBlkBatch = (NT > 512) ? 4 : 8;   // loads of earlier pivots' multipliers issued together (register budget)
+    constexpr int kBlkBatch = (NT > 512) ? 4 : 16;   // loads of earlier pivots' multipliers issued together (register budget)
     __shared__ ArgMinF64 s_arg[32];
     __shared__ int s_int[32];
     __shared__ double s_vc[kBlkMax];       // V[lp][c]: the entering column's cell in the earlier pivot rows
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
     __shared__ int s_W[kBlkMax];           // ranks that owned them
     __shared__ double s_hratio[kMaxRanks]; // this pivot's candidates of all ranks
     __shared__ long long s_hrow[kMaxRanks];
-    __shared__ int s_w, s_flag;
+    __shared__ int s_flag;
     __shared__ long long s_row;
 
     const int nt = (int)blockDim.x, G = (int)gridDim.x, tid = (int)threadIdx.x, cta = (int)blockIdx.x;
@@ -204,7 +204,6 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
         double* On = P.O[cur ^ 1];
         const double* Bc = P.B[cur];
         double* Bn = P.B[cur ^ 1];
-
         // ---- A: stuck counter and rule (simplex.py:123,132-137), entering column ----
         long long stuck_now = stuck;
         if (pending) {
@@ -277,43 +276,31 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
         }
         best = block_argmin(best, s_arg);
         seq += 1;
-        if (tid == 0) {
-            if (solo) s_flag = 1;
-            else {
+        // this rank's best row: every CTA publishes its partial, waits for all of them and reduces them itself (one
+        // hop; a deciding CTA that reduces and then publishes the decision costs two)
+        if (!solo) {
+            if (tid == 0) {
                 __stcg(&P.rblk[cta].key, best.key);
                 __stcg(&P.rblk[cta].idx, best.idx);
                 __threadfence();
                 const unsigned long long old = atomicAdd(&sy->arrive1, 1ull);
-                s_flag = ((old + 1) % (unsigned long long)G == 0);
+                const unsigned long long target = (old / (unsigned long long)G + 1) * (unsigned long long)G;
+                s_flag = wait_seq_gpu(&sy->arrive1, target) ? 1 : 0;
             }
+            __syncthreads();
+            if (!s_flag) { status = LPS_E_PEER; break; }
+            best = ArgMinF64{0.0, INT_MAX};
+            for (int k = tid; k < G; k += nt) best = argmin_pick(best, ArgMinF64{__ldcg(&P.rblk[k].key), __ldcg(&P.rblk[k].idx)});
+            best = block_argmin(best, s_arg);
         }
-        __syncthreads();
-        if (s_flag) {
-            // the CTA that arrived last: this rank's best row.  Row-sharded: its candidate record goes to every rank.
-            if (!solo) {
-                __threadfence();
-                best = ArgMinF64{0.0, INT_MAX};
-                for (int k = tid; k < G; k += nt) best = argmin_pick(best, ArgMinF64{__ldcg(&P.rblk[k].key), __ldcg(&P.rblk[k].idx)});
-                best = block_argmin(best, s_arg);
-            }
+        {
             const int r = best.idx;
             const long long cand = (r == INT_MAX) ? -1 : g.row0 + r;
-            if (a.nranks > 1 && tid < a.nranks) hdr2_store(&a.peers[tid]->hdr2[seq & 1][a.rank][0], best.key, cand, seq);
-            if (tid == 0) {
-                if (solo) s_row = cand;
-                else {
-                    sy->dec_row = cand;
-                    __threadfence();
-                    st_release_gpu(&sy->dec_seq, seq);
-                }
-            }
+            // row-sharded: the rank's candidate record goes to every rank (one CTA sends it)
+            if (a.nranks > 1 && cta == 0 && tid < a.nranks) hdr2_store(&a.peers[tid]->hdr2[seq & 1][a.rank][0], best.key, cand, seq);
+            if (tid == 0) s_row = cand;
         }
-        if (!solo && tid == 0) {
-            if (wait_seq_gpu(&sy->dec_seq, seq)) { s_row = *reinterpret_cast<volatile long long*>(&sy->dec_row); s_w = 0; }
-            else s_w = -3;
-        } else if (solo && tid == 0) s_w = 0;
         __syncthreads();
-        if (s_w == -3) { status = LPS_E_PEER; break; }
         const long long cand_g = s_row;                         // this rank's candidate (global row), -1: none
 
         // ---- C: normalised candidate row -> the row area (every rank's copy); winner; objective row, right-hand
@@ -460,7 +447,6 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
         last_r = (int)r_g;
         last_c = c;
         cur ^= 1;
-
         // ---- end of pivot: everything this pivot wrote is visible before the next one reads it ----
         if (solo) __syncthreads();
         else {
