@@ -75,6 +75,11 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// fire-and-forget arrival: the release orders this thread's (and, through the preceding block barrier, its block's)
+// earlier stores before the increment becomes visible
+__device__ __forceinline__ void red_release_gpu(unsigned long long* p) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

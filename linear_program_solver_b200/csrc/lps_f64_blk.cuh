@@ -51,7 +51,10 @@ struct alignas(128) BlkSync {        // zeroed at lps_solve_begin; counters only
     unsigned long long pad3[13];
     unsigned long long ticket2;      // V-row slices finished (owner of the leaving row)
     unsigned long long exit_ticket;
-    unsigned long long pad4[14];
+    unsigned long long base1, base2; // arrive1 / arrive2 when the running launch started (written by the CTA that left
+                                     // the previous launch last): a CTA knows every barrier's target without reading back
+                                     // its own arrival, so arrivals are fire-and-forget reductions
+    unsigned long long pad4[12];
 };
 
 struct BlkPanel {
@@ -193,6 +196,8 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
     unsigned long long seq = st->xseq;
     int last_r = st->last_r, last_c = st->last_c;
     int cur = P.hdr[1];
+    const unsigned long long base1 = solo ? 0ull : sy->base1, base2 = solo ? 0ull : sy->base2;
+    unsigned long long nb1 = 0, nb2 = 0;                       // grid-wide synchronisations passed in this launch
     const int set = P.hdr[2] & 1;                              // row-area set of this block
     const size_t vset = (size_t)set * P.nr;
     auto Vrow = [&](int lp, int w) { return P.V + ((vset + w) * kBlkMax + lp) * g.ld; };   // rank w's candidate row of pivot lp
@@ -282,13 +287,12 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
             if (tid == 0) {
                 __stcg(&P.rblk[cta].key, best.key);
                 __stcg(&P.rblk[cta].idx, best.idx);
-                __threadfence();
-                const unsigned long long old = atomicAdd(&sy->arrive1, 1ull);
-                const unsigned long long target = (old / (unsigned long long)G + 1) * (unsigned long long)G;
-                s_flag = wait_seq_gpu(&sy->arrive1, target) ? 1 : 0;
+                red_release_gpu(&sy->arrive1);
+                s_flag = wait_seq_gpu(&sy->arrive1, base1 + (nb1 + 1) * (unsigned long long)G) ? 1 : 0;
             }
             __syncthreads();
             if (!s_flag) { status = LPS_E_PEER; break; }
+            ++nb1;
             best = ArgMinF64{0.0, INT_MAX};
             for (int k = tid; k < G; k += nt) best = argmin_pick(best, ArgMinF64{__ldcg(&P.rblk[k].key), __ldcg(&P.rblk[k].idx)});
             best = block_argmin(best, s_arg);
@@ -452,13 +456,12 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
         else {
             __syncthreads();
             if (tid == 0) {
-                __threadfence();
-                const unsigned long long old = atomicAdd(&sy->arrive2, 1ull);
-                const unsigned long long target = (old / (unsigned long long)G + 1) * (unsigned long long)G;
-                s_flag = wait_seq_gpu(&sy->arrive2, target) ? 1 : 0;
+                red_release_gpu(&sy->arrive2);
+                s_flag = wait_seq_gpu(&sy->arrive2, base2 + (nb2 + 1) * (unsigned long long)G) ? 1 : 0;
             }
             __syncthreads();
             if (!s_flag) { status = LPS_E_PEER; break; }
+            ++nb2;
         }
     }
     if (status == LPS_OK && maxp >= 0 && npiv >= maxp) status = LPS_MAX_PIVOTS;
@@ -474,6 +477,7 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
         bool last = true;
         if (!solo) last = ((atomicAdd(&sy->exit_ticket, 1ull) + 1) % (unsigned long long)G == 0);
         if (last) {
+            if (!solo) { sy->base1 = base1 + nb1 * (unsigned long long)G; sy->base2 = base2 + nb2 * (unsigned long long)G; }
             st->status = status;
             st->rule = rule;
             st->stuck = stuck;
