@@ -191,13 +191,15 @@ int lps_step_update(lps_handle *h);
  * reference's order and rounding (tableau.py:295-308).  Results are bit-identical to pivot-by-pivot updates; the grid
  * is read and written once per block instead of once per pivot.  On a row-sharded handle (after lps_p2p_attach) the
  * panel does the per-pivot argmin all-reduce and pivot-row broadcast with peer stores, like lps_step_select.
- * lps_set_block_size: 1..16 pivots per block, 0 = lps_solve runs the rank-1 loop (default: 16 from 1.5 M cells on, 0 below; or the
+ * lps_set_block_size: 1..16 pivots per block, 0 = lps_solve runs the rank-1 loop (default: 16 wherever the cluster panel fits -- up to about 7000 rows at n = 2m -- and from 1.5 M cells on, else 0; or the
  * environment variable LPS_F64_BLOCK). */
 int lps_step_block(lps_handle *h);
 int lps_block_size(lps_handle *h);
 int lps_set_block_size(lps_handle *h, int k);
 /* Launch shape of the panel (tuning / tests): 1 = one CTA of 1024 threads, >= 2 = that many CTAs of 256 threads
- * (at most one per SM).  The default follows the size of the tableau. */
+ * (at most one per SM), -8 / -16 = ONE thread-block cluster of 8 / 16 CTAs with the whole panel in distributed shared
+ * memory (medium tableaux, one rank; LPS_E_INVALID when it does not fit).  The default follows the size of the tableau:
+ * the cluster panel wherever it fits. */
 int lps_set_panel_ctas(lps_handle *h, int ctas);
 int lps_solve_poll(lps_handle *h, int *status, long long *npiv);
 int lps_solve_end(lps_handle *h, int *basis, int *marks, int *trace, long long trace_cap,

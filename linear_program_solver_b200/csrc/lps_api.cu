@@ -104,11 +104,27 @@ static void plan(lps_handle* h) {
         h->pan_blocks = std::max(2, std::min(std::max((h->m + kThreads - 1) / kThreads, (int)((h->ld / 2 + kThreads - 1) / kThreads)), std::min(sms, 256)));
     }
     h->sel_blocks = std::min(h->sel_blocks, sms);
+    // Medium tableaux: the whole panel fits the shared memory of one thread-block cluster (k_blk_panel_cl) -- no L2
+    // round trips and no global-memory barriers inside a pivot.  8 CTAs when that is enough, else 16.
+    h->pan_cluster = 0;
+    for (int C : {8, 16}) {
+        const int rpc = (h->m + C - 1) / C, cpc = (int)(((h->ld + C - 1) / C + 1) / 2 * 2);
+        if (blk_cluster_smem(rpc, cpc) <= (size_t)200 * 1024) { h->pan_cluster = C; h->pan_rpc = rpc; h->pan_cpc = cpc; break; }
+    }
+    if (const char* e = getenv("LPS_F64_PANEL_CLUSTER")) {
+        const int v = atoi(e);
+        if (v == 0) h->pan_cluster = 0;
+        else if (v == 8 || v == 16) {
+            const int rpc = (h->m + v - 1) / v, cpc = (int)(((h->ld + v - 1) / v + 1) / 2 * 2);
+            if (blk_cluster_smem(rpc, cpc) <= (size_t)200 * 1024) { h->pan_cluster = v; h->pan_rpc = rpc; h->pan_cpc = cpc; }
+        }
+    }
     h->sms = sms;
-    // Blocks pay once a pass over the grid costs more than the panel's latency per pivot (~15 us): from about a
-    // million cells on.  Below that the rank-1 loop (two short launches per pivot, replayed as a graph) is faster
-    // (500 x 1000: 82 k pivots/s against 68 k in blocks) and stays the default.
-    h->blk_k = ((size_t)(h->m + 1) * h->ld >= (size_t)1500000) ? kBlkMax : 0;
+    // Blocks pay wherever the panel decides a pivot faster than a (select, update) pair of the rank-1 loop runs: with
+    // the cluster panel at every size it fits (50 x 100: 81 k pivots/s against 36 k, 2000 x 4000: 95 k against 41 k,
+    // profiles/r02g_cluster_panel.txt), with the grid-wide panel once a pass over the grid costs more than its ~15 us
+    // per pivot -- from about 1.5 M cells on.
+    h->blk_k = (h->pan_cluster > 0 || (size_t)(h->m + 1) * h->ld >= (size_t)1500000) ? kBlkMax : 0;
     if (const char* e = getenv("LPS_F64_BLOCK")) { const int v = atoi(e); if (v >= 0 && v <= kBlkMax) h->blk_k = v; }
     if (const char* e = getenv("LPS_F64_PANEL_CTAS")) {   // tuning: 1 = one CTA of 1024 threads, >= 2 = that many CTAs of 256
         const int v = atoi(e);
@@ -162,6 +178,8 @@ extern "C" int lps_create_f64(int m, int n, int device, void* dev_grid, void* st
     plan(h);
     // the fused update's shared-memory ring (stages of the grid, pivot rows): far beyond the 48 KB default
     CU(cudaFuncSetAttribute(k_blk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkRing)));
+    CU(cudaFuncSetAttribute(k_blk_panel_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_blk_panel_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     const size_t ucol_n = ((size_t)m + 1 + kMaxRowBlock - 1) / kMaxRowBlock * kMaxRowBlock + kMaxRowBlock;
     const int maxchunks = (int)((h->ld + kNarrowChunk - 1) / kNarrowChunk);
     {   // the small buffers: one allocation (lps_internal.h, Slab)
@@ -390,7 +408,27 @@ static int blk_sync_panel(lps_handle* h) {
     h->blk_valid = true;
     return LPS_OK;
 }
+static int launch_panel_cluster(lps_handle* h) {
+    BlkClusterArgs a;
+    a.g = grid_of(h); a.p = h->blk; a.st = h->st; a.kmax = h->blk_k; a.rpc = h->pan_rpc; a.cpc = h->pan_cpc;
+    a.basis = h->basis; a.marks = h->use_marks ? h->marks : nullptr; a.trace = h->trace; a.trace_cap = h->trace_cap;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)h->pan_cluster, 1, 1);
+    cfg.blockDim = dim3(kClThreads, 1, 1);
+    cfg.dynamicSmemBytes = blk_cluster_smem(h->pan_rpc, h->pan_cpc);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)h->pan_cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_blk_panel_cl, a);
+    if (e != cudaSuccess) return fail(LPS_E_CUDA, "k_blk_panel_cl launch failed: %s", cudaGetErrorString(e));
+    h->launches_all++;
+    return LPS_OK;
+}
 static int launch_panel(lps_handle* h) {
+    if (h->pan_cluster > 0 && !(h->use_xchg && h->nranks > 1)) return launch_panel_cluster(h);
     BlkPanelArgs a;
     a.g = grid_of(h); a.p = h->blk; a.st = h->st; a.kmax = h->blk_k;
     a.xchg = h->xchg; a.peers = h->d_peers; a.rank = h->rank; a.nranks = h->use_xchg ? h->nranks : 1;
@@ -733,7 +771,16 @@ extern "C" int lps_set_panel_ctas(lps_handle* h, int ctas) {
     if (h->solving) return fail(LPS_E_STATE, "solve in progress");
     int sms = 148;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    if (ctas == -8 || ctas == -16) {   // one cluster of 8 / 16 CTAs with the panel in distributed shared memory
+        const int C = -ctas, rpc = (h->m + C - 1) / C, cpc = (int)(((h->ld + C - 1) / C + 1) / 2 * 2);
+        if (blk_cluster_smem(rpc, cpc) > (size_t)200 * 1024) return fail(LPS_E_INVALID, "the panel of a %d x %d tableau does not fit the shared memory of %d CTAs", h->m, h->n, C);
+        h->pan_cluster = C; h->pan_rpc = rpc; h->pan_cpc = cpc;
+        h->blk_valid = false;
+        if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+        return LPS_OK;
+    }
     if (ctas < 1 || ctas > std::min(sms, 256)) return fail(LPS_E_INVALID, "panel CTAs %d outside 1..%d", ctas, std::min(sms, 256));
+    h->pan_cluster = 0;
     h->pan_blocks = ctas;
     h->pan_threads = (ctas == 1) ? kSelMaxThreads : kThreads;
     h->blk_valid = false;
@@ -775,7 +822,7 @@ static int ensure_burst_graph(lps_handle* h, long long burst) {
     mix((unsigned long long)(uintptr_t)h->basis); mix(h->use_xchg ? 1 : 0); mix((unsigned long long)h->chunk);
     mix((unsigned long long)h->rows_per_cta); mix((unsigned long long)h->sel_blocks); mix((unsigned long long)h->sel_threads);
     mix((unsigned long long)(uintptr_t)h->cand_send); mix((unsigned long long)(uintptr_t)h->cand_all); mix((unsigned long long)burst);
-    mix((unsigned long long)h->blk_k); mix((unsigned long long)h->pan_blocks);
+    mix((unsigned long long)h->blk_k); mix((unsigned long long)h->pan_blocks); mix((unsigned long long)h->pan_cluster);
     mix((unsigned long long)h->n); mix((unsigned long long)(uintptr_t)h->T);
     if (h->gexec && h->gsig == sig && h->gburst == burst) return LPS_OK;
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }

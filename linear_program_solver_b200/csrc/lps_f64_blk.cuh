@@ -29,6 +29,8 @@
 //                      pricing partials of the new objective row, basis / marks / trace are committed
 //   k_blk_update  T <- T with the block's pivots applied, TMA-staged panel tiles, 128-bit streaming accesses
 #pragma once
+#include <cooperative_groups.h>
+
 #include "lps_f64.cuh"
 
 namespace lps {
@@ -487,6 +489,252 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
             st->last_r = last_r;
             st->last_c = last_c;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// panel for medium tableaux: one thread-block cluster, the whole panel in distributed shared memory
+// ------------------------------------------------------------------------------------------------
+// k_blk_panel spends most of a pivot on round trips to L2 and on three grid-wide synchronisations through global memory
+// (profiles/r02e_panel_phases.txt).  When the panel fits the shared memory of ONE cluster -- K (m + ld) doubles, up to
+// about 7000 rows at n = 2m with 16 CTAs -- none of that is needed: CTA k of the cluster owns rows [k rpc, (k+1) rpc)
+// (their multipliers U, right-hand side) and columns [k cpc, (k+1) cpc) (their pivot-row cells V, objective row), all
+// in its shared memory; the only global reads of a pivot are the two gathers from the grid (entering column, leaving
+// row), partial arg-mins are written into every CTA's shared memory (DSMEM) and the two synchronisations per pivot
+// are hardware cluster barriers.  Same decisions, same records for k_blk_update (written through to global memory).
+// One rank only.
+namespace cg = cooperative_groups;
+constexpr int kClThreads = 512;
+constexpr int kClMax = 16;
+
+struct BlkClusterArgs {
+    F64Grid g;
+    BlkPanel p;
+    SolveState* st;
+    int kmax;
+    int rpc, cpc;        // rows / columns per CTA (cpc even)
+    int* basis;
+    int* marks;
+    int* trace;
+    long long trace_cap;
+};
+__host__ __device__ inline size_t blk_cluster_smem(int rpc, int cpc) {
+    return ((size_t)(kBlkMax + 2) * (rpc + cpc)) * sizeof(double) + (size_t)rpc * sizeof(uint2) + 256;
+}
+
+__global__ void __launch_bounds__(kClThreads, 1) k_blk_panel_cl(BlkClusterArgs a) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int C = (int)cl.num_blocks(), me = (int)cl.block_rank();
+    const int tid = (int)threadIdx.x, nt = kClThreads;
+    extern __shared__ __align__(16) unsigned char cl_smem[];
+    const int rpc = a.rpc, cpc = a.cpc;
+    double* sU = reinterpret_cast<double*>(cl_smem);            // [kBlkMax][rpc]  multipliers of my rows
+    double* sV = sU + (size_t)kBlkMax * rpc;                    // [kBlkMax][cpc]  pivot-row cells of my columns
+    double* sO = sV + (size_t)kBlkMax * cpc;                    // [2][cpc]        objective row, my columns
+    double* sB = sO + 2 * (size_t)cpc;                          // [2][rpc]        right-hand side, my rows
+    uint2* sM = reinterpret_cast<uint2*>(sB + 2 * (size_t)rpc); // [rpc]           zero / pivot-row masks of my rows
+    __shared__ ArgMinF64 s_arg[32];
+    __shared__ int s_int[32];
+    __shared__ ArgMinF64 s_rat[kClMax], s_prc[kClMax];          // partials of every CTA (written remotely)
+    __shared__ int s_bld[kClMax];
+    __shared__ double s_vc[kBlkMax], s_ur[kBlkMax];
+    __shared__ long long s_R[kBlkMax];
+
+    SolveState* st = a.st;
+    const F64Grid& g = a.g;
+    const BlkPanel& P = a.p;
+    int status = st->status;
+    if (status != LPS_OK) {
+        if (me == 0 && tid == 0) P.hdr[0] = 0;
+        return;
+    }
+    int rule = st->rule;
+    long long stuck = st->stuck, npiv = st->npiv;
+    const long long maxp = st->max_pivots;
+    int pending = st->pending_zcheck;
+    const double z_entry = st->z_entry_cell;
+    int last_r = st->last_r, last_c = st->last_c;
+    int cur = P.hdr[1];
+    const int set = P.hdr[2] & 1;
+    const size_t vset = (size_t)set * P.nr;
+    const int row_lo = me * rpc, nrows = max(0, min(rpc, g.m - row_lo));
+    const int col_lo = me * cpc, ncols = max(0, min(cpc, (int)g.ld - col_lo));
+    auto remote = [&](auto* p, int rank) { return cl.map_shared_rank(p, rank); };
+
+    // panel state in: my slices of the objective row and the right-hand side; pricing partials of my slice
+    {
+        ArgMinF64 pb{0.0, INT_MAX};
+        int first_neg = INT_MAX;
+        for (int jl = tid; jl < ncols; jl += nt) {
+            const double v = P.O[cur][col_lo + jl];
+            sO[(size_t)cur * cpc + jl] = v;
+            price_consider(v, col_lo + jl, g.n, pb, first_neg);
+        }
+        for (int il = tid; il < nrows; il += nt) sB[(size_t)cur * rpc + il] = P.B[cur][row_lo + il];
+        pb = block_argmin(pb, s_arg);
+        first_neg = block_min_int(first_neg, s_int);
+        if (tid < C) { *remote(&s_prc[me], tid) = pb; *remote(&s_bld[me], tid) = first_neg; }
+    }
+    cl.sync();
+
+    int l = 0;
+    for (; l < a.kmax; ++l) {
+        if (maxp >= 0 && npiv >= maxp) { status = LPS_MAX_PIVOTS; break; }
+        const double* Oc = sO + (size_t)cur * cpc;
+        double* On = sO + (size_t)(cur ^ 1) * cpc;
+        const double* Bc = sB + (size_t)cur * rpc;
+        double* Bn = sB + (size_t)(cur ^ 1) * rpc;
+        const int cta_n = g.n / cpc;                              // owner of the corner cell / right-hand side column
+
+        // ---- A: stuck counter and rule, entering column (from the partials every CTA holds) ----
+        long long stuck_now = stuck;
+        if (pending) {
+            const double corner = *remote(sO + (size_t)cur * cpc + (g.n - cta_n * cpc), cta_n);
+            if (!(corner >= z_entry)) { status = LPS_OBJ_INCREASED; break; }
+            stuck_now = (corner == z_entry) ? stuck + 1 : 0;
+        }
+        int rule_now = rule;
+        if (rule_now == LPS_RULE_DANTZIG && !(stuck_now < g.m_total + (long long)g.n)) rule_now = LPS_RULE_BLAND;
+        int c = INT_MAX;
+        if (rule_now == LPS_RULE_DANTZIG) {
+            ArgMinF64 best{0.0, INT_MAX};
+            for (int k = 0; k < C; ++k) best = argmin_pick(best, s_prc[k]);
+            c = best.idx;
+        } else {
+            for (int k = 0; k < C; ++k) c = min(c, s_bld[k]);
+        }
+        if (c == INT_MAX) { status = LPS_OPTIMAL; break; }
+        const int cta_c = c / cpc, c_loc = c - cta_c * cpc;
+
+        // ---- B: column c through the block's earlier pivots -> my rows' multipliers; ratio test ----
+        if (tid < l) s_vc[tid] = *remote(sV + (size_t)tid * cpc + c_loc, cta_c);
+        const double uobj = *remote(sO + (size_t)cur * cpc + c_loc, cta_c);
+        __syncthreads();
+        ArgMinF64 best{0.0, INT_MAX};
+        for (int il = tid; il < nrows; il += nt) {
+            const int i = row_lo + il;
+            double x = g.T[(size_t)i * g.ld + c];
+            for (int lp = 0; lp < l; ++lp)
+                x = (s_R[lp] == (long long)i) ? s_vc[lp] : blk_apply(x, sU[(size_t)lp * rpc + il], s_vc[lp]);
+            sU[(size_t)l * rpc + il] = x;
+            double* rec = P.U + (size_t)i * kBlkRec;
+            __stcg(&rec[l], x);
+            uint2 mk = (l == 0) ? make_uint2(0u, 0u) : sM[il];
+            if (x == 0.0) mk.x |= 1u << l;
+            sM[il] = mk;
+            if (l == 0 || x == 0.0) __stcg(reinterpret_cast<uint2*>(rec + kBlkMax), mk);
+            if (x > 0.0) {
+                const double ratio = Bc[il] / x;
+                if (best.idx == INT_MAX || ratio < best.key) { best.key = ratio; best.idx = i; }
+            }
+        }
+        if (me == 0 && tid == 0) {
+            double* rec = P.U + (size_t)g.m * kBlkRec;
+            __stcg(&rec[l], uobj);
+            uint2 mk = (l == 0) ? make_uint2(0u, 0u) : __ldcg(reinterpret_cast<const uint2*>(rec + kBlkMax));
+            if (uobj == 0.0) mk.x |= 1u << l;
+            if (l == 0 || uobj == 0.0) __stcg(reinterpret_cast<uint2*>(rec + kBlkMax), mk);
+        }
+        best = block_argmin(best, s_arg);
+        if (tid < C) *remote(&s_rat[me], tid) = best;
+        cl.sync();
+        best = ArgMinF64{0.0, INT_MAX};
+        for (int k = 0; k < C; ++k) best = argmin_pick(best, s_rat[k]);
+        if (best.idx == INT_MAX) { status = LPS_UNBOUNDED; break; }
+        const int r = best.idx;                                 // leaving row (global = local: one rank)
+        const int cta_r = r / rpc, r_loc = r - cta_r * rpc;
+
+        // ---- C: row r through the earlier pivots, normalised -> my columns' cells; objective row; right-hand side ----
+        if (tid < l) s_ur[tid] = *remote(sU + (size_t)tid * rpc + r_loc, cta_r);
+        const double pv = *remote(sU + (size_t)l * rpc + r_loc, cta_r);
+        const double br = *remote(sB + (size_t)cur * rpc + r_loc, cta_r);
+        __syncthreads();
+        const double inv = 1.0 / pv;                            // rowDiv: ONE / d, then rowMult (tableau.py:262-267)
+        const double vn = (inv != 1.0) ? __dmul_rn(br, inv) : br;
+        ArgMinF64 pb{0.0, INT_MAX};
+        int first_neg = INT_MAX;
+        {
+            const double* src = g.T + (size_t)r * g.ld + col_lo;
+            double* Vg = P.V + ((vset + 0) * kBlkMax + l) * g.ld + col_lo;
+            for (int jl = 2 * tid; jl < ncols; jl += 2 * nt) {
+                double2 y = *reinterpret_cast<const double2*>(src + jl);
+                for (int lp = 0; lp < l; ++lp) {
+                    const double2 v = *reinterpret_cast<const double2*>(sV + (size_t)lp * cpc + jl);
+                    if (s_R[lp] == (long long)r) y = v;
+                    else { y.x = blk_apply(y.x, s_ur[lp], v.x); y.y = blk_apply(y.y, s_ur[lp], v.y); }
+                }
+                if (inv != 1.0) { y.x = __dmul_rn(y.x, inv); y.y = __dmul_rn(y.y, inv); }
+                *reinterpret_cast<double2*>(sV + (size_t)l * cpc + jl) = y;
+                stcg2(Vg + jl, y);
+                double2 o = *reinterpret_cast<const double2*>(Oc + jl);
+                o.x = blk_apply(o.x, uobj, y.x);
+                o.y = blk_apply(o.y, uobj, y.y);
+                *reinterpret_cast<double2*>(On + jl) = o;
+                price_consider(o.x, col_lo + jl, g.n, pb, first_neg);
+                price_consider(o.y, col_lo + jl + 1, g.n, pb, first_neg);
+            }
+        }
+        for (int il = tid; il < nrows; il += nt) {
+            const int i = row_lo + il;
+            double b;
+            if (i == r) {
+                b = vn;
+                uint2 mk = sM[il];
+                mk.y |= 1u << l;
+                sM[il] = mk;
+                __stcg(reinterpret_cast<uint2*>(P.U + (size_t)i * kBlkRec + kBlkMax), mk);
+            } else b = blk_apply(Bc[il], sU[(size_t)l * rpc + il], vn);
+            Bn[il] = b;
+        }
+        pb = block_argmin(pb, s_arg);
+        first_neg = block_min_int(first_neg, s_int);
+        if (tid < C) { *remote(&s_prc[me], tid) = pb; *remote(&s_bld[me], tid) = first_neg; }
+        if (tid == 0) {
+            s_R[l] = r;
+            if (me == 0) {   // commit (Simplex._pivot simplex.py:192-197)
+                P.R[l] = r;
+                P.C[l] = c;
+                P.W[l] = 0;
+                if (a.trace && npiv < a.trace_cap) {
+                    a.trace[3 * npiv] = r;
+                    a.trace[3 * npiv + 1] = c;
+                    a.trace[3 * npiv + 2] = rule_now;
+                }
+                if (a.marks) {
+                    const int old = a.basis[r];
+                    if (old >= 0 && old < g.n) a.marks[old] = 0;
+                    a.marks[c] = 1;
+                }
+                a.basis[r] = c;
+            }
+        }
+        npiv += 1;
+        rule = rule_now;
+        stuck = stuck_now;
+        pending = (rule_now == LPS_RULE_DANTZIG);
+        last_r = r;
+        last_c = c;
+        cur ^= 1;
+        cl.sync();
+    }
+    if (status == LPS_OK && maxp >= 0 && npiv >= maxp) status = LPS_MAX_PIVOTS;
+
+    // panel state out
+    for (int jl = tid; jl < ncols; jl += nt) P.O[cur][col_lo + jl] = sO[(size_t)cur * cpc + jl];
+    for (int il = tid; il < nrows; il += nt) P.B[cur][row_lo + il] = sB[(size_t)cur * rpc + il];
+    cl.sync();                                                  // nobody reads a CTA's shared memory after it has left
+    if (me == 0 && tid == 0) {
+        P.hdr[0] = l;
+        P.hdr[1] = cur;
+        P.hdr[3] = set;
+        if (l > 0) P.hdr[2] = P.hdr[2] + 1;
+        st->status = status;
+        st->rule = rule;
+        st->stuck = stuck;
+        st->npiv = npiv;
+        st->pending_zcheck = pending;
+        st->last_r = last_r;
+        st->last_c = last_c;
     }
 }
 

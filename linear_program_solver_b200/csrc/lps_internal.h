@@ -74,6 +74,8 @@ struct lps_handle {
     int blk_k = kBlkMax;             // pivots decided per panel launch (1..kBlkMax); 0: rank-1 path only
     int sms = 148;                   // SMs of the device: size of the persistent grids
     int pan_blocks = 1, pan_threads = 256;
+    int pan_cluster = 0;             // > 0: the panel is ONE cluster of that many CTAs, state in distributed shared memory
+    int pan_rpc = 0, pan_cpc = 0;    // rows / columns per CTA of the cluster panel
     BlkPanel blk{};
     bool blk_valid = false;          // O / B / pricing partials of the panel describe the grid
     bool pp_valid = false;           // pd_val / pd_idx / pb_idx (rank-1 path) describe the grid's objective row

@@ -65,8 +65,12 @@ class ShardedF64Solver:
         # pivots per block of the blocked loop (peer-store exchange only; the collective exchange is per pivot)
         self.block = 0
         if self.exchange == "p2p" and hasattr(self.eng, "block_size"):
-            if block is not None:
-                self.eng.set_block_size(block)
+            if block is None:
+                # the library picks blocks from 1.5 M cells on, by the handle's OWN rows; shards differ by a row, and
+                # every rank must run the same loop: decide from the largest shard, like the burst below
+                ld = int(self.eng.L.lps_grid_ld(self.n))
+                block = 16 if (-(-self.m_total // nranks) + 1) * ld >= 1_500_000 else 0
+            self.eng.set_block_size(block)
             self.block = self.eng.block_size()
         # pivots enqueued between two host checks: ~2 ms of device work, between 4 and 256.  The same number on every
         # rank -- every enqueued pivot is a collective with exchange="nccl" -- so it is derived from the LARGEST

@@ -54,10 +54,11 @@ def test_block_sizes_bit_identical_to_oracle(block, m, seed):
     _check_solve(_grid(m, seed), np.arange(m, 2 * m, dtype=np.int32), block)
 
 
-@pytest.mark.parametrize("ctas", [1, 2, 7, 64, 148])
+@pytest.mark.parametrize("ctas", [1, 2, 7, 64, 148, -8, -16])
 @pytest.mark.parametrize("m,seed", [(50, 1), (333, 2)])
 def test_panel_launch_shapes_agree(ctas, m, seed):
-    """One CTA of 1024 threads and grids that synchronise through memory make the same decisions."""
+    """One CTA of 1024 threads, grids that synchronise through memory and one thread-block cluster with the panel in
+    distributed shared memory (-8, -16) make the same decisions."""
     _check_solve(_grid(m, seed), np.arange(m, 2 * m, dtype=np.int32), 16, ctas=ctas)
 
 
@@ -67,10 +68,11 @@ def test_prefix_stops_inside_a_block(max_pivots):
     T = _grid(m, 5)
     _check_solve(T, np.arange(m, 2 * m, dtype=np.int32), 16, max_pivots=max_pivots)
     _check_solve(T, np.arange(m, 2 * m, dtype=np.int32), 16, ctas=5, max_pivots=max_pivots)
+    _check_solve(T, np.arange(m, 2 * m, dtype=np.int32), 16, ctas=-8, max_pivots=max_pivots)
 
 
 @pytest.mark.parametrize("m,parts,seed", [(48, 3, 0), (64, 4, 6), (80, 4, 2)])
-@pytest.mark.parametrize("ctas", [1, 6])
+@pytest.mark.parametrize("ctas", [1, 6, -8, -16])
 def test_tie_heavy_tableaux(m, parts, seed, ctas):
     """Ties in the ratio test, degenerate pivots (zero right-hand sides), rows that leave again within a block."""
     T = problems.tie_heavy_grid(m, parts, seed)
@@ -97,7 +99,7 @@ def _sparse_canonical(m, n_struct, seed):
 
 
 @pytest.mark.parametrize("seed", range(8))
-@pytest.mark.parametrize("ctas", [1, 3])
+@pytest.mark.parametrize("ctas", [1, 3, -8])
 def test_sparse_mixed_sign_tableaux(seed, ctas):
     m, ns = 30 + 3 * seed, 40 + 5 * seed
     T = _sparse_canonical(m, ns, seed)
@@ -112,7 +114,7 @@ def test_beale_cycling_rule_switch_inside_blocks():
     c, A, b = problems.BEALE
     T = np.array(problems.to_grid([float(x) for x in c], [[float(x) for x in r] for r in A], [float(x) for x in b]))
     g = load_golden("special")["beale_float"]
-    for block, ctas in [(16, 1), (16, 4), (3, 1), (7, 2)]:
+    for block, ctas in [(16, 1), (16, 4), (3, 1), (7, 2), (16, -8), (5, -16)]:
         e = _engine(T, block, ctas)
         basis = np.array([0, 1, 2], dtype=np.int32)
         st, npiv, trace = e.solve(basis, None, trace_cap=64)
@@ -127,7 +129,7 @@ def test_unbounded_is_reported_after_the_decided_pivots_are_applied():
     T0 = np.array([[1.0, -1.0, 1.0, 0.0, 1.0],
                    [-1.0, 0.0, 0.0, 1.0, 2.0],
                    [-1.0, -1.0, 0.0, 0.0, 0.0]])
-    for block, ctas in [(16, 1), (16, 2), (1, 1)]:
+    for block, ctas in [(16, 1), (16, 2), (1, 1), (16, -8)]:
         e = _engine(T0, block, ctas)
         basis = np.array([2, 3], dtype=np.int32)
         st, npiv, trace = e.solve(basis, None, trace_cap=16)
@@ -164,6 +166,24 @@ def test_stepping_blocks_and_rank1_steps_can_be_mixed():
     ob = np.arange(m, 2 * m, dtype=np.int32)
     ost, ok, otrace = C.solve(T, ob)
     assert (st, k) == (ost, ok) and trace.tolist() == otrace.tolist() and basis.tolist() == ob.tolist()
+    assert e.download().tobytes() == T.tobytes()
+    e.close()
+
+
+@pytest.mark.parametrize("m,seed,block", [(1200, 0, 16), (2000, 0, 16), (700, 3, 7)])
+def test_medium_tableaux_take_the_cluster_panel_by_default(m, seed, block):
+    """The default plan of a medium tableau: the panel as one cluster (8 CTAs here), whole solve against the oracle."""
+    T = problems.hashed_dense_grid(m, seed).astype(np.float64)
+    from linear_program_solver_b200.engine import F64Engine
+    from oracle import c_oracle as C
+    e = F64Engine(m, 2 * m)
+    e.set_block_size(block)
+    e.upload(T)
+    basis = np.arange(m, 2 * m, dtype=np.int32)
+    st, npiv, trace = e.solve(basis, None, trace_cap=1 << 16)
+    ob = np.arange(m, 2 * m, dtype=np.int32)
+    ost, ok, otrace = C.solve(T, ob)
+    assert (st, npiv) == (ost, ok) and trace.tolist() == otrace.tolist() and basis.tolist() == ob.tolist()
     assert e.download().tobytes() == T.tobytes()
     e.close()
 
