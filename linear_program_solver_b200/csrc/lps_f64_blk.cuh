@@ -607,13 +607,15 @@ __global__ void __launch_bounds__(kClThreads, 1) k_blk_panel_cl(BlkClusterArgs a
         const int cta_c = c / cpc, c_loc = c - cta_c * cpc;
 
         // ---- B: column c through the block's earlier pivots -> my rows' multipliers; ratio test ----
+        double x_first = 0.0;                                     // (issued before the block waits for the remote cells)
+        if (tid < nrows) x_first = g.T[(size_t)(row_lo + tid) * g.ld + c];
         if (tid < l) s_vc[tid] = *remote(sV + (size_t)tid * cpc + c_loc, cta_c);
         const double uobj = *remote(sO + (size_t)cur * cpc + c_loc, cta_c);
         __syncthreads();
         ArgMinF64 best{0.0, INT_MAX};
         for (int il = tid; il < nrows; il += nt) {
             const int i = row_lo + il;
-            double x = g.T[(size_t)i * g.ld + c];
+            double x = (il == tid) ? x_first : g.T[(size_t)i * g.ld + c];
             for (int lp = 0; lp < l; ++lp)
                 x = (s_R[lp] == (long long)i) ? s_vc[lp] : blk_apply(x, sU[(size_t)lp * rpc + il], s_vc[lp]);
             sU[(size_t)l * rpc + il] = x;
@@ -645,6 +647,8 @@ __global__ void __launch_bounds__(kClThreads, 1) k_blk_panel_cl(BlkClusterArgs a
         const int cta_r = r / rpc, r_loc = r - cta_r * rpc;
 
         // ---- C: row r through the earlier pivots, normalised -> my columns' cells; objective row; right-hand side ----
+        double2 y_first = make_double2(0.0, 0.0);
+        if (2 * tid < ncols) y_first = *reinterpret_cast<const double2*>(g.T + (size_t)r * g.ld + col_lo + 2 * tid);
         if (tid < l) s_ur[tid] = *remote(sU + (size_t)tid * rpc + r_loc, cta_r);
         const double pv = *remote(sU + (size_t)l * rpc + r_loc, cta_r);
         const double br = *remote(sB + (size_t)cur * rpc + r_loc, cta_r);
@@ -657,7 +661,7 @@ __global__ void __launch_bounds__(kClThreads, 1) k_blk_panel_cl(BlkClusterArgs a
             const double* src = g.T + (size_t)r * g.ld + col_lo;
             double* Vg = P.V + ((vset + 0) * kBlkMax + l) * g.ld + col_lo;
             for (int jl = 2 * tid; jl < ncols; jl += 2 * nt) {
-                double2 y = *reinterpret_cast<const double2*>(src + jl);
+                double2 y = (jl == 2 * tid) ? y_first : *reinterpret_cast<const double2*>(src + jl);
                 for (int lp = 0; lp < l; ++lp) {
                     const double2 v = *reinterpret_cast<const double2*>(sV + (size_t)lp * cpc + jl);
                     if (s_R[lp] == (long long)r) y = v;
