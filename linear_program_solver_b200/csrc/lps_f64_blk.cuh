@@ -17,17 +17,19 @@
 // updates the whole tableau after every pivot.  k_blk_update then applies the K pivots to every cell with the same
 // per-cell sequence: one read and one write of the tableau per K pivots.
 //
-//   k_blk_init    O <- objective row, B <- right-hand side, pricing partials (at lps_solve_begin)
-//   k_blk_panel   persistent grid (<= one CTA per SM), two grid-wide synchronisations per pivot:
-//                   A  pricing from the partials (Dantzig simplex.py:262-267 / Bland :228-232), stuck counter and
-//                      rule switch (simplex.py:118-137), redundantly in every CTA
-//                   B  column c gathered + corrected -> U[l], ratio test (simplex.py:272-279) over the CTA's rows
-//                      -> the CTA that arrives last reduces the partials and -- row-sharded tableaux -- exchanges the
-//                      64-byte candidate header with every peer GPU by peer stores (the argmin all-reduce)
-//                   C  the owner of the leaving row gathers + corrects + normalises it -> V[l] (stored into every
-//                      peer GPU's panel: the pivot-row broadcast), objective row and right-hand side move on,
-//                      pricing partials of the new objective row, basis / marks / trace are committed
-//   k_blk_update  T <- T with the block's pivots applied, TMA-staged panel tiles, 128-bit streaming accesses
+//   k_blk_init      O <- objective row, B <- right-hand side, pricing partials (first block of a solve)
+//   k_blk_panel     persistent grid (<= one CTA per SM), two grid-wide synchronisations per pivot:
+//                     A  pricing from the partials (Dantzig simplex.py:262-267 / Bland :228-232), stuck counter, rule
+//                        switch and objective assert (simplex.py:118-137), redundantly in every CTA
+//                     B  column c gathered + corrected -> the rows' records, ratio test (simplex.py:272-279) over the
+//                        CTA's rows; every CTA then reduces all partials itself
+//                     C  the candidate row gathered + corrected + normalised -> V[l]; row-sharded tableaux: every rank
+//                        sends a self-validating candidate record and its candidate row to every rank (ONE exchange
+//                        per pivot, peer stores over NVLink) and every CTA picks the winner itself; objective row and
+//                        right-hand side move on, pricing partials, basis / marks / trace are committed
+//   k_blk_panel_cl  the same decisions for tableaux whose panel fits the shared memory of ONE thread-block cluster:
+//                   state in distributed shared memory, partials through DSMEM, hardware cluster barriers
+//   k_blk_update    T <- T with the block's pivots applied: persistent, warp-specialised, TMA ring in shared memory
 #pragma once
 #include <cooperative_groups.h>
 
@@ -42,21 +44,16 @@ constexpr int kBlkRec = kBlkMax + 2;   // doubles per row record of the panel's 
 constexpr int kBlkStages = 6;          // stages of the update's shared-memory ring
 constexpr int kBlkConsumers = 256;     // consumer threads of the fused update (one double2 column each)
 
-struct alignas(128) BlkSync {        // zeroed at lps_solve_begin; counters only ever grow
-    unsigned long long arrive1;      // phase B arrivals: the CTA that makes it a multiple of the grid size decides
+struct alignas(128) BlkSync {        // zeroed when the panel state is (re)read from the grid; counters only ever grow
+    unsigned long long arrive1;      // ratio-test partials published (grid-wide synchronisation 1 of a pivot)
     unsigned long long pad1[15];
-    unsigned long long arrive2;      // end-of-pivot barrier
+    unsigned long long arrive2;      // end-of-pivot synchronisation
     unsigned long long pad2[15];
-    unsigned long long dec_seq;      // decision of select round `seq` published
-    long long dec_row;
-    int dec_w, dec_pad;
+    unsigned long long exit_ticket;  // the CTA that leaves a launch last writes the solver state back
+    unsigned long long base1, base2; // arrive1 / arrive2 when the running launch started (written by that last CTA): a
+                                     // CTA knows every synchronisation's target without reading back its own arrival,
+                                     // so arrivals are fire-and-forget release reductions
     unsigned long long pad3[13];
-    unsigned long long ticket2;      // V-row slices finished (owner of the leaving row)
-    unsigned long long exit_ticket;
-    unsigned long long base1, base2; // arrive1 / arrive2 when the running launch started (written by the CTA that left
-                                     // the previous launch last): a CTA knows every barrier's target without reading back
-                                     // its own arrival, so arrivals are fire-and-forget reductions
-    unsigned long long pad4[12];
 };
 
 struct BlkPanel {

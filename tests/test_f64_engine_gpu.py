@@ -240,8 +240,9 @@ def _same_bits(a: np.ndarray, b: np.ndarray, rows: int = 1024) -> bool:
 
 def test_c4_full_size_prefix_bit_identical_to_oracle(eng_mod):
     """BASELINE.json config 4 at its full size, 32768 x 65536 (17.2 GB): the seeded family generated on the device
-    equals the oracle's, and after a 3-pivot prefix of the solve loop the whole tableau, the pivot trace and the
-    basis are byte-identical to the C oracle's (about 15 s: one download and three CPU pivots)."""
+    equals the oracle's, and after a 19-pivot prefix of the solve loop -- one full block of 16 through the grid-wide
+    panel and the fused update's fast path, then a short block of 3 -- the whole tableau, the pivot trace and the basis
+    are byte-identical to the C oracle's (about 25 s: two downloads and 19 CPU pivots)."""
     import torch
     from oracle import c_oracle as C
     m = 32768
@@ -249,6 +250,7 @@ def test_c4_full_size_prefix_bit_identical_to_oracle(eng_mod):
     if _mem_available() < 2.4 * need or torch.cuda.mem_get_info()[0] < 1.1 * need:
         pytest.skip("needs about 40 GB of host memory and 19 GB of device memory")
     e = eng_mod.F64Engine(m, 2 * m)
+    assert e.block_size() == 16                                   # the blocked loop is what runs at this size
     e.fill_dense(0, 1, 9)
     T = np.empty((m + 1, 2 * m + 1), dtype=np.float64)
     C.fill_dense(T, m, 0, 0, 1, 9)
@@ -256,10 +258,10 @@ def test_c4_full_size_prefix_bit_identical_to_oracle(eng_mod):
     assert _same_bits(got, T)                                     # same input on both sides
     del got
     basis = np.arange(m, 2 * m, dtype=np.int32)
-    st, npiv, trace = e.solve(basis, None, max_pivots=3, trace_cap=3)
+    st, npiv, trace = e.solve(basis, None, max_pivots=19, trace_cap=19)
     ob = np.arange(m, 2 * m, dtype=np.int32)
-    ost, ok, otrace = C.solve(T, ob, max_pivots=3)
-    assert (st, npiv) == (4, 3) and ok == 3
+    ost, ok, otrace = C.solve(T, ob, max_pivots=19)
+    assert (st, npiv) == (4, 19) and ok == 19
     assert trace.tolist() == otrace.tolist() and basis.tolist() == ob.tolist()
     got = e.download()
     assert _same_bits(got, T)
