@@ -810,6 +810,12 @@ extern "C" int lps_solve_end(lps_handle* h, int* basis, int* marks, int* trace, 
         if (cnt > 0) CU(cudaMemcpyAsync(trace, h->trace, (size_t)cnt * 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     }
     CU(cudaStreamSynchronize(h->stream));
+    if (h->st_host->status == LPS_E_PEER) {
+        static const char* what[] = {"?", "the panel's first grid-wide synchronisation", "a peer's candidate record", "the winner's slice record",
+                                     "the winner's row slice (its checksum never agreed)", "the panel's end-of-pivot synchronisation"};
+        const int k = -100 - h->st_host->last_r;
+        return fail(LPS_E_PEER, "the blocked loop gave up after %lld pivots waiting for %s", (long long)h->st_host->npiv, what[(k >= 1 && k <= 5) ? k : 0]);
+    }
     return h->st_host->status;
 }
 
@@ -957,6 +963,14 @@ static int attach_blocks(lps_handle* h, long long row0, long long m_total, int r
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     h->row0 = row0; h->m_total = m_total; h->rank = rank; h->nranks = nranks;
     h->use_xchg = (nranks > 1);          // one rank: k_select writes the normalised row itself, no exchange
+    if (nranks > 1) {
+        // the panel's slices of a candidate row are exchanged CTA by CTA: every rank must cut the row the same way, so
+        // the launch shape follows the LARGEST shard (shards differ by a row), not this handle's own rows
+        const int mm = (int)((m_total + nranks - 1) / nranks);
+        h->pan_threads = kThreads;
+        h->pan_blocks = std::max(2, std::min(std::max((mm + kThreads - 1) / kThreads, (int)((h->ld / 2 + kThreads - 1) / kThreads)), std::min(h->sms, 256)));
+        h->pan_cluster = 0;
+    }
     CU(cudaFree(h->basis));
     CU(cudaMalloc(&h->basis, (size_t)m_total * sizeof(int)));
     CU(cudaMemsetAsync(h->basis, 0xff, (size_t)m_total * sizeof(int), h->stream));

@@ -54,9 +54,12 @@ struct XchgBlock {
     // blocked loop (lps_f64_blk.cuh): ONE exchange per pivot.  Every rank stores a 32-byte self-validating candidate
     // record (ratio bits, row | sequence number << 32, check word) into slot `rank` of every rank's hdr2 -- no fence,
     // no flag: a reader takes a record only when its sequence number and check word agree -- and its own normalised
-    // candidate row into every rank's row area, slice by slice, each slice followed by rowflag[rank][cta] = sequence.
+    // candidate row into every rank's row area, slice by slice, each slice followed by a record of the same kind in
+    // rowrec[rank][cta]: a position-weighted checksum of the slice, the sequence number, the row's right-hand side.
+    // No fence there either: the receiver reads the slice (it needs it anyway), recomputes the checksum and reads
+    // again until it agrees -- a record that overtakes its data is noticed, not trusted.
     unsigned long long hdr2[2][kMaxRanks][4];
-    unsigned long long rowflag[kMaxRanks][kMaxPanelCtas];
+    unsigned long long rowrec[2][kMaxRanks][kMaxPanelCtas][4];   // by sequence parity, like hdr2: a rank can be one pivot ahead
     // followed by the row area (128-byte aligned): the rank-1 loop uses its first ld doubles (vrow); the blocked loop
     // [set 2][rank nranks][pivot kBlkMax][ld]
 };

@@ -159,6 +159,46 @@ __device__ __forceinline__ bool hdr2_wait(const unsigned long long* slot, unsign
     }
 }
 
+// ---- slice records of the one-exchange protocol (XchgBlock::rowrec) ----
+// checksum of a row slice: sum over its cells of (bit pattern) x (odd weight from the column index), modulo 2^64
+__device__ __forceinline__ unsigned long long slice_term(double2 y, int j) {
+    return (unsigned long long)__double_as_longlong(y.x) * (2ull * (unsigned long long)j + 1ull) +
+           (unsigned long long)__double_as_longlong(y.y) * (2ull * (unsigned long long)j + 3ull);
+}
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    unsigned long long r = (lane < nwarps) ? scratch[lane] : 0ull;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+    return r;
+}
+__device__ __forceinline__ void rowrec_store(unsigned long long* slot, unsigned long long sum, unsigned long long seq, double vn) {
+    const unsigned long long w2 = (unsigned long long)__double_as_longlong(vn);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(slot), "l"(sum), "l"(seq) : "memory");
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(slot + 2), "l"(w2), "l"(sum ^ seq ^ w2 ^ kHdrMagic) : "memory");
+}
+__device__ __forceinline__ bool rowrec_wait(const unsigned long long* slot, unsigned long long seq, unsigned long long* sum, double* vn) {
+    const unsigned long long t0 = global_ns();
+    unsigned int polls = 0;
+    for (;;) {
+        const unsigned long long w1 = ld_relaxed_sys(slot + 1);
+        if (w1 == seq) {
+            const unsigned long long w0 = ld_relaxed_sys(slot), w2 = ld_relaxed_sys(slot + 2), w3 = ld_relaxed_sys(slot + 3);
+            if ((w0 ^ w1 ^ w2 ^ kHdrMagic) == w3) {
+                *sum = w0;
+                *vn = __longlong_as_double((long long)w2);
+                return true;
+            }
+        }
+        if ((++polls & 1023u) == 0 && global_ns() - t0 > 10000000000ull) return false;
+    }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
     constexpr int kBlkBatch = (NT > 512) ? 4 : 16;   // loads of earlier pivots' multipliers issued together (register budget)
@@ -172,6 +212,8 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
     __shared__ long long s_hrow[kMaxRanks];
     __shared__ int s_flag;
     __shared__ long long s_row;
+    __shared__ unsigned long long s_sum[32], s_want;
+    __shared__ double s_vn;
 
     const int nt = (int)blockDim.x, G = (int)gridDim.x, tid = (int)threadIdx.x, cta = (int)blockIdx.x;
     const bool solo = (G == 1);
@@ -290,7 +332,7 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
                 s_flag = wait_seq_gpu(&sy->arrive1, base1 + (nb1 + 1) * (unsigned long long)G) ? 1 : 0;
             }
             __syncthreads();
-            if (!s_flag) { status = LPS_E_PEER; break; }
+            if (!s_flag) { status = LPS_E_PEER; last_r = -101; break; }   // (which wait gave up: reported by lps_solve_end)
             ++nb1;
             best = ArgMinF64{0.0, INT_MAX};
             for (int k = tid; k < G; k += nt) best = argmin_pick(best, ArgMinF64{__ldcg(&P.rblk[k].key), __ldcg(&P.rblk[k].idx)});
@@ -332,6 +374,7 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
             vn = (inv != 1.0) ? __dmul_rn(br, inv) : br;
             double* Vl = Vrow(l, a.rank);
             const size_t peer_off = (size_t)(Vl - P.V);
+            unsigned long long csum = 0ull;
             for (int j = j_first; j < (int)g.ld; j += 2 * G * nt) {
                 double2 y = (j == j_first) ? y_first : *reinterpret_cast<const double2*>(src + j);
                 for (int l0 = 0; l0 < l; l0 += kBlkBatch / 2) {
@@ -358,15 +401,14 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
                 } else {
                     for (int k = 0; k < a.nranks; ++k)
                         if (k != a.rank) *reinterpret_cast<double2*>(xchg_vrow(a.peers[k]) + peer_off + j) = y;
+                    csum += slice_term(y, j);
                 }
             }
             if (a.nranks > 1) {
-                // this CTA's slice is out: one system-scope fence by one thread (the block barrier orders the other
-                // threads' stores before it), then the slice's flag on every rank
-                __syncthreads();
-                if (tid == 0) __threadfence_system();
-                __syncthreads();
-                if (tid < a.nranks) st_relaxed_sys(&a.peers[tid]->rowflag[a.rank][cta], seq);
+                // this CTA's slice is out: its record (checksum, sequence number, the row's right-hand side) follows it to
+                // every rank -- no fence; a receiver whose copy of the slice does not add up yet reads it again
+                csum = block_sum_u64(csum, s_sum);
+                if (tid < a.nranks) rowrec_store(&a.peers[tid]->rowrec[seq & 1][a.rank][cta][0], csum, seq, vn);
             }
         }
         if (a.nranks > 1) {
@@ -388,24 +430,41 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
                 if (row < 0) continue;
                 if (w < 0 || s_hratio[k] < s_hratio[w] || (s_hratio[k] == s_hratio[w] && row < r_g)) { w = k; r_g = row; }
             }
-            if (dead) { status = LPS_E_PEER; break; }
+            if (dead) { status = LPS_E_PEER; last_r = -102; break; }
             if (w < 0) { status = LPS_UNBOUNDED; break; }
-            const int pair_n = g.n / 2;                         // the column pair that holds the right-hand side
-            const int cta_n = (pair_n % (G * nt)) / nt;
-            if (tid == 0) s_flag = (wait_seq(&a.xchg->rowflag[w][cta], seq) && wait_seq(&a.xchg->rowflag[w][cta_n], seq)) ? 1 : 0;
-            __syncthreads();
-            if (!s_flag) { status = LPS_E_PEER; break; }
-            const double* Vw = Vrow(l, w);
-            vn = __ldcg(&Vw[g.n]);
-            for (int j = 2 * (cta * nt + tid); j < (int)g.ld; j += 2 * G * nt) {
-                const double2 y = ldcg2(Vw + j);
-                double2 o = ldcg2(Oc + j);
-                o.x = blk_apply(o.x, uobj, y.x);
-                o.y = blk_apply(o.y, uobj, y.y);
-                stcg2(On + j, o);
-                price_consider(o.x, j, g.n, pb, first_neg);
-                price_consider(o.y, j + 1, g.n, pb, first_neg);
+            if (tid == 0) {
+                unsigned long long want = 0ull;
+                double vnw = 0.0;
+                s_flag = rowrec_wait(&a.xchg->rowrec[seq & 1][w][cta][0], seq, &want, &vnw) ? 1 : 0;
+                s_want = want;
+                s_vn = vnw;
             }
+            __syncthreads();
+            if (!s_flag) { status = LPS_E_PEER; last_r = -103; break; }
+            vn = s_vn;
+            const unsigned long long want = s_want;
+            const double* Vw = Vrow(l, w);
+            for (unsigned int tries = 0;; ++tries) {
+                // objective row over my slice of the winner's row; the slice's checksum on the way (the record may
+                // have overtaken the data: then the sums differ and the slice is read again)
+                unsigned long long got = 0ull;
+                pb = ArgMinF64{0.0, INT_MAX};
+                first_neg = INT_MAX;
+                for (int j = 2 * (cta * nt + tid); j < (int)g.ld; j += 2 * G * nt) {
+                    const double2 y = ldcg2(Vw + j);
+                    got += slice_term(y, j);
+                    double2 o = ldcg2(Oc + j);
+                    o.x = blk_apply(o.x, uobj, y.x);
+                    o.y = blk_apply(o.y, uobj, y.y);
+                    stcg2(On + j, o);
+                    price_consider(o.x, j, g.n, pb, first_neg);
+                    price_consider(o.y, j + 1, g.n, pb, first_neg);
+                }
+                got = block_sum_u64(got, s_sum);
+                if (got == want) break;
+                if (tries > (1u << 22)) { status = LPS_E_PEER; last_r = -104; break; }   // (uniform across the block: several seconds)
+            }
+            if (status != LPS_OK) break;
         }
         for (int i = cta * nt + tid; i < g.m; i += G * nt) {
             double b;
@@ -459,7 +518,7 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
                 s_flag = wait_seq_gpu(&sy->arrive2, base2 + (nb2 + 1) * (unsigned long long)G) ? 1 : 0;
             }
             __syncthreads();
-            if (!s_flag) { status = LPS_E_PEER; break; }
+            if (!s_flag) { status = LPS_E_PEER; last_r = -105; break; }
             ++nb2;
         }
     }
