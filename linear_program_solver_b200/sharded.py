@@ -38,6 +38,13 @@ def shard_rows(m_total: int, rank: int, nranks: int) -> Tuple[int, int]:
     return lo, hi - lo
 
 
+def default_block(m_total: int, nranks: int, ld: int) -> int:
+    """Pivots per block of the blocked loop for a row-sharded tableau: 16 from 1.5 M cells per shard on, else 0 (the
+    rank-1 loop).  The library makes this choice from a handle's OWN rows; shards differ by a row and every rank must
+    run the same loop, so the driver decides from the LARGEST shard and tells every handle."""
+    return 16 if (-(-m_total // nranks) + 1) * ld >= 1_500_000 else 0
+
+
 class ShardedF64Solver:
     def __init__(self, m_total: int, n: int, rank: int = 0, nranks: int = 1, device: Optional[int] = None,
                  group=None, engine_factory: Optional[Callable] = None, burst: Optional[int] = None,
@@ -66,10 +73,7 @@ class ShardedF64Solver:
         self.block = 0
         if self.exchange == "p2p" and hasattr(self.eng, "block_size"):
             if block is None:
-                # the library picks blocks from 1.5 M cells on, by the handle's OWN rows; shards differ by a row, and
-                # every rank must run the same loop: decide from the largest shard, like the burst below
-                ld = int(self.eng.L.lps_grid_ld(self.n))
-                block = 16 if (-(-self.m_total // nranks) + 1) * ld >= 1_500_000 else 0
+                block = default_block(self.m_total, nranks, int(self.eng.L.lps_grid_ld(self.n)))
             self.eng.set_block_size(block)
             self.block = self.eng.block_size()
         # pivots enqueued between two host checks: ~2 ms of device work, between 4 and 256.  The same number on every

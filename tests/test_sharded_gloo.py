@@ -191,6 +191,22 @@ def test_default_burst_is_the_same_on_every_rank_with_uneven_shards():
     assert differing >= 1          # the per-rank formula really did disagree on one of these shapes
 
 
+def test_every_rank_picks_the_same_loop_with_uneven_shards():
+    """The library picks the blocked loop by the handle's OWN rows; the sharded driver decides from the largest shard
+    (`default_block`) so that ranks whose shards straddle the 1.5 M-cell threshold still run the same loop."""
+    from linear_program_solver_b200.sharded import default_block, shard_rows
+    ld = (15998 + 1 + 15) // 16 * 16
+    straddling = 0
+    for world in (2, 3, 8):
+        for m_total in range(100, 1200):
+            own = {16 if (shard_rows(m_total, r, world)[1] + 1) * ld >= 1_500_000 else 0 for r in range(world)}
+            assert default_block(m_total, world, ld) in (0, 16)
+            if len(own) == 2:                              # the per-handle rule disagrees between these ranks ...
+                straddling += 1
+                assert default_block(m_total, world, ld) == 16   # ... the driver's rule gives one answer (the largest shard's)
+    assert straddling >= 3
+
+
 def test_node_lps_shard_by_lp_without_overlap():
     """C5 over several GPUs: contiguous, balanced, exhaustive shares."""
     from linear_program_solver_b200.batch import shard_lps
