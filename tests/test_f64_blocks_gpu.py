@@ -188,6 +188,26 @@ def test_medium_tableaux_take_the_cluster_panel_by_default(m, seed, block):
     e.close()
 
 
+def test_upper_medium_tableau_takes_the_16_cta_cluster_panel_by_default():
+    """5000 x 10000 (400 MB): the panel does not fit 8 CTAs' shared memory any more, the default plan is the cluster of
+    16 (non-portable cluster size); a 40-pivot prefix is byte-identical to the oracle."""
+    from oracle import c_oracle as C
+    from linear_program_solver_b200.engine import F64Engine
+    m = 5000
+    e = F64Engine(m, 2 * m)
+    assert e.block_size() == 16
+    e.fill_dense(1, 1, 9)
+    basis = np.arange(m, 2 * m, dtype=np.int32)
+    st, npiv, trace = e.solve(basis, None, max_pivots=40, trace_cap=64)
+    T = np.empty((m + 1, 2 * m + 1))
+    C.fill_dense(T, m, 0, 1, 1, 9)
+    ob = np.arange(m, 2 * m, dtype=np.int32)
+    ost, ok, otrace = C.solve(T, ob, max_pivots=40)
+    assert (st, npiv) == (ost, ok) and trace.tolist() == otrace.tolist() and basis.tolist() == ob.tolist()
+    assert e.download().tobytes() == T.tobytes()
+    e.close()
+
+
 def test_large_tableau_takes_the_multi_cta_panel_by_default():
     """9000 x 18000 (1.3 GB): the default plan is a multi-CTA panel and the streaming update; a 40-pivot prefix is
     byte-identical to the oracle."""
