@@ -136,3 +136,21 @@ def test_blocked_prefix_stops(max_pivots):
     got, gb = T0.copy(), b0.copy()
     st, trace = blocked_solve(got, gb, 16, max_pivots=max_pivots)
     assert st == wst and [list(t) for t in trace] == wtrace.tolist() and got.tobytes() == want.tobytes()
+
+
+def test_blocked_algebra_reproduces_the_reference_float_runs():
+    """tests/golden/dense_float.json was recorded from the UNMODIFIED reference with its arithmetic type rebound to float
+    (tools/make_golden.py): pivots, basis, objective and basic solution as hex floats.  The blocked loop's algebra has
+    to reproduce them exactly -- not only the C oracle."""
+    from conftest import load_golden
+    for rec in load_golden("dense_float"):
+        m = rec["m"]
+        T = np.array(problems.to_grid(*problems.dense_lp(m, rec["seed"], rec["lo"], rec["hi"])), dtype=np.float64)
+        basis = np.arange(m, 2 * m, dtype=np.int32)
+        for K in (16, 3):
+            got, gb = T.copy(), basis.copy()
+            st, trace = blocked_solve(got, gb, K)
+            assert st == 1 and [list(t) for t in trace] == rec["pivots"], (m, rec["seed"], K)
+            assert gb.tolist() == rec["basis"]
+            assert float(-got[m, 2 * m]).hex() == rec["objective"]
+            assert {str(int(gb[i])): float(got[i, 2 * m]).hex() for i in range(m)} == rec["bfs"]
