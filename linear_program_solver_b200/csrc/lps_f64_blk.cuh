@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(NT, 1) k_blk_panel(BlkPanelArgs a) {
         }
         if (a.nranks > 1) {
             // every CTA reads all candidates and picks the same winner: lowest ratio, then lowest global row
-            // (simplex.py:277); then it needs the winner's row only where it works: its own slice, and the slice
-            // that holds the right-hand side
+            // (simplex.py:277); then it needs the winner's row only where it works -- its own slice -- and the row's
+            // right-hand side, which travels in every slice record
             if (tid < a.nranks) {
                 double hr = 0.0;
                 long long hrow = -1;
