@@ -83,7 +83,9 @@ class ShardedF64Solver:
         est_us = max(4.0, (rows_max + 1) * (self.n + 1) * 16.0 / 5.0e6)
         self.burst = burst or int(max(4, min(256, 2000.0 / est_us)))
         if self.block:
-            blocks = max(1, min(64, int(2000.0 / (est_us + 10.0 * self.block))))
+            # blocks between two host checks: about 8 ms of device work (a check costs a stream synchronisation and a
+            # small copy: tens of microseconds against a block of about 1 ms on an 8-GPU shard of C4)
+            blocks = max(1, min(64, int(8000.0 / (est_us + 20.0 * self.block))))
             self.burst = burst or blocks * self.block
         self._active = False
 
